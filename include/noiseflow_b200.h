@@ -1,0 +1,150 @@
+/*
+ * noiseflow_b200 -- C ABI of the B200-native Noise Flow density / sampling engine.
+ *
+ * Drop-in boundary for the bijector-chain hot path of BorealisAI/noise_flow (pure TF1 Python; it has
+ * no FFI of its own, so each entry point cites the Python interface it replaces; paths are relative
+ * to the reference repository root).  Plain pointers and sizes only: no torch / CUDA types in the
+ * signatures (streams travel as void*).  Unless a function name ends in _host, every data pointer
+ * is a DEVICE pointer owned by the caller; the library owns only the opaque model handle (host
+ * memory -- parameters are passed to each kernel launch by value) and never allocates device
+ * memory behind the caller's back.  The _host entry points take host buffers and own a bounded
+ * staging pool for the duration of the call.
+ *
+ * All functions return 0 on success and a negative nf_status otherwise; nf_last_error() returns a
+ * thread-local human-readable message.  Nothing here throws, exits or prints.  Entry points are
+ * re-entrant: a finalized model may be used concurrently from many host threads (the reference is
+ * driven by 16-32 Python threads sharing one session: train_noise_flow.py:38-47,
+ * train_dncnn_noiseflow.py:195-198); mutation (nf_model_add_*, nf_model_set_*) must not race with
+ * launches on the same handle.
+ *
+ * Tensor layout: NHWC float32, patch = [32][32][4] (sidd patches: train_noise_flow.py:287-288).
+ * Naming follows the reference: "inverse" = data -> latent (likelihood direction),
+ * "forward" = latent -> data (sampling direction)  (noise_flow_model.py:394,430).
+ */
+#ifndef NOISEFLOW_B200_H
+#define NOISEFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NF_ABI_VERSION 1
+
+typedef enum nf_status {
+    NF_OK = 0,
+    NF_ERR_INVALID = -1,      /* bad argument */
+    NF_ERR_UNSUPPORTED = -2,  /* shape / width / capacity outside what the sm_100a kernels are built for */
+    NF_ERR_CUDA = -3,         /* CUDA runtime error (message carries cudaGetErrorString) */
+    NF_ERR_STATE = -4         /* call order (e.g. launch before nf_model_finalize) */
+} nf_status;
+
+typedef struct nf_model nf_model;   /* opaque */
+
+/* Reference-shaped parameters of one AffineCoupling + real_nvp_conv_template(width = 4):
+ * borealisflows/layers.py:251-375 (coupling), :452-498 (template), :586-613 (conv2d),
+ * :651-674 (conv2d_zeros), :378-401 (batch_norm).  Filters use TensorFlow's [kh][kw][in][out]
+ * layout exactly as stored in the checkpoint. */
+typedef struct nf_coupling_weights {
+    const float* l1_w;      /* [3][3][2][4]  model/real_nvp_conv_template*/
+    const float* l1_b;      /* [4] */
+    const float* bn1_mean;  /* [4]  moving statistics (is_training == False path, layers.py:400) */
+    const float* bn1_var;   /* [4] */
+    const float* l2_w;      /* [1][1][4][4] */
+    const float* l2_b;      /* [4] */
+    const float* bn2_mean;  /* [4] */
+    const float* bn2_var;   /* [4] */
+    const float* last_w;    /* [3][3][5][4]  (input channel 4 = edge indicator, layers.py:555-583) */
+    const float* last_b;    /* [4] */
+    const float* last_logs; /* [4]  output is multiplied by exp(3 * logs), layers.py:671-673 */
+    float rescaling_scale;  /* level0/bijector{i}/rescaling_scale0, layers.py:271-273 */
+    float bn_eps;           /* 1e-4, layers.py:378 */
+} nf_coupling_weights;
+
+/* Scale-layer kinds: every AffineCouplingSdn* / Gain* / CamSdn template reduces to one of the two
+ * (borealisflows/noise_flow_layers/*.py, cond_utils.py); the host computes the per-(camera, ISO)
+ * scalars. */
+#define NF_SCALE_SDN 1   /* scale = sqrt(a*y + b); table row = {a, b}     e.g. AffineCouplingSdnEx5.py */
+#define NF_SCALE_GAIN 2  /* scale = g;             table row = {g, unused} e.g. AffineCouplingGainEx4.py */
+
+/* ---- library ----------------------------------------------------------------------------------- */
+int nf_abi_version(void);
+const char* nf_last_error(void);
+/* Fills in the SM count / max opt-in shared memory of the current device; negative if no usable GPU. */
+int nf_device_info(int* sm_count, int* max_smem_optin, int* cc_major, int* cc_minor);
+
+/* ---- model construction: mirrors NoiseFlow.noise_flow_arch (noise_flow_model.py:71-235) -------- */
+/* x_shape must be 32x32x4 and width 4 (the shipped configuration); anything else -> NF_ERR_UNSUPPORTED. */
+int nf_model_create(int height, int width, int channels, int net_width, nf_model** out);
+int nf_model_destroy(nf_model* m);
+/* Conv2d1x1 (layers.py:74-145, bias=False): A / A_inv are [in][out] row-major as produced by
+ * matrix_param_lu (matrix_param.py:130-138); log_abs_det = sum(log_S). */
+int nf_model_add_conv1x1(nf_model* m, const float* A, const float* A_inv, float log_abs_det);
+/* tfb.Permute(permutation) (noise_flow_model.py:80-84): forward y[..., i] = x[..., perm[i]]. */
+int nf_model_add_permute(nf_model* m, const int32_t* perm);
+int nf_model_add_affine_coupling(nf_model* m, const nf_coupling_weights* w);
+/* table: [n_rows][2] floats; logdet_full_sum = 0 reproduces the Gain/GainEx1/GainEx3 quirk whose
+ * log-det is log(scale) instead of 4096*log(scale) (AffineCouplingGain.py:86,96,111,125). */
+int nf_model_add_scale(nf_model* m, int kind, int logdet_full_sum, const float* table, int n_rows);
+int nf_model_finalize(nf_model* m);
+int nf_model_num_layers(const nf_model* m);
+/* In-place parameter updates of layer `layer` (index in add order), e.g. after an optimizer step. */
+int nf_model_set_conv1x1(nf_model* m, int layer, const float* A, const float* A_inv, float log_abs_det);
+int nf_model_set_affine_coupling(nf_model* m, int layer, const nf_coupling_weights* w);
+int nf_model_set_scale(nf_model* m, int layer, const float* table, int n_rows);
+/* Launch tuning: resident patches (warps) per CTA in [1, 12] and CTA count (0 = one per SM). */
+int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas);
+
+/* ---- hot path (device pointers) ---------------------------------------------------------------- */
+/* rows: per-patch conditioning-table row (int32, device) or NULL -> default_row for every patch.
+ * The reference feeds ONE (iso, cam) per minibatch (sidd/MiniBatchSampler.py:60-64). */
+
+/* NoiseFlow._loss (noise_flow_model.py:458-480): nll[n] = -(sum ldj + log N(z; 0, I)),
+ * sdz[n] = sqrt(var(z_n)) (the reference returns their batch mean: use nf_reduce_sums),
+ * z (optional) = latent.  x, y: [n][32][32][4]. */
+int nf_log_prob(const nf_model* m, const float* x, const float* y, const int32_t* rows, int32_t default_row,
+                int64_t n, float* nll, float* sdz, float* z, void* stream);
+/* NoiseFlow.inverse (noise_flow_model.py:394-428): z and per-patch objective increment logdet[n]. */
+int nf_inverse(const nf_model* m, const float* x, const float* y, const int32_t* rows, int32_t default_row,
+               int64_t n, float* z, float* logdet, void* stream);
+/* NoiseFlow.forward (noise_flow_model.py:430-447): x = chain^-1(z); logdet optional. */
+int nf_forward(const nf_model* m, const float* z, const float* y, const int32_t* rows, int32_t default_row,
+               int64_t n, float* x, float* logdet, void* stream);
+/* NoiseFlow.sample (noise_flow_model.py:449-456,499-504): z = eps * temp, x = forward(z).
+ * eps == NULL draws eps in-kernel: Philox4x32-10, key = seed, counter = (pixel, patch, offset),
+ * Box-Muller; patch index = patch_base + position in this call. */
+int nf_sample(const nf_model* m, const float* y, const int32_t* rows, int32_t default_row, int64_t n,
+              float temp, const float* eps, uint64_t seed, uint64_t offset, uint64_t patch_base,
+              float* x, void* stream);
+/* Per-bijector access (_inverse_and_log_det_jacobian / _forward_and_log_det_jacobian of the
+ * bijectors first..last-1 in add order; layers.py:132-140,333-375 and noise_flow_layers/*).
+ * direction: 0 = inverse, 1 = forward. `in` and `out` may alias. */
+int nf_run_layers(const nf_model* m, int first, int last, int direction, const float* in, const float* y,
+                  const int32_t* rows, int32_t default_row, int64_t n, float* out, float* logdet, void* stream);
+/* tf.reduce_mean pieces (noise_flow_model.py:478,484), deterministic fp64:
+ * sums[0] = sum nll, sums[1] = sum sdz, sums[2] = n  (device double[3]; either input may be NULL). */
+int nf_reduce_sums(const float* nll, const float* sdz, int64_t n, double* sums, void* stream);
+
+/* squeeze2d / unsqueeze2d (borealisflows/utils.py:30-86): bit-exact index permutation.
+ * squeeze_type: 0 = 'chessboard' (also the unknown-type fallback), 1 = 'patch'.
+ * H, W, C always describe the UN-squeezed tensor [n][H][W][C]. */
+int nf_squeeze2d(const float* x, int64_t n, int H, int W, int C, int factor, int squeeze_type, float* out, void* stream);
+int nf_unsqueeze2d(const float* x, int64_t n, int H, int W, int C, int factor, int squeeze_type, float* out, void* stream);
+
+/* ---- host-buffer entry points (what NoiseFlowWrapper.sample_noise_nf / sess.run replace) -------- */
+/* Host pointers; copies are chunked and double-buffered on two internal streams.  Buffers from
+ * nf_host_alloc (pinned) overlap copies with compute; pageable memory works but serialises.
+ * sums (host double[3], optional) as nf_reduce_sums. rows_host may be NULL. */
+int nf_log_prob_host(const nf_model* m, const float* x_host, const float* y_host, const int32_t* rows_host,
+                     int32_t default_row, int64_t n, float* nll_host, float* sdz_host, float* z_host, double* sums_host);
+int nf_sample_host(const nf_model* m, const float* y_host, const int32_t* rows_host, int32_t default_row, int64_t n,
+                   float temp, const float* eps_host, uint64_t seed, uint64_t offset, float* x_host);
+int nf_host_alloc(void** ptr, size_t bytes);   /* cudaHostAlloc (pinned) */
+int nf_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOISEFLOW_B200_H */

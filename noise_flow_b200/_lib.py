@@ -1,0 +1,89 @@
+"""ctypes binding of the C-ABI in ``include/noiseflow_b200.h``.
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised.  ctypes releases the GIL around every call, which preserves the reference's threading contract
+(many Python threads driving one model: ``train_noise_flow.py:38-47``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnoiseflow_b200.so")
+
+NF_OK = 0
+c_float_p = C.POINTER(C.c_float)
+
+
+class NfCouplingWeights(C.Structure):
+    _fields_ = [(n, c_float_p) for n in ("l1_w", "l1_b", "bn1_mean", "bn1_var", "l2_w", "l2_b", "bn2_mean",
+                                          "bn2_var", "last_w", "last_b", "last_logs")] + \
+               [("rescaling_scale", C.c_float), ("bn_eps", C.c_float)]
+
+
+# name -> (restype, argtypes); every symbol the header declares is listed here (tests check both ways)
+SIGNATURES = {
+    "nf_abi_version": (C.c_int, []),
+    "nf_last_error": (C.c_char_p, []),
+    "nf_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
+    "nf_model_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "nf_model_destroy": (C.c_int, [C.c_void_p]),
+    "nf_model_add_conv1x1": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_float]),
+    "nf_model_add_permute": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "nf_model_add_affine_coupling": (C.c_int, [C.c_void_p, C.POINTER(NfCouplingWeights)]),
+    "nf_model_add_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int]),
+    "nf_model_finalize": (C.c_int, [C.c_void_p]),
+    "nf_model_num_layers": (C.c_int, [C.c_void_p]),
+    "nf_model_set_conv1x1": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p, C.c_float]),
+    "nf_model_set_affine_coupling": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(NfCouplingWeights)]),
+    "nf_model_set_scale": (C.c_int, [C.c_void_p, C.c_int, c_float_p, C.c_int]),
+    "nf_model_set_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "nf_log_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nf_inverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nf_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nf_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p,
+                            C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "nf_run_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nf_reduce_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "nf_squeeze2d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nf_unsqueeze2d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nf_log_prob_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nf_sample_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p,
+                                 C.c_uint64, C.c_uint64, C.c_void_p]),
+    "nf_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "nf_host_free": (C.c_int, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load ``libnoiseflow_b200.so`` (once) and declare every prototype.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "%s is missing: the CUDA extension is not built (run `python -m noise_flow_b200.build`); "
+            "there is no CPU fallback by design" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError here = header / library drift
+        fn.restype = res
+        fn.argtypes = args
+    if lib.nf_abi_version() != 1:
+        raise RuntimeError("libnoiseflow_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != NF_OK:
+        msg = load().nf_last_error()
+        raise RuntimeError("noiseflow_b200 %s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -1,0 +1,598 @@
+// C-ABI of the B200 Noise Flow engine (declared in include/noiseflow_b200.h): model handle, host-side
+// parameter folding (reference-shaped weights -> kernel-ready NfModelParams), launches, host-buffer
+// pipeline.  No torch types, no exceptions across the boundary, no global mutable state except the
+// thread-local error string.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/noiseflow_b200.h"
+#include "nf_kernels.h"
+#include "nf_params.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define NF_CUDA(call)                                                                                 \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) return fail(NF_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));   \
+    } while (0)
+
+enum LayerKind { L_CONV1X1 = 1, L_PERMUTE = 2, L_COUPLING = 3, L_SCALE = 4 };
+
+struct Layer {
+    int kind = 0;
+    // conv1x1 / permute: mixing matrices as the kernel wants them, [o][i]
+    float a[4][4] = {};
+    float ainv[4][4] = {};
+    double log_abs_det = 0.0;   // per pixel (conv1x1), 0 for permutations
+    // coupling (folded)
+    NfCouplingP cp = {};
+    // scale
+    int scale_kind = 0, full_sum = 1, n_rows = 0;
+    float table[NF_MAX_ROWS][4] = {};
+};
+
+}  // namespace
+
+struct nf_model {
+    std::vector<Layer> layers;
+    bool finalized = false;
+    int warps_per_cta = NF_MAX_WARPS_PER_CTA;
+    int num_ctas = 0;
+    int sm_count = 0;
+    NfModelParams full = {};     // fused program of the whole chain
+    float full_ldj_const = 0.f;
+    std::mutex pool_mu;          // guards the _host staging pool
+    struct Staging {
+        float *x = nullptr, *y = nullptr, *z = nullptr, *nll = nullptr, *sdz = nullptr;
+        int32_t* rows = nullptr;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+    } st[2];
+    double* d_sums = nullptr;
+    int64_t chunk = 0;
+};
+
+namespace {
+
+// ---- folding: reference-shaped coupling weights -> NfCouplingP (double precision on the host) -----
+// real_nvp_conv_template, layers.py:469-494 with batch_norm in moving-statistics mode (:400):
+//   h1 = relu((conv(x0;W1)+b1 - m1)/sqrt(v1+eps))  ->  W1' = W1*s1, b1' = (b1-m1)*s1
+//   h2 = relu((h1.W2+b2 - m2)/sqrt(v2+eps))        ->  W2' = W2*s2, b2' = (b2-m2)*s2
+//   h3 = (conv_valid([pad(h2), ring]; W3) + b3) * exp(3*logs)
+//      -> W3' = W3[:,:,:4,:]*e, b3'[row class][col class] = (b3 + sum of ring taps)*e
+int fold_coupling(const nf_coupling_weights* w, NfCouplingP* out) {
+    if (!w || !w->l1_w || !w->l1_b || !w->bn1_mean || !w->bn1_var || !w->l2_w || !w->l2_b || !w->bn2_mean ||
+        !w->bn2_var || !w->last_w || !w->last_b || !w->last_logs)
+        return fail(NF_ERR_INVALID, "nf_coupling_weights: null pointer");
+    const double eps = w->bn_eps;
+    double s1[4], s2[4], e[4];
+    for (int o = 0; o < 4; ++o) {
+        if (!(w->bn1_var[o] + eps > 0.0) || !(w->bn2_var[o] + eps > 0.0))
+            return fail(NF_ERR_INVALID, "batch-norm variance + eps must be positive");
+        s1[o] = 1.0 / sqrt((double)w->bn1_var[o] + eps);
+        s2[o] = 1.0 / sqrt((double)w->bn2_var[o] + eps);
+        e[o] = exp(3.0 * (double)w->last_logs[o]);
+    }
+    for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx)
+            for (int o = 0; o < 4; ++o) {
+                for (int i = 0; i < 2; ++i)
+                    out->w1[dy][dx][o][i] = (float)((double)w->l1_w[((dy * 3 + dx) * 2 + i) * 4 + o] * s1[o]);
+                for (int i = 0; i < 4; ++i)
+                    out->w3[dy][dx][o][i] = (float)((double)w->last_w[((dy * 3 + dx) * 5 + i) * 4 + o] * e[o]);
+            }
+    for (int o = 0; o < 4; ++o) {
+        out->b1[o] = (float)(((double)w->l1_b[o] - (double)w->bn1_mean[o]) * s1[o]);
+        out->b2[o] = (float)(((double)w->l2_b[o] - (double)w->bn2_mean[o]) * s2[o]);
+        for (int i = 0; i < 4; ++i) out->w2[o][i] = (float)((double)w->l2_w[i * 4 + o] * s2[o]);
+    }
+    // edge indicator (layers.py:567-571): 1 on the one-pixel ring of the 34x34 padded map.  Output
+    // pixel (r,c) sees padded positions (r+dy, c+dx): on the ring iff r+dy in {0,33} or c+dx in {0,33}.
+    for (int rc = 0; rc < 3; ++rc)
+        for (int cc = 0; cc < 3; ++cc)
+            for (int o = 0; o < 4; ++o) {
+                double acc = w->last_b[o];
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const bool ring = (rc == 0 && dy == 0) || (rc == 2 && dy == 2) || (cc == 0 && dx == 0) ||
+                                          (cc == 2 && dx == 2);
+                        if (ring) acc += (double)w->last_w[((dy * 3 + dx) * 5 + 4) * 4 + o];
+                    }
+                out->b3[rc][cc][o] = (float)(acc * e[o]);
+            }
+    out->scale = w->rescaling_scale;
+    return NF_OK;
+}
+
+void identity4(float m[4][4]) {
+    for (int o = 0; o < 4; ++o)
+        for (int i = 0; i < 4; ++i) m[o][i] = o == i ? 1.f : 0.f;
+}
+
+int set_scale_table(Layer& L, const float* table, int n_rows) {
+    if (!table || n_rows < 1 || n_rows > NF_MAX_ROWS)
+        return fail(NF_ERR_INVALID, "scale table: need 1..%d rows", NF_MAX_ROWS);
+    L.n_rows = n_rows;
+    memset(L.table, 0, sizeof(L.table));
+    for (int r = 0; r < n_rows; ++r) {
+        const double p0 = table[2 * r], p1 = table[2 * r + 1];
+        if (L.scale_kind == NF_SCALE_SDN) {
+            L.table[r][0] = (float)p0;
+            L.table[r][1] = (float)p1;
+        } else {
+            // scale = g: inverse x /= g, log-det -sum log g (AffineCouplingGainEx4.py:115-124);
+            // quirk variants return -log g without the sum over the 4096 dimensions.
+            L.table[r][0] = (float)p0;
+            L.table[r][1] = (float)(1.0 / p0);
+            L.table[r][2] = (float)(-(L.full_sum ? (double)NF_DIMS : 1.0) * log(p0));
+        }
+    }
+    return NF_OK;
+}
+
+// Build the kernel program for the bijectors [first, last): a conv1x1 / permutation that is
+// immediately followed (data->latent order) by a coupling inside the range is fused into it.
+int build_program(const nf_model* m, int first, int last, NfModelParams* mp, float* ldj_const) {
+    memset(mp, 0, sizeof(*mp));
+    double ldj = 0.0;
+    int n_cp = 0, n_mix = 0, n_sc = 0, n_ops = 0, n_rows = 0;
+    for (int l = first; l < last; ++l) {
+        const Layer& L = m->layers[l];
+        if (n_ops >= NF_MAX_LAYERS) return fail(NF_ERR_UNSUPPORTED, "more than %d kernel ops", NF_MAX_LAYERS);
+        if (L.kind == L_CONV1X1 || L.kind == L_PERMUTE) {
+            ldj += L.log_abs_det * (double)NF_PIXELS;   // layers.py:129-130
+            const bool fuse = (l + 1 < last) && m->layers[l + 1].kind == L_COUPLING;
+            if (fuse) continue;   // picked up by the coupling below
+            if (n_mix >= NF_MAX_MIX) return fail(NF_ERR_UNSUPPORTED, "more than %d stand-alone 1x1 layers", NF_MAX_MIX);
+            memcpy(mp->mix[n_mix].a, L.a, sizeof(L.a));
+            memcpy(mp->mix[n_mix].ainv, L.ainv, sizeof(L.ainv));
+            mp->op[n_ops] = NF_KOP_MIX;
+            mp->slot[n_ops++] = (uint8_t)n_mix++;
+        } else if (L.kind == L_COUPLING) {
+            if (n_cp >= NF_MAX_COUPLINGS) return fail(NF_ERR_UNSUPPORTED, "more than %d couplings", NF_MAX_COUPLINGS);
+            NfCouplingP& C = mp->cp[n_cp];
+            C = L.cp;
+            const bool fused = l > first && (m->layers[l - 1].kind == L_CONV1X1 || m->layers[l - 1].kind == L_PERMUTE);
+            if (fused) {
+                memcpy(C.a, m->layers[l - 1].a, sizeof(C.a));
+                memcpy(C.ainv, m->layers[l - 1].ainv, sizeof(C.ainv));
+                C.has_mix = 1;
+            } else {
+                identity4(C.a);
+                identity4(C.ainv);
+                C.has_mix = 0;
+            }
+            mp->op[n_ops] = NF_KOP_COUPLING;
+            mp->slot[n_ops++] = (uint8_t)n_cp++;
+        } else if (L.kind == L_SCALE) {
+            if (n_sc >= NF_MAX_SCALE) return fail(NF_ERR_UNSUPPORTED, "more than %d scale layers", NF_MAX_SCALE);
+            memcpy(mp->sc[n_sc].t, L.table, sizeof(L.table));
+            if (L.n_rows > n_rows) n_rows = L.n_rows;
+            mp->op[n_ops] = L.scale_kind == NF_SCALE_SDN ? NF_KOP_SDN : NF_KOP_GAIN;
+            mp->slot[n_ops++] = (uint8_t)n_sc++;
+        }
+    }
+    mp->n_layers = n_ops;
+    mp->n_rows = n_rows;
+    *ldj_const = (float)ldj;
+    return NF_OK;
+}
+
+bool range_has_sdn(const nf_model* m, int first, int last) {
+    for (int l = first; l < last; ++l)
+        if (m->layers[l].kind == L_SCALE && m->layers[l].scale_kind == NF_SCALE_SDN) return true;
+    return false;
+}
+
+int check_ready(const nf_model* m) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    if (!m->finalized) return fail(NF_ERR_STATE, "model not finalized (call nf_model_finalize)");
+    return NF_OK;
+}
+
+int num_ctas_for(const nf_model* m) { return m->num_ctas > 0 ? m->num_ctas : m->sm_count; }
+
+int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainArgs& a, cudaStream_t stream) {
+    if (a.n < 0) return fail(NF_ERR_INVALID, "negative patch count");
+    if (a.n == 0) return NF_OK;
+    if (!a.y && range_has_sdn(m, first, last)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
+    if (a.default_row < 0 || a.default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
+    cudaError_t e;
+    if (first == 0 && last == (int)m->layers.size()) {
+        a.first_layer = 0;
+        a.last_layer = m->full.n_layers;
+        a.ldj_const = m->full_ldj_const;
+        if (a.in && nf::program_is_scale_only(m->full, 0, m->full.n_layers))
+            e = nf::launch_scale_stream(m->full, a, inverse, m->sm_count, stream);   // HBM-bound streaming path
+        else
+            e = nf::launch_chain(m->full, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
+    } else {
+        NfModelParams mp;
+        float ldj = 0.f;
+        int rc = build_program(m, first, last, &mp, &ldj);
+        if (rc) return rc;
+        a.first_layer = 0;
+        a.last_layer = mp.n_layers;
+        a.ldj_const = ldj;
+        if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
+            e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);
+        else
+            e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
+    }
+    if (e != cudaSuccess) return fail(NF_ERR_CUDA, "chain kernel launch: %s", cudaGetErrorString(e));
+    return NF_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int nf_abi_version(void) { return NF_ABI_VERSION; }
+const char* nf_last_error(void) { return g_err; }
+
+int nf_device_info(int* sm_count, int* max_smem_optin, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    NF_CUDA(cudaGetDevice(&dev));
+    int v = 0;
+    NF_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    if (sm_count) *sm_count = v;
+    NF_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (max_smem_optin) *max_smem_optin = v;
+    NF_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc_major) *cc_major = v;
+    NF_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev));
+    if (cc_minor) *cc_minor = v;
+    return NF_OK;
+}
+
+int nf_model_create(int height, int width, int channels, int net_width, nf_model** out) {
+    if (!out) return fail(NF_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (height != NF_PATCH_H || width != NF_PATCH_W || channels != NF_PATCH_C)
+        return fail(NF_ERR_UNSUPPORTED, "kernels are built for %dx%dx%d patches, got %dx%dx%d", NF_PATCH_H, NF_PATCH_W,
+                    NF_PATCH_C, height, width, channels);
+    if (net_width != 4) return fail(NF_ERR_UNSUPPORTED, "kernels are built for coupling-net width 4, got %d", net_width);
+    nf_model* m = new (std::nothrow) nf_model();
+    if (!m) return fail(NF_ERR_INVALID, "out of host memory");
+    *out = m;
+    return NF_OK;
+}
+
+int nf_model_destroy(nf_model* m) {
+    if (!m) return NF_OK;
+    for (auto& s : m->st) {
+        if (s.x) cudaFree(s.x);
+        if (s.y) cudaFree(s.y);
+        if (s.z) cudaFree(s.z);
+        if (s.nll) cudaFree(s.nll);
+        if (s.sdz) cudaFree(s.sdz);
+        if (s.rows) cudaFree(s.rows);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (m->d_sums) cudaFree(m->d_sums);
+    delete m;
+    return NF_OK;
+}
+
+static int fill_conv1x1(Layer& L, const float* A, const float* A_inv, float log_abs_det) {
+    if (!A || !A_inv) return fail(NF_ERR_INVALID, "A / A_inv is null");
+    L.kind = L_CONV1X1;
+    for (int o = 0; o < 4; ++o)
+        for (int i = 0; i < 4; ++i) {
+            L.a[o][i] = A[i * 4 + o];          // inverse: x_out[o] = sum_i y[i] * A[i][o]   (layers.py:118-119)
+            L.ainv[o][i] = A_inv[i * 4 + o];   // forward: uses A_inv                         (layers.py:113-114)
+        }
+    L.log_abs_det = log_abs_det;
+    return NF_OK;
+}
+
+int nf_model_add_conv1x1(nf_model* m, const float* A, const float* A_inv, float log_abs_det) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    Layer L;
+    int rc = fill_conv1x1(L, A, A_inv, log_abs_det);
+    if (rc) return rc;
+    m->layers.push_back(L);
+    m->finalized = false;
+    return NF_OK;
+}
+
+int nf_model_add_permute(nf_model* m, const int32_t* perm) {
+    if (!m || !perm) return fail(NF_ERR_INVALID, "null argument");
+    Layer L;
+    L.kind = L_PERMUTE;
+    bool seen[4] = {false, false, false, false};
+    for (int i = 0; i < 4; ++i) {
+        if (perm[i] < 0 || perm[i] > 3 || seen[perm[i]]) return fail(NF_ERR_INVALID, "perm is not a permutation of 0..3");
+        seen[perm[i]] = true;
+    }
+    // forward y[i] = x[perm[i]]  -> ainv[o=i][in=perm[i]] = 1 ; inverse x[perm[i]] = y[i] -> a[o=perm[i]][in=i] = 1
+    memset(L.a, 0, sizeof(L.a));
+    memset(L.ainv, 0, sizeof(L.ainv));
+    for (int i = 0; i < 4; ++i) {
+        L.ainv[i][perm[i]] = 1.f;
+        L.a[perm[i]][i] = 1.f;
+    }
+    L.log_abs_det = 0.0;
+    m->layers.push_back(L);
+    m->finalized = false;
+    return NF_OK;
+}
+
+int nf_model_add_affine_coupling(nf_model* m, const nf_coupling_weights* w) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    Layer L;
+    L.kind = L_COUPLING;
+    int rc = fold_coupling(w, &L.cp);
+    if (rc) return rc;
+    m->layers.push_back(L);
+    m->finalized = false;
+    return NF_OK;
+}
+
+int nf_model_add_scale(nf_model* m, int kind, int logdet_full_sum, const float* table, int n_rows) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    if (kind != NF_SCALE_SDN && kind != NF_SCALE_GAIN) return fail(NF_ERR_INVALID, "unknown scale kind %d", kind);
+    Layer L;
+    L.kind = L_SCALE;
+    L.scale_kind = kind;
+    L.full_sum = logdet_full_sum ? 1 : 0;
+    int rc = set_scale_table(L, table, n_rows);
+    if (rc) return rc;
+    m->layers.push_back(L);
+    m->finalized = false;
+    return NF_OK;
+}
+
+int nf_model_finalize(nf_model* m) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    if (m->layers.empty()) return fail(NF_ERR_STATE, "model has no layers");
+    int rc = build_program(m, 0, (int)m->layers.size(), &m->full, &m->full_ldj_const);
+    if (rc) return rc;
+    if (m->sm_count == 0) {
+        int sms = 0;
+        rc = nf_device_info(&sms, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        m->sm_count = sms;
+    }
+    m->finalized = true;
+    return NF_OK;
+}
+
+int nf_model_num_layers(const nf_model* m) { return m ? (int)m->layers.size() : fail(NF_ERR_INVALID, "null model"); }
+
+static int refinalize(nf_model* m) { return m->finalized ? nf_model_finalize(m) : NF_OK; }
+
+int nf_model_set_conv1x1(nf_model* m, int layer, const float* A, const float* A_inv, float log_abs_det) {
+    if (!m || layer < 0 || layer >= (int)m->layers.size() || m->layers[layer].kind != L_CONV1X1)
+        return fail(NF_ERR_INVALID, "layer %d is not a conv1x1", layer);
+    int rc = fill_conv1x1(m->layers[layer], A, A_inv, log_abs_det);
+    return rc ? rc : refinalize(m);
+}
+
+int nf_model_set_affine_coupling(nf_model* m, int layer, const nf_coupling_weights* w) {
+    if (!m || layer < 0 || layer >= (int)m->layers.size() || m->layers[layer].kind != L_COUPLING)
+        return fail(NF_ERR_INVALID, "layer %d is not an affine coupling", layer);
+    int rc = fold_coupling(w, &m->layers[layer].cp);
+    return rc ? rc : refinalize(m);
+}
+
+int nf_model_set_scale(nf_model* m, int layer, const float* table, int n_rows) {
+    if (!m || layer < 0 || layer >= (int)m->layers.size() || m->layers[layer].kind != L_SCALE)
+        return fail(NF_ERR_INVALID, "layer %d is not a scale layer", layer);
+    int rc = set_scale_table(m->layers[layer], table, n_rows);
+    return rc ? rc : refinalize(m);
+}
+
+int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    if (warps_per_cta < 1 || warps_per_cta > NF_MAX_WARPS_PER_CTA)
+        return fail(NF_ERR_INVALID, "warps_per_cta must be in [1, %d]", NF_MAX_WARPS_PER_CTA);
+    if (num_ctas < 0) return fail(NF_ERR_INVALID, "num_ctas must be >= 0");
+    m->warps_per_cta = warps_per_cta;
+    m->num_ctas = num_ctas;
+    return NF_OK;
+}
+
+// ---- hot path -------------------------------------------------------------------------------------
+int nf_log_prob(const nf_model* m, const float* x, const float* y, const int32_t* rows, int32_t default_row, int64_t n,
+                float* nll, float* sdz, float* z, void* stream) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (!x || !nll) return fail(NF_ERR_INVALID, "x and nll are required");
+    NfChainArgs a = {};
+    a.in = x; a.y = y; a.rows = rows; a.out = z; a.nll = nll; a.sdz = sdz; a.n = n; a.default_row = default_row; a.temp = 1.f;
+    return launch_range(m, 0, (int)m->layers.size(), true, a, (cudaStream_t)stream);
+}
+
+int nf_inverse(const nf_model* m, const float* x, const float* y, const int32_t* rows, int32_t default_row, int64_t n,
+               float* z, float* logdet, void* stream) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (!x || !z) return fail(NF_ERR_INVALID, "x and z are required");
+    NfChainArgs a = {};
+    a.in = x; a.y = y; a.rows = rows; a.out = z; a.logdet = logdet; a.n = n; a.default_row = default_row; a.temp = 1.f;
+    return launch_range(m, 0, (int)m->layers.size(), true, a, (cudaStream_t)stream);
+}
+
+int nf_forward(const nf_model* m, const float* z, const float* y, const int32_t* rows, int32_t default_row, int64_t n,
+               float* x, float* logdet, void* stream) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (!z || !x) return fail(NF_ERR_INVALID, "z and x are required");
+    NfChainArgs a = {};
+    a.in = z; a.y = y; a.rows = rows; a.out = x; a.logdet = logdet; a.n = n; a.default_row = default_row; a.temp = 1.f;
+    return launch_range(m, 0, (int)m->layers.size(), false, a, (cudaStream_t)stream);
+}
+
+int nf_sample(const nf_model* m, const float* y, const int32_t* rows, int32_t default_row, int64_t n, float temp,
+              const float* eps, uint64_t seed, uint64_t offset, uint64_t patch_base, float* x, void* stream) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (!x) return fail(NF_ERR_INVALID, "x is required");
+    NfChainArgs a = {};
+    a.in = eps; a.y = y; a.rows = rows; a.out = x; a.n = n; a.default_row = default_row; a.temp = temp;
+    a.seed = seed; a.offset = offset; a.patch_base = patch_base;
+    return launch_range(m, 0, (int)m->layers.size(), false, a, (cudaStream_t)stream);
+}
+
+int nf_run_layers(const nf_model* m, int first, int last, int direction, const float* in, const float* y,
+                  const int32_t* rows, int32_t default_row, int64_t n, float* out, float* logdet, void* stream) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (first < 0 || last > (int)m->layers.size() || first >= last) return fail(NF_ERR_INVALID, "bad layer range [%d,%d)", first, last);
+    if (!in || !out) return fail(NF_ERR_INVALID, "in and out are required");
+    if (direction != 0 && direction != 1) return fail(NF_ERR_INVALID, "direction must be 0 (inverse) or 1 (forward)");
+    NfChainArgs a = {};
+    a.in = in; a.y = y; a.rows = rows; a.out = out; a.logdet = logdet; a.n = n; a.default_row = default_row; a.temp = 1.f;
+    return launch_range(m, first, last, direction == 0, a, (cudaStream_t)stream);
+}
+
+int nf_reduce_sums(const float* nll, const float* sdz, int64_t n, double* sums, void* stream) {
+    if (!sums || n < 0) return fail(NF_ERR_INVALID, "sums is null or n < 0");
+    cudaError_t e = nf::launch_reduce(nll, sdz, n, sums, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(NF_ERR_CUDA, "reduce kernel launch: %s", cudaGetErrorString(e));
+    return NF_OK;
+}
+
+static int squeeze_common(const float* x, int64_t n, int H, int W, int C, int factor, int type, float* out, void* stream, int inv) {
+    if (!x || !out || n < 0) return fail(NF_ERR_INVALID, "null pointer or n < 0");
+    if (factor < 1 || H < 1 || W < 1 || C < 1 || H % factor || W % factor) return fail(NF_ERR_INVALID, "H and W must be multiples of factor");
+    if (x == out && factor != 1) return fail(NF_ERR_INVALID, "squeeze cannot run in place");
+    if (factor == 1) {   // identity (utils.py:32-33,65-66)
+        if (x != out) NF_CUDA(cudaMemcpyAsync(out, x, (size_t)n * H * W * C * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return NF_OK;
+    }
+    cudaError_t e = nf::launch_squeeze(x, out, n, H, W, C, factor, type == 1 ? 1 : 0, inv, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(NF_ERR_CUDA, "squeeze kernel launch: %s", cudaGetErrorString(e));
+    return NF_OK;
+}
+int nf_squeeze2d(const float* x, int64_t n, int H, int W, int C, int factor, int squeeze_type, float* out, void* stream) {
+    return squeeze_common(x, n, H, W, C, factor, squeeze_type, out, stream, 0);
+}
+int nf_unsqueeze2d(const float* x, int64_t n, int H, int W, int C, int factor, int squeeze_type, float* out, void* stream) {
+    return squeeze_common(x, n, H, W, C, factor, squeeze_type, out, stream, 1);
+}
+
+// ---- host-buffer pipeline ---------------------------------------------------------------------------
+static const int64_t kChunk = 4096;   // patches per staged chunk: 64 MiB per tensor
+
+static int ensure_staging(nf_model* m) {
+    if (m->chunk) return NF_OK;
+    const size_t pb = (size_t)NF_DIMS * sizeof(float);
+    for (auto& s : m->st) {
+        NF_CUDA(cudaMalloc(&s.x, kChunk * pb));
+        NF_CUDA(cudaMalloc(&s.y, kChunk * pb));
+        NF_CUDA(cudaMalloc(&s.z, kChunk * pb));
+        NF_CUDA(cudaMalloc(&s.nll, kChunk * sizeof(float)));
+        NF_CUDA(cudaMalloc(&s.sdz, kChunk * sizeof(float)));
+        NF_CUDA(cudaMalloc(&s.rows, kChunk * sizeof(int32_t)));
+        NF_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        NF_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    NF_CUDA(cudaMalloc(&m->d_sums, 3 * sizeof(double)));
+    m->chunk = kChunk;
+    return NF_OK;
+}
+
+int nf_log_prob_host(const nf_model* cm, const float* x_host, const float* y_host, const int32_t* rows_host,
+                     int32_t default_row, int64_t n, float* nll_host, float* sdz_host, float* z_host, double* sums_host) {
+    int rc = check_ready(cm);
+    if (rc) return rc;
+    if (!x_host || n < 0) return fail(NF_ERR_INVALID, "x_host is required");
+    if (!nll_host && !sums_host) return fail(NF_ERR_INVALID, "nll_host or sums_host is required");
+    nf_model* m = const_cast<nf_model*>(cm);
+    std::lock_guard<std::mutex> lock(m->pool_mu);   // one host pipeline per handle at a time
+    rc = ensure_staging(m);
+    if (rc) return rc;
+    const size_t pb = (size_t)NF_DIMS * sizeof(float);
+    double tot[3] = {0.0, 0.0, 0.0};
+    std::vector<float> tmp_nll, tmp_sdz;
+    if (sums_host && !nll_host) tmp_nll.resize((size_t)n);
+    if (sums_host && !sdz_host) tmp_sdz.resize((size_t)n);
+    float* nll_dst = nll_host ? nll_host : tmp_nll.data();
+    float* sdz_dst = sdz_host ? sdz_host : (sums_host ? tmp_sdz.data() : nullptr);
+    int64_t k = 0;
+    for (int64_t off = 0; off < n; off += m->chunk, ++k) {
+        nf_model::Staging& s = m->st[k & 1];
+        const int64_t c = (n - off < m->chunk) ? n - off : m->chunk;
+        NF_CUDA(cudaEventSynchronize(s.done));   // previous use of this slot has drained
+        NF_CUDA(cudaMemcpyAsync(s.x, x_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));
+        if (y_host) NF_CUDA(cudaMemcpyAsync(s.y, y_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));
+        if (rows_host) NF_CUDA(cudaMemcpyAsync(s.rows, rows_host + off, c * sizeof(int32_t), cudaMemcpyHostToDevice, s.stream));
+        rc = nf_log_prob(m, s.x, y_host ? s.y : nullptr, rows_host ? s.rows : nullptr, default_row, c, s.nll, s.sdz,
+                         z_host ? s.z : nullptr, s.stream);
+        if (rc) return rc;
+        NF_CUDA(cudaMemcpyAsync(nll_dst + off, s.nll, c * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        if (sdz_dst) NF_CUDA(cudaMemcpyAsync(sdz_dst + off, s.sdz, c * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        if (z_host) NF_CUDA(cudaMemcpyAsync(z_host + off * NF_DIMS, s.z, c * pb, cudaMemcpyDeviceToHost, s.stream));
+        NF_CUDA(cudaEventRecord(s.done, s.stream));
+    }
+    for (auto& s : m->st) NF_CUDA(cudaStreamSynchronize(s.stream));
+    if (sums_host) {   // fixed-order fp64 accumulation on the host: identical for any chunking
+        for (int64_t i = 0; i < n; ++i) {
+            tot[0] += (double)nll_dst[i];
+            if (sdz_dst) tot[1] += (double)sdz_dst[i];
+        }
+        tot[2] = (double)n;
+        memcpy(sums_host, tot, sizeof(tot));
+    }
+    return NF_OK;
+}
+
+int nf_sample_host(const nf_model* cm, const float* y_host, const int32_t* rows_host, int32_t default_row, int64_t n,
+                   float temp, const float* eps_host, uint64_t seed, uint64_t offset, float* x_host) {
+    int rc = check_ready(cm);
+    if (rc) return rc;
+    if (!x_host || n < 0) return fail(NF_ERR_INVALID, "x_host is required");
+    nf_model* m = const_cast<nf_model*>(cm);
+    std::lock_guard<std::mutex> lock(m->pool_mu);
+    rc = ensure_staging(m);
+    if (rc) return rc;
+    const size_t pb = (size_t)NF_DIMS * sizeof(float);
+    int64_t k = 0;
+    for (int64_t off = 0; off < n; off += m->chunk, ++k) {
+        nf_model::Staging& s = m->st[k & 1];
+        const int64_t c = (n - off < m->chunk) ? n - off : m->chunk;
+        NF_CUDA(cudaEventSynchronize(s.done));
+        if (y_host) NF_CUDA(cudaMemcpyAsync(s.y, y_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));
+        if (eps_host) NF_CUDA(cudaMemcpyAsync(s.x, eps_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));
+        if (rows_host) NF_CUDA(cudaMemcpyAsync(s.rows, rows_host + off, c * sizeof(int32_t), cudaMemcpyHostToDevice, s.stream));
+        rc = nf_sample(m, y_host ? s.y : nullptr, rows_host ? s.rows : nullptr, default_row, c, temp,
+                       eps_host ? s.x : nullptr, seed, offset, (uint64_t)off, s.z, s.stream);
+        if (rc) return rc;
+        NF_CUDA(cudaMemcpyAsync(x_host + off * NF_DIMS, s.z, c * pb, cudaMemcpyDeviceToHost, s.stream));
+        NF_CUDA(cudaEventRecord(s.done, s.stream));
+    }
+    for (auto& s : m->st) NF_CUDA(cudaStreamSynchronize(s.stream));
+    return NF_OK;
+}
+
+int nf_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(NF_ERR_INVALID, "ptr is null");
+    NF_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return NF_OK;
+}
+int nf_host_free(void* ptr) {
+    if (ptr) NF_CUDA(cudaFreeHost(ptr));
+    return NF_OK;
+}
+
+}  // extern "C"

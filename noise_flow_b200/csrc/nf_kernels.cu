@@ -1,0 +1,467 @@
+// Fused Noise Flow bijector-chain kernels for sm_100a (B200).
+//
+// Design:  ONE WARP OWNS ONE 32x32x4 PATCH.  The patch (16 KiB, NHWC float4 per
+// pixel) stays resident in that warp's shared memory across the whole bijector chain; lane l owns
+// image column l and the warp streams down the 32 rows.  A coupling layer
+// (1x1 mix -> conv3x3 -> BN -> ReLU -> conv1x1 -> BN -> ReLU -> edge-padded conv3x3 -> tanh/exp affine)
+// is ONE software-pipelined pass over the rows: stage A (row t) mixes channels and publishes the
+// conditioning half x0, stage B (row t-1) scatters that row into the three pending conv-1
+// accumulators and emits h2 row t-2, stage C (row t-3) scatters the h2 row into the three pending
+// conv-3 accumulators and finishes output row t-4 (affine update + log-det).  Rows travel between
+// lanes through two tiny double-buffered row rings, so a pass needs one __syncwarp per row, no
+// __syncthreads at all, and every activation is read from shared memory exactly once per consumer
+// lane.  All convolution arithmetic is packed fma.rn.f32x2 (FFMA2) over input-channel pairs with
+// the weights broadcast from the __grid_constant__ parameter block through uniform registers.
+//
+// Reference semantics restated here (file:line in /root/reference):
+//   borealisflows/layers.py:117-130   Conv2d1x1 inverse/forward + constant log-det
+//   borealisflows/layers.py:333-375   AffineCoupling forward/inverse + log-det
+//   borealisflows/layers.py:452-498   real_nvp_conv_template (BN folded for is_training=False)
+//   borealisflows/layers.py:555-583,651-674  add_edge_padding + conv2d_zeros
+//   borealisflows/noise_flow_layers/AffineCouplingSdnEx5.py:66-132, AffineCouplingGainEx4.py:62-127
+//   borealisflows/noise_flow_model.py:394-447,458-480,525-541  inverse / forward / prior / sd_z
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nf_params.h"
+#include "nf_kernels.h"
+
+namespace nf {
+
+struct __align__(16) WarpSmem {
+    float4 z[NF_PIXELS];   // z[row * 32 + lane]
+    float4 hr[2][34];      // h2 row ring: [1..32] = columns, [0] and [33] = zero halo
+    float2 xr[2][34];      // x0 row ring
+};
+static_assert(sizeof(WarpSmem) == NF_WARP_SMEM_BYTES, "WarpSmem size");
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    ra = *reinterpret_cast<unsigned long long*>(&a);
+    rb = *reinterpret_cast<unsigned long long*>(&b);
+    rc = *reinterpret_cast<unsigned long long*>(&c);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+// out[o] = sum_i v[i] * m[o][i]
+__device__ __forceinline__ float4 mix4(float4 v, const float (&m)[4][4]) {
+    const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+    float r[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        float2 t = ffma2(lo, ld2(&m[o][0]), make_float2(0.f, 0.f));
+        t = ffma2(hi, ld2(&m[o][2]), t);
+        r[o] = t.x + t.y;
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// tanh(v) = 1 - 2 / (exp(2v) + 1): ex2.approx + rcp.approx, ~1e-7 absolute error, saturates cleanly.
+__device__ __forceinline__ float fast_tanh(float v) {
+    const float e = exp2f(v * 2.885390081777927f);   // exp(2v); compiled with -use_fast_math -> ex2.approx
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
+__device__ __forceinline__ float fast_exp(float v) { return exp2f(v * 1.4426950408889634f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11); one call per pixel -> four normals by two Box-Muller pairs.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(unsigned int r) { return fmaf((float)r, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long offset,
+                                                 unsigned long long patch, unsigned int pixel) {
+    const uint4 r = philox4x32_10(make_uint4(pixel, (unsigned int)patch, (unsigned int)(patch >> 32), (unsigned int)offset),
+                                  make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
+    float4 o;
+    float s, c;
+    float rad = sqrtf(-2.f * __logf(u01(r.x)));
+    sincospif(2.f * u01(r.y), &s, &c);
+    o.x = rad * c; o.y = rad * s;
+    rad = sqrtf(-2.f * __logf(u01(r.z)));
+    sincospif(2.f * u01(r.w), &s, &c);
+    o.z = rad * c; o.w = rad * s;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one affine coupling (+ fused 1x1 mix) as a single pipelined pass over the 32 rows of the patch
+// ------------------------------------------------------------------------------------------------
+template <int SLOT, bool INV>
+__device__ __forceinline__ void coupling_pass(const NfModelParams& mp, WarpSmem& s, const int lane, float& ldj) {
+    const NfCouplingP& P = mp.cp[SLOT];
+    const bool has_mix = P.has_mix != 0;
+
+    // edge-indicator bias of conv2d_zeros by (row class, this lane's column class)
+    float b3t[4], b3m[4], b3b[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        b3t[o] = lane == 0 ? P.b3[0][0][o] : (lane == 31 ? P.b3[0][2][o] : P.b3[0][1][o]);
+        b3m[o] = lane == 0 ? P.b3[1][0][o] : (lane == 31 ? P.b3[1][2][o] : P.b3[1][1][o]);
+        b3b[o] = lane == 0 ? P.b3[2][0][o] : (lane == 31 ? P.b3[2][2][o] : P.b3[2][1][o]);
+    }
+
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 c1a[4], c1b[4];   // conv-1 accumulators: output rows i-1 (a) and i (b) while consuming input row i
+    float2 c3a[4], c3b[4];   // conv-3 accumulators, same roles
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { c1a[o] = c1b[o] = c3a[o] = c3b[o] = zero2; }
+
+#pragma unroll 1
+    for (int t = 0; t < 36; ++t) {
+        // ---------------- stage A: row t -> (mix) -> publish x0 = first two channels
+        if (t < 32) {
+            float4 z = s.z[t * 32 + lane];
+            if (INV && has_mix) {
+                z = mix4(z, P.a);
+                s.z[t * 32 + lane] = z;
+            }
+            s.xr[t & 1][lane + 1] = make_float2(z.x, z.y);
+        }
+        // ---------------- stage B: consume x0 row i = t-1, emit h2 row i-1
+        if (t >= 1 && t <= 33) {
+            const int i = t - 1;
+            float2 c1c[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) c1c[o] = zero2;
+            if (i <= 31) {
+                float2 xin[3];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) xin[dx] = s.xr[i & 1][lane + dx];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        c1a[o] = ffma2(xin[dx], ld2(&P.w1[2][dx][o][0]), c1a[o]);
+                        c1b[o] = ffma2(xin[dx], ld2(&P.w1[1][dx][o][0]), c1b[o]);
+                        c1c[o] = ffma2(xin[dx], ld2(&P.w1[0][dx][o][0]), c1c[o]);
+                    }
+                }
+            }
+            if (i >= 1) {
+                float h1[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) h1[o] = fmaxf(c1a[o].x + c1a[o].y + P.b1[o], 0.f);
+                const float2 h01 = make_float2(h1[0], h1[1]), h23 = make_float2(h1[2], h1[3]);
+                float h2[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    float2 u = ffma2(h01, ld2(&P.w2[o][0]), zero2);
+                    u = ffma2(h23, ld2(&P.w2[o][2]), u);
+                    h2[o] = fmaxf(u.x + u.y + P.b2[o], 0.f);
+                }
+                s.hr[(i - 1) & 1][lane + 1] = make_float4(h2[0], h2[1], h2[2], h2[3]);
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) { c1a[o] = c1b[o]; c1b[o] = c1c[o]; }
+        }
+        // ---------------- stage C: consume h2 row j = t-3, finish output row j-1
+        if (t >= 3) {
+            const int j = t - 3;
+            float2 c3c[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) c3c[o] = zero2;
+            if (j <= 31) {
+                float4 hin[3];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) hin[dx] = s.hr[j & 1][lane + dx];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float2 lo = make_float2(hin[dx].x, hin[dx].y), hi = make_float2(hin[dx].z, hin[dx].w);
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        c3a[o] = ffma2(lo, ld2(&P.w3[2][dx][o][0]), c3a[o]);
+                        c3a[o] = ffma2(hi, ld2(&P.w3[2][dx][o][2]), c3a[o]);
+                        c3b[o] = ffma2(lo, ld2(&P.w3[1][dx][o][0]), c3b[o]);
+                        c3b[o] = ffma2(hi, ld2(&P.w3[1][dx][o][2]), c3b[o]);
+                        c3c[o] = ffma2(lo, ld2(&P.w3[0][dx][o][0]), c3c[o]);
+                        c3c[o] = ffma2(hi, ld2(&P.w3[0][dx][o][2]), c3c[o]);
+                    }
+                }
+            }
+            if (j >= 1) {
+                const int q = j - 1;
+                float h3[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const float b = q == 0 ? b3t[o] : (q == 31 ? b3b[o] : b3m[o]);
+                    h3[o] = c3a[o].x + c3a[o].y + b;
+                }
+                // shift = h3[0:2], log_scale = scale * tanh(h3[2:4])      (layers.py:362 / :342)
+                const float ls0 = P.scale * fast_tanh(h3[2]);
+                const float ls1 = P.scale * fast_tanh(h3[3]);
+                float4 z = s.z[q * 32 + lane];
+                if (INV) {
+                    z.z = fmaf(z.z, fast_exp(ls0), h3[0]);                 // layers.py:363-367
+                    z.w = fmaf(z.w, fast_exp(ls1), h3[1]);
+                    ldj += ls0 + ls1;                                      // layers.py:372
+                } else {
+                    z.z = (z.z - h3[0]) * fast_exp(-ls0);                  // layers.py:343-347
+                    z.w = (z.w - h3[1]) * fast_exp(-ls1);
+                    ldj -= ls0 + ls1;                                      // layers.py:352
+                    if (has_mix) z = mix4(z, P.ainv);                      // layers.py:113-114
+                }
+                s.z[q * 32 + lane] = z;
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) { c3a[o] = c3b[o]; c3b[o] = c3c[o]; }
+        }
+        __syncwarp();
+    }
+}
+
+template <bool INV>
+__device__ __forceinline__ void coupling_dispatch(const NfModelParams& mp, WarpSmem& s, int lane, float& ldj, int slot) {
+    switch (slot) {
+#define NF_CASE(K) case K: coupling_pass<K, INV>(mp, s, lane, ldj); break;
+        NF_CASE(0) NF_CASE(1) NF_CASE(2) NF_CASE(3) NF_CASE(4) NF_CASE(5) NF_CASE(6) NF_CASE(7)
+        NF_CASE(8) NF_CASE(9) NF_CASE(10) NF_CASE(11) NF_CASE(12) NF_CASE(13) NF_CASE(14) NF_CASE(15)
+#undef NF_CASE
+        default: break;
+    }
+}
+
+// stand-alone 4x4 channel mix (Conv2d1x1 / tfb.Permute not followed by a coupling)
+template <bool INV>
+__device__ __forceinline__ void mix_pass(const NfMixP& M, WarpSmem& s, int lane) {
+    float m[4][4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[o][i] = INV ? M.a[o][i] : M.ainv[o][i];
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) s.z[r * 32 + lane] = mix4(s.z[r * 32 + lane], m);
+}
+
+// scale layers: sdn* (scale^2 = a*y + b) and gain* (scale = g)
+template <bool INV>
+__device__ __forceinline__ void sdn_pass(const float4* __restrict__ yp, float a, float b, WarpSmem& s, int lane, float& ldj) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+        const float4 y = __ldg(yp + r * 32 + lane);
+        float4 z = s.z[r * 32 + lane];
+        const float v0 = fmaf(a, y.x, b), v1 = fmaf(a, y.y, b), v2 = fmaf(a, y.z, b), v3 = fmaf(a, y.w, b);
+        const float r0 = rsqrtf(v0), r1 = rsqrtf(v1), r2 = rsqrtf(v2), r3 = rsqrtf(v3);
+        if (INV) { z.x *= r0; z.y *= r1; z.z *= r2; z.w *= r3; }                       // SdnEx5.py:125-126
+        else     { z.x *= v0 * r0; z.y *= v1 * r1; z.z *= v2 * r2; z.w *= v3 * r3; }   // SdnEx5.py:106-107
+        acc += (__logf(v0) + __logf(v1)) + (__logf(v2) + __logf(v3));
+        s.z[r * 32 + lane] = z;
+    }
+    ldj += INV ? -0.5f * acc : 0.5f * acc;                                              // SdnEx5.py:129 / :110
+}
+
+template <bool INV>
+__device__ __forceinline__ void gain_pass(float g, float ginv, float ldj_inv, WarpSmem& s, int lane, float& ldj) {
+    const float m = INV ? ginv : g;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+        float4 z = s.z[r * 32 + lane];
+        z.x *= m; z.y *= m; z.z *= m; z.w *= m;
+        s.z[r * 32 + lane] = z;
+    }
+    if (lane == 0) ldj += INV ? ldj_inv : -ldj_inv;
+}
+
+template <bool INV>
+__device__ __forceinline__ void run_layer(const NfModelParams& mp, const NfChainArgs& a, WarpSmem& s, int lane,
+                                          int l, long long p, int row, float& ldj) {
+    const int op = mp.op[l], slot = mp.slot[l];
+    switch (op) {
+        case NF_KOP_COUPLING: coupling_dispatch<INV>(mp, s, lane, ldj, slot); break;
+        case NF_KOP_MIX: mix_pass<INV>(mp.mix[slot], s, lane); break;
+        case NF_KOP_SDN:
+            sdn_pass<INV>(reinterpret_cast<const float4*>(a.y) + p * NF_PIXELS, mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], s, lane, ldj);
+            break;
+        case NF_KOP_GAIN:
+            gain_pass<INV>(mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], mp.sc[slot].t[row][2], s, lane, ldj);
+            break;
+        default: break;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused chain kernel: persistent warps, one patch per warp at a time
+// ------------------------------------------------------------------------------------------------
+template <bool INV>
+__global__ void __launch_bounds__(NF_MAX_CTA_THREADS, 1)
+nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
+    WarpSmem& s = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+
+    if (lane < 2) {   // zero halo columns of the row rings (never written again)
+        s.hr[0][lane * 33] = s.hr[1][lane * 33] = make_float4(0.f, 0.f, 0.f, 0.f);
+        s.xr[0][lane * 33] = s.xr[1][lane * 33] = make_float2(0.f, 0.f);
+    }
+    __syncwarp();
+
+    const long long stride = (long long)gridDim.x * warps_per_cta;
+    for (long long p = (long long)blockIdx.x * warps_per_cta + warp; p < a.n; p += stride) {
+        int row = a.rows ? a.rows[p] : a.default_row;
+        row = min(max(row, 0), NF_MAX_ROWS - 1);
+
+        // ---- load the patch into this warp's shared memory (coalesced 512 B per row)
+        if (a.in) {
+            const float4* src = reinterpret_cast<const float4*>(a.in) + p * NF_PIXELS;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                float4 v = __ldcs(src + r * 32 + lane);
+                if (!INV) { v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp; }   // noise_flow_model.py:501
+                s.z[r * 32 + lane] = v;
+            }
+        } else {
+#pragma unroll 2
+            for (int r = 0; r < 32; ++r) {
+                float4 v = philox_normal4(a.seed, a.offset, a.patch_base + (unsigned long long)p, (unsigned int)(r * 32 + lane));
+                v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp;
+                s.z[r * 32 + lane] = v;
+            }
+        }
+        __syncwarp();
+
+        float ldj = 0.f;
+        if (INV) {
+            for (int l = a.first_layer; l < a.last_layer; ++l) run_layer<true>(mp, a, s, lane, l, p, row, ldj);
+        } else {
+            for (int l = a.last_layer - 1; l >= a.first_layer; --l) run_layer<false>(mp, a, s, lane, l, p, row, ldj);
+        }
+
+        // ---- epilogue: store the patch, reduce log-det / prior / latent statistics
+        float s1 = 0.f, s2 = 0.f;
+        float4* dst = a.out ? reinterpret_cast<float4*>(a.out) + p * NF_PIXELS : nullptr;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const float4 z = s.z[r * 32 + lane];
+            if (dst) __stcs(dst + r * 32 + lane, z);
+            s1 += (z.x + z.y) + (z.z + z.w);
+            s2 = fmaf(z.x, z.x, fmaf(z.y, z.y, fmaf(z.z, z.z, fmaf(z.w, z.w, s2))));
+        }
+        ldj = warp_sum(ldj);
+        if (a.nll || a.sdz) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
+        if (lane == 0) {
+            const float logdet = ldj + (INV ? a.ldj_const : -a.ldj_const);
+            if (a.logdet) a.logdet[p] = logdet;
+            if (a.nll) {   // -(logdet + sum -0.5 (log 2pi + z^2))       noise_flow_model.py:474-475,537-539
+                const float logp = -0.5f * (NF_DIMS * 1.8378770664093453f + s2);
+                a.nll[p] = -(logdet + logp);
+            }
+            if (a.sdz) {   // population std-dev of z                     noise_flow_model.py:477-478
+                const float mean = s1 * (1.f / NF_DIMS);
+                a.sdz[p] = sqrtf(fmaxf(s2 * (1.f / NF_DIMS) - mean * mean, 0.f));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic batch reduction: sums[0] = sum nll, sums[1] = sum sd_z, sums[2] = n   (fp64)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+nf_reduce_kernel(const float* __restrict__ nll, const float* __restrict__ sdz, long long n, double* __restrict__ sums) {
+    __shared__ double sh[2][1024];
+    double a = 0.0, b = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) {
+        if (nll) a += (double)nll[i];
+        if (sdz) b += (double)sdz[i];
+    }
+    sh[0][threadIdx.x] = a;
+    sh[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + w];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { sums[0] = sh[0][0]; sums[1] = sh[1][0]; sums[2] = (double)n; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// squeeze2d / unsqueeze2d (reference borealisflows/utils.py:30-86): pure index permutation, bit-exact
+// ------------------------------------------------------------------------------------------------
+// out[n, h/f, w/f, chan] with chan = c*f*f + dy*f + dx  <- in[n, hh, ww, c]
+//   chessboard: hh = (h/f)*f + dy, ww = (w/f)*f + dx       (utils.py:44-47)
+//   patch     : hh = dy*(H/f) + h/f, ww = dx*(W/f) + w/f   (utils.py:48-51)
+__global__ void nf_squeeze_kernel(const float* __restrict__ in, float* __restrict__ out, long long total,
+                                  int H, int W, int C, int f, int patch_type, int inverse) {
+    const int Ho = H / f, Wo = W / f, Co = C * f * f;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long t = idx;
+        const int chan = (int)(t % Co); t /= Co;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho); t /= Ho;
+        const long long n = t;
+        const int dx = chan % f, dy = (chan / f) % f, c = chan / (f * f);
+        const int hh = patch_type ? dy * Ho + ho : ho * f + dy;
+        const int ww = patch_type ? dx * Wo + wo : wo * f + dx;
+        const long long full = ((n * H + hh) * W + ww) * C + c;
+        if (inverse) out[full] = in[idx]; else out[idx] = in[full];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers (called by nf_api.cu)
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_chain(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, int warps_per_cta,
+                         cudaStream_t stream) {
+    if (args.n <= 0) return cudaSuccess;
+    const size_t smem = (size_t)warps_per_cta * sizeof(WarpSmem);
+    static bool attr_done[2] = {false, false};   // idempotent; a benign race sets the same value twice
+    cudaError_t e;
+    if (inverse) {
+        if (!attr_done[0]) {
+            e = cudaFuncSetAttribute(nf_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NF_MAX_CTA_SMEM);
+            if (e != cudaSuccess) return e;
+            attr_done[0] = true;
+        }
+    } else if (!attr_done[1]) {
+        e = cudaFuncSetAttribute(nf_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NF_MAX_CTA_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done[1] = true;
+    }
+    long long ctas = (args.n + warps_per_cta - 1) / warps_per_cta;
+    if (ctas > num_sms) ctas = num_sms;
+    if (inverse) nf_chain_kernel<true><<<(unsigned)ctas, warps_per_cta * 32, smem, stream>>>(mp, args);
+    else         nf_chain_kernel<false><<<(unsigned)ctas, warps_per_cta * 32, smem, stream>>>(mp, args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce(const float* nll, const float* sdz, long long n, double* sums, cudaStream_t stream) {
+    nf_reduce_kernel<<<1, 1024, 0, stream>>>(nll, sdz, n, sums);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_squeeze(const float* in, float* out, long long n, int H, int W, int C, int factor, int patch_type,
+                           int inverse, cudaStream_t stream) {
+    const long long total = n * H * W * C;
+    if (total <= 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    nf_squeeze_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, out, total, H, W, C, factor, patch_type, inverse);
+    return cudaGetLastError();
+}
+
+}  // namespace nf

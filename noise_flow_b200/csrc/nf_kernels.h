@@ -1,0 +1,20 @@
+// Internal launcher interface between nf_api.cu (C-ABI, host logic) and nf_kernels.cu (device code).
+#pragma once
+#include <cuda_runtime.h>
+#include "nf_params.h"
+
+#define NF_WARP_SMEM_BYTES (NF_PIXELS * 16 + 2 * 34 * 16 + 2 * 34 * 8)   // 18016 B per resident patch
+#define NF_MAX_WARPS_PER_CTA 12
+#define NF_MAX_CTA_THREADS (NF_MAX_WARPS_PER_CTA * 32)
+#define NF_MAX_CTA_SMEM (NF_MAX_WARPS_PER_CTA * NF_WARP_SMEM_BYTES)      // 216192 B <= 227 KB
+
+namespace nf {
+cudaError_t launch_chain(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, int warps_per_cta,
+                         cudaStream_t stream);
+cudaError_t launch_reduce(const float* nll, const float* sdz, long long n, double* sums, cudaStream_t stream);
+cudaError_t launch_squeeze(const float* in, float* out, long long n, int H, int W, int C, int factor, int patch_type,
+                           int inverse, cudaStream_t stream);
+bool program_is_scale_only(const NfModelParams& mp, int first, int last);
+cudaError_t launch_scale_stream(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms,
+                                cudaStream_t stream);
+}  // namespace nf

@@ -1,0 +1,402 @@
+"""``NoiseFlow`` -- the reference's model API (``borealisflows/noise_flow_model.py:44-513``) on top of
+the fused sm_100a kernels.  Same method names, argument order and naming trap as the reference:
+``inverse`` = data -> latent (likelihood), ``forward`` = latent -> data (sampling).
+
+Tensors are ``torch`` CUDA tensors (used as device memory only; numpy inputs are copied over), shaped
+``[N, 32, 32, 4]`` float32.  Every compute call goes through the C-ABI in ``include/noiseflow_b200.h``;
+there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .params import (BN_EPS, MAX_ROWS, N_STD_ROWS, NO_FULL_SUM, SCALE_GAIN, SCALE_SDN, SDN_TOKENS, ModelSpec,
+                     std_row)
+
+LOG_2PI = float(np.log(2.0 * np.pi))
+N_DIMS = 32 * 32 * 4
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(_lib.c_float_p)
+
+
+class _Engine:
+    """Owns one ``nf_model`` handle built from a :class:`ModelSpec` (host-side, needs no GPU to build)."""
+
+    def __init__(self, spec: ModelSpec):
+        self.lib = _lib.load()
+        self.spec = spec
+        self._keep: List[np.ndarray] = []
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.nf_model_create(32, 32, 4, int(spec.width), C.byref(self.handle)), "nf_model_create")
+        self.scale_layers: List[int] = []
+        for idx, l in enumerate(spec.layers):
+            self._add(idx, l)
+        self._finalized = False
+
+    def _coupling_struct(self, l):
+        w = self.spec.coupling_weights(l)
+        st = _lib.NfCouplingWeights()
+        keep = []
+        for k in ("l1_w", "l1_b", "bn1_mean", "bn1_var", "l2_w", "l2_b", "bn2_mean", "bn2_var", "last_w",
+                  "last_b", "last_logs"):
+            arr = np.ascontiguousarray(w[k], dtype=np.float32)
+            keep.append(arr)
+            setattr(st, k, _fp(arr))
+        st.rescaling_scale = w["rescaling_scale"]
+        st.bn_eps = BN_EPS
+        return st, keep
+
+    def _add(self, idx, l):
+        lib, h = self.lib, self.handle
+        if l.kind == "conv1x1":
+            a, a_inv, lad = self.spec.conv1x1_matrices(l)
+            a32, i32 = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(a_inv, np.float32)
+            _lib.check(lib.nf_model_add_conv1x1(h, _fp(a32), _fp(i32), lad), "nf_model_add_conv1x1")
+        elif l.kind == "permute":
+            perm = (C.c_int32 * 4)(*l.data["perm"])
+            _lib.check(lib.nf_model_add_permute(h, perm), "nf_model_add_permute")
+        elif l.kind == "coupling":
+            st, keep = self._coupling_struct(l)
+            _lib.check(lib.nf_model_add_affine_coupling(h, C.byref(st)), "nf_model_add_affine_coupling")
+            del keep
+        elif l.kind == "scale":
+            tab = np.ascontiguousarray(self.spec.scale_table(l), np.float32)
+            kind = SCALE_SDN if l.token in SDN_TOKENS else SCALE_GAIN
+            full = 0 if l.token in NO_FULL_SUM else 1
+            _lib.check(lib.nf_model_add_scale(h, kind, full, _fp(tab), tab.shape[0]), "nf_model_add_scale")
+            self.scale_layers.append(idx)
+        else:
+            raise ValueError(l.kind)
+
+    def finalize(self):
+        if not self._finalized:
+            _lib.check(self.lib.nf_model_finalize(self.handle), "nf_model_finalize")
+            self._finalized = True
+
+    def update_scale_tables(self, extra):
+        for idx in self.scale_layers:
+            tab = np.ascontiguousarray(self.spec.scale_table(self.spec.layers[idx], extra), np.float32)
+            _lib.check(self.lib.nf_model_set_scale(self.handle, idx, _fp(tab), tab.shape[0]), "nf_model_set_scale")
+
+    def refresh_parameters(self):
+        """Re-upload every layer from the variable store (after an optimizer step / BN update)."""
+        lib, h = self.lib, self.handle
+        for idx, l in enumerate(self.spec.layers):
+            if l.kind == "conv1x1":
+                a, a_inv, lad = self.spec.conv1x1_matrices(l)
+                a32, i32 = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(a_inv, np.float32)
+                _lib.check(lib.nf_model_set_conv1x1(h, idx, _fp(a32), _fp(i32), lad), "nf_model_set_conv1x1")
+            elif l.kind == "coupling":
+                st, keep = self._coupling_struct(l)
+                _lib.check(lib.nf_model_set_affine_coupling(h, idx, C.byref(st)), "nf_model_set_affine_coupling")
+                del keep
+        self.update_scale_tables(None)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.nf_model_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class NoiseFlow(object):
+    """Drop-in for ``borealisflows.noise_flow_model.NoiseFlow`` (arch-string models, ``n_levels == 1``).
+
+    Parameters mirror the reference constructor ``NoiseFlow(x_shape, is_training, hps)``; the extra keyword
+    arguments replace what TensorFlow's graph/session machinery supplied:
+
+    ``variables``   ``{tf_variable_name: ndarray}`` (e.g. from :func:`tf_checkpoint.load_checkpoint`) = Saver.restore;
+                    missing names are initialised exactly as the reference initialises them.
+    ``first_call``  which graph function is traced first and therefore fixes the ``real_nvp_conv_template[_k]``
+                    checkpoint names (``tf.make_template`` names scopes at first call): ``'inverse'`` for a
+                    training script (loss first), ``'forward'`` for ``NoiseFlowWrapper`` (sample only).
+    """
+
+    def __init__(self, x_shape, is_training, hps=None, variables: Optional[Dict[str, np.ndarray]] = None,
+                 first_call: Optional[str] = None, device: Union[str, torch.device, None] = None, seed: int = 0):
+        if list(x_shape) != [32, 32, 4]:
+            raise NotImplementedError("kernels are built for x_shape [32, 32, 4], got %s" % (list(x_shape),))
+        self.x_shape = list(x_shape)
+        self.hps = hps
+        self.depth = getattr(hps, "depth", -1)
+        self.n_levels = getattr(hps, "n_levels", 1)
+        self._is_training = is_training
+        self.spec = ModelSpec(hps, variables, seed)
+        self.model = [self.spec.layers]
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self.device = torch.device(device)
+        self._engine: Optional[_Engine] = None
+        self._lock = threading.Lock()
+        self._extra_rows: List[tuple] = []
+        self._seed = seed
+        self._sample_calls = 0
+        if first_call is not None:
+            self.build(first_call)
+
+    # ------------------------------------------------------------------ construction
+    def build(self, first_call: str = "inverse"):
+        """Create template variables (first-call naming) + scale variables and the device engine."""
+        with self._lock:
+            if self._engine is None:
+                self.spec.assign_template_scopes(first_call)
+                self.spec.create_scale_variables()
+                eng = _Engine(self.spec)
+                eng.finalize()
+                self._engine = eng
+        return self
+
+    @property
+    def variables(self) -> Dict[str, np.ndarray]:
+        return self.spec.store.vars
+
+    def num_trainable_params(self) -> int:
+        return self.spec.store.num_trainable()
+
+    def get_layer_names(self):                                                      # noise_flow_model.py:508-513
+        return self.spec.get_layer_names()
+
+    def refresh_parameters(self):
+        if self._engine is not None:
+            with self._lock:
+                self._engine.refresh_parameters()
+
+    def set_launch(self, warps_per_cta: int = 12, num_ctas: int = 0):
+        self.build()
+        _lib.check(self._engine.lib.nf_model_set_launch(self._engine.handle, warps_per_cta, num_ctas), "nf_model_set_launch")
+
+    # ------------------------------------------------------------------ helpers
+    def _check_training(self, is_training):
+        t = self._is_training if is_training is None else is_training
+        if callable(t):
+            t = t()
+        if bool(t):
+            raise NotImplementedError(
+                "batch-statistics BatchNorm (is_training=True, reference layers.py:388-398) is not implemented by "
+                "the fused kernels yet; pass is_training=False for the moving-statistics path")
+
+    def _dev(self, a, name):
+        if a is None:
+            return None
+        if not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(np.asarray(a))
+        a = a.to(device=self.device, dtype=torch.float32).contiguous()
+        if a.dim() != 4 or tuple(a.shape[1:]) != (32, 32, 4):
+            raise ValueError("%s must have shape [N, 32, 32, 4], got %s" % (name, tuple(a.shape)))
+        return a
+
+    def _rows(self, n, nlf0, nlf1, iso, cam):
+        """(rows tensor or None, default_row).  The reference feeds length-1 ``iso``/``cam`` lists per
+        minibatch (sidd/MiniBatchSampler.py:60-64); per-patch arrays of length N are an extension."""
+        def scal(v, default):
+            if v is None:
+                return default
+            arr = np.asarray(v, dtype=np.float64).reshape(-1)
+            return arr
+        iso_a, cam_a = scal(iso, np.array([100.0])), scal(cam, np.array([0.0]))
+        n0_a, n1_a = scal(nlf0, np.array([0.0])), scal(nlf1, np.array([1.0]))
+        needs_nlf = any(l.kind == "scale" and l.token == "camsdn" for l in self.spec.layers)
+        per_patch = max(len(iso_a), len(cam_a)) > 1
+        if per_patch:
+            if len(iso_a) not in (1, n) or len(cam_a) not in (1, n):
+                raise ValueError("iso / cam must have length 1 or N")
+            iso_f = np.broadcast_to(iso_a, (n,))
+            cam_f = np.broadcast_to(cam_a, (n,))
+            rows = np.empty(n, dtype=np.int32)
+            for key in set(zip(cam_f.tolist(), iso_f.tolist())):
+                r = self._row_for(key[0], key[1], float(n0_a[0]), float(n1_a[0]), needs_nlf)
+                rows[(cam_f == key[0]) & (iso_f == key[1])] = r
+            return torch.as_tensor(rows, device=self.device), 0
+        return None, self._row_for(float(cam_a[0]), float(iso_a[0]), float(n0_a[0]), float(n1_a[0]), needs_nlf)
+
+    def _row_for(self, cam, iso, n0, n1, needs_nlf) -> int:
+        r = None if needs_nlf else std_row(cam, iso)
+        if r is not None:
+            return r
+        key = (cam, iso, n0, n1) if needs_nlf else (cam, iso, 0.0, 1.0)
+        with self._lock:
+            if key not in self._extra_rows:
+                if N_STD_ROWS + len(self._extra_rows) >= MAX_ROWS:
+                    self._extra_rows.pop(0)          # recycle the oldest non-standard conditioning row
+                self._extra_rows.append(key)
+                self._engine.update_scale_tables(self._extra_rows)
+            return N_STD_ROWS + self._extra_rows.index(key)
+
+    # ------------------------------------------------------------------ reference API
+    def inverse(self, x, objective, yy=None, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None):
+        """noise_flow_model.py:394-428 -> ``(z, objective + sum of log-dets)``."""
+        self._check_training(is_training)
+        self.build("inverse")
+        x, yy = self._dev(x, "x"), self._dev(yy, "yy")
+        n = x.shape[0]
+        rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
+        z = torch.empty_like(x)
+        ld = torch.empty(n, device=self.device, dtype=torch.float32)
+        e = self._engine
+        with torch.cuda.device(self.device):
+            _lib.check(e.lib.nf_inverse(e.handle, x.data_ptr(), yy.data_ptr() if yy is not None else None,
+                                        rows.data_ptr() if rows is not None else None, drow, n,
+                                        z.data_ptr(), ld.data_ptr(), _stream_ptr(self.device)), "nf_inverse")
+        if objective is None:
+            return z, ld
+        obj = objective if isinstance(objective, torch.Tensor) else torch.as_tensor(np.asarray(objective))
+        return z, obj.to(self.device, torch.float32) + ld
+
+    def forward(self, z, eps_std=None, yy=None, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None):
+        """noise_flow_model.py:430-447 (``eps_std`` only matters for multi-level models, as in the reference)."""
+        self._check_training(is_training)
+        self.build("forward")
+        z, yy = self._dev(z, "z"), self._dev(yy, "yy")
+        n = z.shape[0]
+        rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
+        x = torch.empty_like(z)
+        e = self._engine
+        with torch.cuda.device(self.device):
+            _lib.check(e.lib.nf_forward(e.handle, z.data_ptr(), yy.data_ptr() if yy is not None else None,
+                                        rows.data_ptr() if rows is not None else None, drow, n,
+                                        x.data_ptr(), None, _stream_ptr(self.device)), "nf_forward")
+        return x
+
+    def sample(self, y, eps_std=None, yy=None, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None,
+               eps=None, seed=None, offset=None, patch_base: int = 0):
+        """noise_flow_model.py:449-456: ``z = eps * eps_std``, ``x = forward(z)``.
+
+        ``eps`` injects the standard-normal draw (parity tests); otherwise it is drawn in-kernel with
+        Philox4x32-10 keyed by ``seed`` (default: the constructor seed) and ``offset`` (default: a per-model
+        call counter, so successive calls give fresh noise like ``tf.random_normal``)."""
+        self._check_training(is_training)
+        self.build("forward")
+        y = self._dev(y, "y")
+        yy = self._dev(yy, "yy") if yy is not None else None
+        n = y.shape[0]
+        rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
+        temp = 1.0 if eps_std is None else float(np.asarray(eps_std).reshape(-1)[0])
+        eps = self._dev(eps, "eps")
+        if offset is None:
+            with self._lock:
+                offset = self._sample_calls
+                self._sample_calls += 1
+        x = torch.empty_like(y)
+        e = self._engine
+        with torch.cuda.device(self.device):
+            _lib.check(e.lib.nf_sample(e.handle, yy.data_ptr() if yy is not None else None,
+                                       rows.data_ptr() if rows is not None else None, drow, n, temp,
+                                       eps.data_ptr() if eps is not None else None,
+                                       int(self._seed if seed is None else seed), int(offset), int(patch_base),
+                                       x.data_ptr(), _stream_ptr(self.device)), "nf_sample")
+        return x
+
+    def _loss(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, reuse=False, is_training=None, return_z=False):
+        """noise_flow_model.py:458-480 -> ``(nll[N], sd_z)``."""
+        self._check_training(is_training)
+        self.build("inverse")
+        x = self._dev(x, "x")
+        cond = getattr(self.hps, "sidd_cond", "mix")
+        yy = self._dev(y, "y") if (cond is not None and cond != "uncond") else None     # :464-467
+        n = x.shape[0]
+        rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
+        nll = torch.empty(n, device=self.device, dtype=torch.float32)
+        sdz = torch.empty(n, device=self.device, dtype=torch.float32)
+        z = torch.empty_like(x) if return_z else None
+        sums = torch.empty(3, device=self.device, dtype=torch.float64)
+        e = self._engine
+        with torch.cuda.device(self.device):
+            st = _stream_ptr(self.device)
+            _lib.check(e.lib.nf_log_prob(e.handle, x.data_ptr(), yy.data_ptr() if yy is not None else None,
+                                         rows.data_ptr() if rows is not None else None, drow, n, nll.data_ptr(),
+                                         sdz.data_ptr(), z.data_ptr() if z is not None else None, st), "nf_log_prob")
+            _lib.check(e.lib.nf_reduce_sums(nll.data_ptr(), sdz.data_ptr(), n, sums.data_ptr(), st), "nf_reduce_sums")
+        self.last_sums = sums                                   # [sum nll, sum sd_z, n] (fp64, deterministic)
+        sd_z = (sums[1] / max(n, 1)).to(torch.float32)          # tf.reduce_mean(tf.sqrt(var_z))  :478
+        if return_z:
+            return nll, sd_z, z
+        return nll, sd_z
+
+    def loss(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, reuse=False, is_training=None):
+        """noise_flow_model.py:482-484 -> ``(mean NLL, sd_z)``; the mean is the fp64 deterministic reduction."""
+        nll, sd_z = self._loss(x, y, nlf0, nlf1, iso, cam, reuse, is_training)
+        return (self.last_sums[0] / max(nll.shape[0], 1)).to(torch.float32), sd_z
+
+    def log_prob(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None):
+        """``log p(x | y, cam, iso)`` per patch (= ``-nll``; named by BASELINE.json's north star)."""
+        return -self._loss(x, y, nlf0, nlf1, iso, cam, is_training=is_training)[0]
+
+    def prior(self, name, x):
+        """noise_flow_model.py:486-506: standard-normal base measure ``(logp, sample)``."""
+        n = x.shape[0]
+
+        def logp(z1):
+            z1 = self._dev(z1, "z")
+            return (-0.5 * (LOG_2PI + z1 * z1)).sum(dim=(1, 2, 3))
+
+        def sample(eps_std=None):
+            eps = torch.randn((n, 32, 32, 4), device=self.device, dtype=torch.float32)
+            return eps if eps_std is None else eps * float(np.asarray(eps_std).reshape(-1)[0])
+
+        return logp, sample
+
+    # ------------------------------------------------------------------ per-bijector access (tests, config 1)
+    def run_layers(self, first: int, last: int, direction: str, x, yy=None, nlf0=None, nlf1=None, iso=None, cam=None):
+        """``_inverse_and_log_det_jacobian`` / ``_forward_and_log_det_jacobian`` of bijectors first..last-1."""
+        self.build("inverse")
+        x, yy = self._dev(x, "x"), self._dev(yy, "yy")
+        n = x.shape[0]
+        rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
+        out = torch.empty_like(x)
+        ld = torch.empty(n, device=self.device, dtype=torch.float32)
+        e = self._engine
+        with torch.cuda.device(self.device):
+            _lib.check(e.lib.nf_run_layers(e.handle, first, last, 0 if direction == "inverse" else 1, x.data_ptr(),
+                                           yy.data_ptr() if yy is not None else None,
+                                           rows.data_ptr() if rows is not None else None, drow, n, out.data_ptr(),
+                                           ld.data_ptr(), _stream_ptr(self.device)), "nf_run_layers")
+        return out, ld
+
+
+# ---------------------------------------------------------------------------------------------------
+# squeeze2d / unsqueeze2d (borealisflows/utils.py:30-86) on the device, bit-exact
+# ---------------------------------------------------------------------------------------------------
+def _squeeze_common(x: torch.Tensor, factor: int, squeeze_type: str, inverse: bool) -> torch.Tensor:
+    lib = _lib.load()
+    if not x.is_cuda:
+        raise RuntimeError("squeeze2d/unsqueeze2d run on the GPU; got a CPU tensor")
+    assert factor >= 1
+    if factor == 1:
+        return x                                                                    # utils.py:32-33,65-66
+    x = x.to(torch.float32).contiguous()
+    n, h, w, c = x.shape
+    st = 1 if squeeze_type == "patch" else 0                                        # unknown type -> chessboard
+    if not inverse:
+        assert h % factor == 0 and w % factor == 0
+        out = torch.empty((n, h // factor, w // factor, c * factor * factor), device=x.device, dtype=x.dtype)
+        H, W, Cc, fn = h, w, c, lib.nf_squeeze2d
+    else:
+        assert c >= 4 and c % 4 == 0
+        H, W, Cc = h * factor, w * factor, c // (factor * factor)
+        out = torch.empty((n, H, W, Cc), device=x.device, dtype=x.dtype)
+        fn = lib.nf_unsqueeze2d
+    with torch.cuda.device(x.device):
+        _lib.check(fn(x.data_ptr(), n, H, W, Cc, factor, st, out.data_ptr(), _stream_ptr(x.device)), "squeeze")
+    return out
+
+
+def squeeze2d(x, factor=2, squeeze_type="chessboard"):
+    return _squeeze_common(x, factor, squeeze_type, False)
+
+
+def unsqueeze2d(x, factor=2, squeeze_type="chessboard"):
+    return _squeeze_common(x, factor, squeeze_type, True)
