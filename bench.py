@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark: 32x32 patches/sec of the fused Noise Flow ``log_prob`` (NLL) path.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port), host cores
+
+A "step" is one ``NoiseFlow.loss`` over a batch of ``--batch`` synthetic SIDD-shaped patches per GPU with the
+shipped S-Ax4-G-Ax4 weights: fused chain kernel (x, y -> nll, sd_z) + deterministic fp64 batch reduction
+(+ one NCCL all-reduce of [sum nll, sum sd_z, n] when N > 1).  ``value`` keeps inputs resident in HBM;
+``e2e`` times the host-buffer C-ABI call (pinned host x, y -> H2D -> kernel -> D2H nll) for the same batch.
+Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+ALG_BYTES_LOG_PROB = 32 * 32 * 4 * 4 * 2 + 8        # read x, y; write nll + sd_z (no conditioning-row array here)
+ALG_BYTES_SAMPLE = 32 * 32 * 4 * 4 * 2              # read y, write x (in-kernel Philox)
+CONV_FLOP_PER_PATCH = 2 * 1024 * 8 * (72 + 16 + 144 + 16)   # 2 x MACs of the 8 couplings
+FALLBACK_HBM_GBS = 6650.0                            # B200_PROFILING.md fallback
+
+
+def load_model_files():
+    from noise_flow_b200 import hps_loader, load_checkpoint
+    g = os.path.join(ROOT, "tests", "golden", "NoiseFlow")
+    return hps_loader(os.path.join(g, "hps.txt")), load_checkpoint(os.path.join(g, "ckpt", "model.ckpt.best"))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(hps, ck, seconds_target=12.0, threads=None):
+    """patches/s of the oracle port (torch-CPU fp32, all host threads) on a bounded sample."""
+    from common import make_oracle, synth_batch
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    orc = make_oracle(hps, ck, dtype=torch.float32)
+    x, y = synth_batch(256, seed=3)
+    orc._loss(x, y, iso=[100.0], cam=[2.0])                      # warm-up
+    t0 = time.perf_counter()
+    orc._loss(x, y, iso=[100.0], cam=[2.0])
+    dt = time.perf_counter() - t0
+    n = int(min(16384, max(256, 256 * seconds_target / max(dt, 1e-3))))
+    x, y = synth_batch(n, seed=4)
+    t0 = time.perf_counter()
+    orc._loss(x, y, iso=[100.0], cam=[2.0])
+    dt = time.perf_counter() - t0
+    return n / dt, threads, "log_prob of %d synthetic S6/ISO-100 patches, oracle port torch-CPU fp32, %.1f s" % (n, dt)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path = oracle port (TF 1.12 cannot run), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from common import make_oracle, synth_batch
+    hps, ck = load_model_files()
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    orc = make_oracle(hps, ck, dtype=torch.float32)
+    per_step = args.ref_patches
+    x, y = synth_batch(per_step, seed=5)
+    for _ in range(max(args.warmup, 1)):
+        orc._loss(x, y, iso=[100.0], cam=[2.0])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.loss(x, y, iso=[100.0], cam=[2.0])
+    dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    out = {"impl": "reference", "metric": "patches_per_sec_nll", "value": val, "unit": "patches/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "log_prob S-Ax4-G-Ax4 (shipped weights), %d patches/step on host cores" % per_step,
+                      "note": "TF 1.12/TFP 0.5 reference cannot run here; timed arm = oracle port (torch-CPU fp32)"},
+           "cpu_baseline": {"value": val, "unit": "patches/s", "cores": threads, "kind": "port",
+                            "sample": "%d steps x %d patches" % (args.steps, per_step)},
+           "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="patches per GPU per step")
+    ap.add_argument("--mode", default="log_prob", choices=["log_prob", "sample"])
+    ap.add_argument("--ref-patches", type=int, default=1024)
+    ap.add_argument("--warps", type=int, default=0, help="resident patches per CTA (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from noise_flow_b200 import NoiseFlow, _lib
+    from noise_flow_b200.distributed import allreduce_sums
+    hps, ck = load_model_files()
+    nf = NoiseFlow([32, 32, 4], False, hps, variables=ck, first_call="inverse", device=dev)
+    if args.warps:
+        nf.set_launch(args.warps, 0)
+    lib, eng = _lib.load(), nf._engine
+    B = args.batch
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    y = torch.rand((B, 32, 32, 4), device=dev, generator=g)
+    x = torch.randn((B, 32, 32, 4), device=dev, generator=g) * torch.sqrt(0.000479 * y + 0.000002)
+    nll = torch.empty(B, device=dev)
+    sdz = torch.empty(B, device=dev)
+    xs = torch.empty_like(x) if args.mode == "sample" else None
+    sums = torch.zeros(3, device=dev, dtype=torch.float64)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    row = 2 * 5 + 0   # S6, ISO 100
+
+    def kernel_only(i):
+        if args.mode == "log_prob":
+            _lib.check(lib.nf_log_prob(eng.handle, x.data_ptr(), y.data_ptr(), None, row, B, nll.data_ptr(),
+                                       sdz.data_ptr(), None, stream))
+        else:
+            _lib.check(lib.nf_sample(eng.handle, y.data_ptr(), None, row, B, 0.6, None, 7, i, rank * B,
+                                     xs.data_ptr(), stream))
+
+    def step(i):
+        kernel_only(i)
+        if args.mode == "log_prob":
+            _lib.check(lib.nf_reduce_sums(nll.data_ptr(), sdz.data_ptr(), B, sums.data_ptr(), stream))
+            if world > 1:
+                allreduce_sums(sums)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    # dominant kernel alone (CUDA events on the launching stream), for the roofline line
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(args.steps):
+        kernel_only(1000 + i)
+    k1.record()
+    torch.cuda.synchronize(dev)
+    kms = k0.elapsed_time(k1) / args.steps
+    t = torch.tensor([ms, kms], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, kms = float(t[0]), float(t[1])
+    mean_nll = float(sums[0] / sums[2]) / 4096 if args.mode == "log_prob" else None
+
+    # ---- e2e: host buffers through the C-ABI host entry point (copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        nb = B * 4096 * 4
+        hx_t = torch.empty((B, 32, 32, 4), dtype=torch.float32, pin_memory=True)
+        hy_t = torch.empty((B, 32, 32, 4), dtype=torch.float32, pin_memory=True)
+        hn_t = torch.empty((B,), dtype=torch.float32, pin_memory=True)
+        hx_t.copy_(x); hy_t.copy_(y)
+        torch.cuda.synchronize(dev)
+        hx, hy, hn = hx_t.data_ptr(), hy_t.data_ptr(), hn_t.data_ptr()
+        hsums = (C.c_double * 3)()
+        e_steps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            if args.mode == "log_prob":
+                _lib.check(lib.nf_log_prob_host(eng.handle, hx, hy, None, row, B, hn, None, None, hsums))
+            else:
+                _lib.check(lib.nf_sample_host(eng.handle, hy, None, row, B, 0.6, None, 7, 0, hx))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        barrier()
+        edt = time.perf_counter() - t0
+        tt = torch.tensor([edt], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        edt = float(tt[0])
+        h2d = 2 * nb if args.mode == "log_prob" else nb
+        d2h = B * 4 if args.mode == "log_prob" else nb
+        e2e = {"value": world * B * e_steps / edt, "unit": "patches/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e_steps,
+               "path": "nf_%s_host: pinned host buffers, 4096-patch chunks double-buffered on 2 streams" % args.mode}
+        del hx_t, hy_t, hn_t
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return 0
+    value = world * B * args.steps / (ms * 1e-3)
+    peak, peak_src = measured_peak()
+    alg = ALG_BYTES_LOG_PROB if args.mode == "log_prob" else ALG_BYTES_SAMPLE
+    achieved = B * alg / (kms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("%s_%d" % (args.mode, B))
+        except Exception:
+            traffic = None
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    out = {"metric": "patches_per_sec_nll" if args.mode == "log_prob" else "patches_per_sec_sample",
+           "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "%s S-Ax4-G-Ax4 (shipped weights, arch %s), batch %d 32x32x4 patches per GPU, "
+                                  "cam S6 / ISO 100" % (args.mode, hps.arch, B),
+                      "per_gpu_batch": B, "global_batch": world * B, "parallelism": "dp%d" % world,
+                      "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (2 * B * 16384 / 2 ** 30),
+                      "mean_nll_per_dim": mean_nll},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic, "peak_source": peak_src, "kernel": "nf_chain_kernel",
+                        "kernel_ms": kms, "alg_bytes_per_patch": alg,
+                        "note": "binding roof is the FP32 FMA pipe (see roofline_fp32), not HBM"},
+           "roofline_fp32": {"bound": "fp32_fma", "achieved": B * CONV_FLOP_PER_PATCH / (kms * 1e-3) / 1e12,
+                             "peak": fp32_peak, "unit": "TFLOP/s",
+                             "frac": B * CONV_FLOP_PER_PATCH / (kms * 1e-3) / 1e12 / fp32_peak,
+                             "peak_source": "148 SMs x 128 FMA/clk x 2 x median SM clock under load"},
+           "e2e": e2e, "gpu_launches": world * args.steps * (2 if args.mode == "log_prob" else 1), "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_oracle_rate(hps, ck)
+        out["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,334 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances (north star: |NLL - reference| < 1e-4 nats/dim; bit-exact for index work):
+  * per-patch NLL:  |cuda - oracle(fp64)| / 4096 < 1e-4 nats/dim (asserted), and < 2e-5 in practice
+  * latent z / samples x: max abs error < 2e-5 x (1 + max|value|)
+  * squeeze / unsqueeze: bit-exact
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import make_oracle, synth_batch
+
+pytestmark = pytest.mark.gpu
+
+NLL_TOL_PER_DIM = 1e-4
+
+
+def _nf(hps, ck, **kw):
+    from noise_flow_b200 import NoiseFlow
+    return NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=ck, device="cuda:0", **kw)
+
+
+def _close(a, b, rel=2e-5):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() <= rel * (1.0 + np.abs(b).max())
+
+
+@pytest.mark.parametrize("cam,iso", [(2, 100), (0, 1600), (4, 800), (2, 3200)])
+def test_log_prob_matches_oracle(shipped, cam, iso):
+    hps, ck = shipped
+    x, y = synth_batch(48, cam=cam, iso=iso, seed=10 + cam)
+    nf = _nf(hps, ck)
+    nll, sd_z, z = nf._loss(x, y, iso=[float(iso)], cam=[float(cam)], return_z=True)
+    orc = make_oracle(hps, ck)
+    nll_o, sd_o = orc._loss(x, y, iso=[float(iso)], cam=[float(cam)])
+    err = np.abs(nll.cpu().numpy() - nll_o.numpy()).max() / 4096
+    assert err < NLL_TOL_PER_DIM, err
+    assert err < 2e-5, "fp32 kernel is expected well inside the tolerance, got %g" % err
+    assert abs(float(sd_z) - float(sd_o)) < 1e-5
+    assert _close(z.cpu().numpy(), orc.last_z.numpy())
+    mean, _ = nf.loss(x, y, iso=[float(iso)], cam=[float(cam)])
+    assert abs(float(mean) - float(nll_o.mean())) / 4096 < NLL_TOL_PER_DIM
+
+
+def test_inverse_forward_api_and_roundtrip(shipped):
+    hps, ck = shipped
+    x, y = synth_batch(16, seed=3)
+    nf = _nf(hps, ck)
+    obj0 = torch.zeros(16, device="cuda:0")
+    z, obj = nf.inverse(x, obj0, yy=y, iso=[100.0], cam=[2.0])
+    orc = make_oracle(hps, ck)
+    z_o, obj_o = orc.inverse(x, torch.zeros(16, dtype=torch.float64), yy=y, iso=[100.0], cam=[2.0])
+    assert _close(z.cpu().numpy(), z_o.numpy())
+    assert np.abs(obj.cpu().numpy() - obj_o.numpy()).max() / 4096 < 2e-5
+    xr = nf.forward(z, None, yy=y, iso=[100.0], cam=[2.0])
+    assert np.abs(xr.cpu().numpy() - x).max() < 1e-6 * (1 + 100 * np.abs(x).max())   # fwd(inv(x)) = x
+    x_o = orc.forward(z_o, None, yy=y, iso=[100.0], cam=[2.0])
+    assert _close(xr.cpu().numpy(), x_o.numpy())
+
+
+@pytest.mark.parametrize("temp", [0.6, 1.0])
+def test_sample_with_injected_eps_matches_oracle(shipped, temp):
+    hps, ck = shipped
+    _, y = synth_batch(24, seed=5)
+    eps = np.random.RandomState(6).randn(24, 32, 32, 4).astype(np.float32)
+    nf = _nf(hps, ck)
+    xs = nf.sample(y, temp, y, iso=[800.0], cam=[2.0], eps=eps).cpu().numpy()
+    xo = make_oracle(hps, ck).sample(eps, temp, y, iso=[800.0], cam=[2.0]).numpy()
+    assert np.abs(xs - xo).max() < 2e-6 * (1 + 100 * np.abs(xo).max())
+
+
+def test_sample_philox_stream_matches_oracle(shipped):
+    from oracle.noise_flow_oracle import philox_normal
+    hps, ck = shipped
+    _, y = synth_batch(8, seed=7)
+    nf = _nf(hps, ck)
+    xs = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], seed=123456789012345, offset=3, patch_base=5).cpu().numpy()
+    eps = philox_normal(123456789012345, 3, 8, first_patch=5)
+    xo = make_oracle(hps, ck).sample(eps, 0.6, y, iso=[100.0], cam=[2.0]).numpy()
+    # Box-Muller in fp32 (lg2/sincospi approximations) vs fp64: eps agrees to ~1e-5 absolute
+    assert np.abs(xs - xo).max() < 5e-5 * (1 + 100 * np.abs(xo).max())
+    # fresh noise on successive calls, deterministic for a fixed (seed, offset)
+    a = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0]).cpu().numpy()
+    b = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0]).cpu().numpy()
+    c = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], offset=0).cpu().numpy()
+    assert not np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_each_bijector_matches_oracle(shipped):
+    """Per-bijector _inverse/_forward_and_log_det_jacobian (BASELINE config 1: single AffineCoupling round trip)."""
+    from oracle.noise_flow_oracle import ScaleBijector
+    hps, ck = shipped
+    x, y = synth_batch(4, seed=11)
+    x = (x * 30).astype(np.float32)    # O(1) activations, as inside the chain
+    nf = _nf(hps, ck)
+    orc = make_oracle(hps, ck)
+    xt = torch.as_tensor(x, dtype=torch.float64)
+    for i, b in enumerate(orc.model[0]):
+        if isinstance(b, ScaleBijector):
+            zo, ldo = b._inverse_and_log_det_jacobian(xt, torch.as_tensor(y, dtype=torch.float64), None, None, [100.0], [2.0])
+            fo, lfo = b._forward_and_log_det_jacobian(xt, torch.as_tensor(y, dtype=torch.float64), None, None, [100.0], [2.0])
+        else:
+            zo, ldo = b._inverse_and_log_det_jacobian(xt)
+            fo, lfo = b._forward_and_log_det_jacobian(xt)
+        z, ld = nf.run_layers(i, i + 1, "inverse", x, yy=y, iso=[100.0], cam=[2.0])
+        f, lf = nf.run_layers(i, i + 1, "forward", x, yy=y, iso=[100.0], cam=[2.0])
+        assert _close(z.cpu().numpy(), zo.numpy()), (i, b.name)
+        assert _close(f.cpu().numpy(), fo.numpy()), (i, b.name)
+        ldo = np.broadcast_to(ldo.numpy(), (4,))
+        lfo = np.broadcast_to(lfo.numpy(), (4,))
+        assert np.abs(ld.cpu().numpy() - ldo).max() / 4096 < 2e-5, (i, b.name)
+        assert np.abs(lf.cpu().numpy() - lfo).max() / 4096 < 2e-5, (i, b.name)
+        back, _ = nf.run_layers(i, i + 1, "forward", z, yy=y, iso=[100.0], cam=[2.0])
+        assert np.abs(back.cpu().numpy() - x).max() < 2e-5 * (1 + np.abs(x).max()), (i, b.name)
+
+
+def test_per_patch_conditioning_rows(shipped):
+    """Extension: per-patch (cam, iso); must equal evaluating each conditioning class on its own."""
+    hps, ck = shipped
+    x, y = synth_batch(12, seed=13)
+    cams = np.array([0, 2, 4] * 4, dtype=np.float64)
+    isos = np.array([100, 800, 100, 1600, 3200, 800] * 2, dtype=np.float64)
+    nf = _nf(hps, ck)
+    nll = nf._loss(x, y, iso=isos, cam=cams)[0].cpu().numpy()
+    orc = make_oracle(hps, ck)
+    for k in range(12):
+        n_o, _ = orc._loss(x[k:k + 1], y[k:k + 1], iso=[isos[k]], cam=[cams[k]])
+        assert abs(nll[k] - float(n_o[0])) / 4096 < 2e-5, k
+
+
+def test_unknown_iso_quirk_and_unknown_cam(shipped):
+    """ISO outside {100..3200} silently selects g = 0 (cond_utils.py:226-228); an unknown camera raises."""
+    hps, ck = shipped
+    x, y = synth_batch(4, seed=17)
+    nf = _nf(hps, ck)
+    nll = nf._loss(x, y, iso=[500.0], cam=[1.0])[0].cpu().numpy()
+    n_o, _ = make_oracle(hps, ck)._loss(x, y, iso=[500.0], cam=[1.0])
+    assert np.abs(nll - n_o.numpy()).max() / 4096 < 2e-5
+    with pytest.raises(IndexError):
+        nf._loss(x, y, iso=[100.0], cam=[7.0])
+
+
+ARCHS = [
+    ("sdn5|gain4", 1),
+    ("sdn|unc|gain|unc", 0),
+    ("sdn1|gain1|unc", 1),
+    ("sdn2|unc|unc|gain2", 2),
+    ("sdn3|gain3", 1),
+    ("sdn4|unc|gain4", 1),
+    ("sdn6|unc|gain4", 0),
+    ("unc|unc", 1),
+    ("unc|camsdn", 1),
+]
+
+
+@pytest.mark.parametrize("arch,perm", ARCHS)
+def test_other_archs_fresh_and_perturbed_weights(arch, perm):
+    """Every scale-layer variant, both permutation kinds, stand-alone/fused 1x1: randomly perturbed weights
+    (so couplings are not the identity) shared by construction between engine and oracle."""
+    from noise_flow_b200 import NoiseFlow, make_hps
+    hps = make_hps(arch=arch, flow_permutation=perm)
+    nf0 = NoiseFlow([32, 32, 4], False, copy.copy(hps), device="cuda:0", seed=4, first_call="inverse")
+    rng = np.random.RandomState(5)
+    vs = {k: v.copy() for k, v in nf0.variables.items()}
+    for k in vs:
+        if k.endswith("/l_1/W") or k.endswith("/l_2/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.5).astype(np.float32)
+        elif k.endswith("/l_last/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.1).astype(np.float32)
+        elif k.endswith("/b") or k.endswith("/logs") or k.endswith("/mean"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.2).astype(np.float32)
+        elif k.endswith("/var"):
+            vs[k] = (rng.rand(*vs[k].shape) + 0.05).astype(np.float32)
+        elif "rescaling_scale" in k:
+            vs[k] = np.float32(0.3 + 0.5 * rng.rand())
+        elif k.startswith("model/") and vs[k].size <= 15 and "cam_params" not in k:
+            vs[k] = (vs[k] + rng.randn(*vs[k].shape) * 0.1).astype(np.float32)
+    nf = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+    assert not nf.spec.store.created
+    orc = make_oracle(hps, vs)
+    x, y = synth_batch(6, cam=2, iso=800, seed=19)
+    x = (x * 5).astype(np.float32)
+    kw = dict(nlf0=[0.003], nlf1=[0.00002], iso=[800.0], cam=[3.0])
+    nll, sdz, z = nf._loss(x, y, return_z=True, **kw)
+    nll_o, sd_o = orc._loss(x, y, **kw)
+    assert not orc.store.created, orc.store.created
+    assert np.abs(nll.cpu().numpy() - nll_o.numpy()).max() / 4096 < 2e-5
+    assert _close(z.cpu().numpy(), orc.last_z.numpy())
+    eps = rng.randn(6, 32, 32, 4).astype(np.float32)
+    xs = nf.sample(y, 0.8, y, eps=eps, **kw).cpu().numpy()
+    xo = orc.sample(eps, 0.8, y, **kw).numpy()
+    assert _close(xs, xo)
+
+
+def test_sdn_only_closed_form_known_answer():
+    """Known answer from the reference's own baseline formula (sidd/PatchStatsCalculator.py:104-115):
+    a camsdn-only flow is exactly the heteroscedastic Gaussian NLL with (nlf0, nlf1)."""
+    from noise_flow_b200 import NoiseFlow, make_hps
+    from oracle.noise_flow_oracle import nll_sdn_closed_form
+    x, y = synth_batch(32, cam=2, iso=1600, seed=23)
+    nf = NoiseFlow([32, 32, 4], False, make_hps(arch="camsdn"), device="cuda:0", first_call="inverse")
+    nll = nf._loss(x, y, nlf0=[0.008211], nlf1=[0.000002])[0].cpu().numpy()
+    ref = nll_sdn_closed_form(x, y, np.float32(0.008211), np.float32(0.000002))
+    assert np.abs(nll - ref).max() / 4096 < 2e-5
+
+
+def test_fresh_model_is_identity_coupling():
+    """Fresh 'unc' (l_last W = b = 0): coupling is the identity, 1x1 conv is orthogonal -> ldj ~ 0, z = x.A."""
+    from noise_flow_b200 import NoiseFlow, make_hps
+    nf = NoiseFlow([32, 32, 4], False, make_hps(arch="unc"), device="cuda:0", first_call="inverse", seed=9)
+    x, _ = synth_batch(3, seed=29)
+    z, ld = nf.inverse(x, None)
+    a, _, lad = nf.spec.conv1x1_matrices(nf.spec.layers[0])
+    assert abs(lad) < 1e-5 and np.abs(ld.cpu().numpy()).max() < 1e-2
+    assert np.abs(z.cpu().numpy() - x.astype(np.float64) @ a).max() < 1e-6
+
+
+@pytest.mark.parametrize("stype", ["chessboard", "patch", "bogus"])
+@pytest.mark.parametrize("factor", [1, 2, 4])
+def test_squeeze_unsqueeze_bit_exact(stype, factor):
+    from noise_flow_b200 import squeeze2d, unsqueeze2d
+    from oracle import noise_flow_oracle as O
+    rng = np.random.RandomState(31)
+    x = rng.randn(5, 32, 32, 4).astype(np.float32)
+    xd = torch.as_tensor(x, device="cuda:0")
+    s = squeeze2d(xd, factor, stype)
+    so = O.squeeze2d(x, factor, stype)
+    assert s.shape == so.shape and np.array_equal(s.cpu().numpy(), so)
+    u = unsqueeze2d(s, factor, stype)
+    assert np.array_equal(u.cpu().numpy(), x)
+    if factor > 1:
+        xs = rng.randn(3, 8, 8, 16).astype(np.float32)
+        uo = O.unsqueeze2d(xs, factor, stype) if 16 % (factor * factor) == 0 else None
+        if uo is not None:
+            assert np.array_equal(unsqueeze2d(torch.as_tensor(xs, device="cuda:0"), factor, stype).cpu().numpy(), uo)
+
+
+def test_wrapper_drop_in(golden_dir, shipped):
+    """NoiseFlowWrapper(path, temp).sample_noise_nf(batch_x, b1, b2, iso, cam) -> np.float32 [N,32,32,4]."""
+    from noise_flow_b200 import NoiseFlowWrapper
+    hps, ck = shipped
+    w = NoiseFlowWrapper(os.path.join(golden_dir, "NoiseFlow"), sampling_temperature=0.6)
+    assert w.is_cond and w.temp == 0.6 and w.x_shape == [None, 32, 32, 4]
+    assert w.nf_model.get_layer_names()[:3] == ["sdn_0", "Conv2d_1x1_1", "unc_1"]
+    _, y = synth_batch(5, seed=37)
+    out = w.sample_noise_nf(y.astype(np.float64), 0.0, 0.0, 100, 2)
+    assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == (5, 32, 32, 4)
+    assert np.isfinite(out).all() and 1e-3 < out.std() < 0.1
+    # reference graph-construction order (sample traced first) vs training order: distinct, both match the oracle
+    eps = np.random.RandomState(41).randn(5, 32, 32, 4).astype(np.float32)
+    for order, first in (("reference", "forward"), ("training", "inverse")):
+        ww = NoiseFlowWrapper(os.path.join(golden_dir, "NoiseFlow"), 0.6, template_order=order)
+        xs = ww.nf_model.sample(y, 0.6, y, [0.0], [0.0], [100], [2], eps=eps).cpu().numpy()
+        xo = make_oracle(hps, ck, first_call=first).sample(eps, 0.6, y, iso=[100.0], cam=[2.0]).numpy()
+        assert np.abs(xs - xo).max() < 2e-6 * (1 + 100 * np.abs(xo).max()), order
+
+
+def test_host_buffer_entry_points(shipped):
+    import ctypes as C
+    from noise_flow_b200 import _lib
+    hps, ck = shipped
+    n = 9000   # > 2 chunks of 4096, ragged tail
+    x, y = synth_batch(n, seed=43)
+    nf = _nf(hps, ck, first_call="inverse")
+    lib, h = _lib.load(), nf._engine.handle
+    nll = np.empty(n, np.float32)
+    sdz = np.empty(n, np.float32)
+    sums = (C.c_double * 3)()
+    _lib.check(lib.nf_log_prob_host(h, x.ctypes.data, y.ctypes.data, None, 10, n, nll.ctypes.data, sdz.ctypes.data, None, sums))
+    dev_nll, dev_sd = nf._loss(x, y, iso=[100.0], cam=[2.0])
+    assert np.array_equal(nll, dev_nll.cpu().numpy())
+    assert abs(sums[0] - float(nf.last_sums[0])) < 1e-6 * abs(sums[0]) and sums[2] == n
+    out = np.empty_like(x)
+    eps = np.random.RandomState(47).randn(n, 32, 32, 4).astype(np.float32)
+    _lib.check(lib.nf_sample_host(h, y.ctypes.data, None, 10, n, 0.6, eps.ctypes.data, 0, 0, out.ctypes.data))
+    dev = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], eps=eps).cpu().numpy()
+    assert np.array_equal(out, dev)
+
+
+def test_error_paths_fail_loudly(shipped):
+    from noise_flow_b200 import NoiseFlow, make_hps
+    hps, ck = shipped
+    with pytest.raises(NotImplementedError):
+        NoiseFlow([16, 16, 16], False, hps)
+    with pytest.raises(RuntimeError):
+        NoiseFlow([32, 32, 4], False, make_hps(width=8), device="cuda:0").build()
+    nf = _nf(hps, ck)
+    with pytest.raises(ValueError):
+        nf._loss(np.zeros((2, 16, 16, 4), np.float32), np.zeros((2, 16, 16, 4), np.float32))
+    with pytest.raises(NotImplementedError):
+        nf._loss(*synth_batch(2), iso=[100.0], cam=[2.0], is_training=True)
+
+
+def test_empty_and_single_patch(shipped):
+    hps, ck = shipped
+    nf = _nf(hps, ck)
+    x, y = synth_batch(1, seed=53)
+    nll, _ = nf._loss(x, y, iso=[100.0], cam=[2.0])
+    n_o, _ = make_oracle(hps, ck)._loss(x, y, iso=[100.0], cam=[2.0])
+    assert abs(float(nll[0]) - float(n_o[0])) / 4096 < 2e-5
+    e = np.zeros((0, 32, 32, 4), np.float32)
+    nll0, _ = nf._loss(e, e, iso=[100.0], cam=[2.0])
+    assert nll0.shape == (0,)
+
+
+def test_full_size_properties(shipped):
+    """BASELINE-size batch (65 536 patches): size-independent properties instead of the (slow) oracle."""
+    hps, ck = shipped
+    nf = _nf(hps, ck)
+    n = 65536
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    y = torch.rand((n, 32, 32, 4), device="cuda:0", generator=g)
+    x = torch.randn((n, 32, 32, 4), device="cuda:0", generator=g) * torch.sqrt(0.000479 * y + 0.000002)
+    nll, sd_z, z = nf._loss(x, y, iso=[100.0], cam=[2.0], return_z=True)
+    s_full = nf.last_sums.clone()
+    # (1) determinism + batch-composition independence: any sub-batch gives bit-identical per-patch results
+    nll_b, _ = nf._loss(x[1000:1777], y[1000:1777], iso=[100.0], cam=[2.0])
+    assert torch.equal(nll_b, nll[1000:1777])
+    nll2, _ = nf._loss(x, y, iso=[100.0], cam=[2.0])
+    assert torch.equal(nll2, nll) and torch.equal(nf.last_sums, s_full)
+    # (2) round trip forward(inverse(x)) = x
+    xr = nf.forward(z, None, yy=y, iso=[100.0], cam=[2.0])
+    assert float((xr - x).abs().max()) < 2e-6
+    # (3) sanity values the reference logs (train_noise_flow.py:340): sd_z ~ 1, NLL near the generating NLF
+    assert 0.85 < float(sd_z) < 1.05
+    assert -2.95 < float(s_full[0] / n) / 4096 < -2.80
+    # (4) a spot sample of patches against the oracle
+    idx = [0, 12345, 65535]
+    n_o, _ = make_oracle(hps, ck)._loss(x[idx].cpu().numpy(), y[idx].cpu().numpy(), iso=[100.0], cam=[2.0])
+    assert np.abs(nll[idx].cpu().numpy() - n_o.numpy()).max() / 4096 < 2e-5
