@@ -163,7 +163,7 @@ int build_program(const nf_model* m, int first, int last, NfModelParams* mp, flo
             memcpy(mp->mix[n_mix].a, L.a, sizeof(L.a));
             memcpy(mp->mix[n_mix].ainv, L.ainv, sizeof(L.ainv));
             mp->op[n_ops] = NF_KOP_MIX;
-            mp->slot[n_ops++] = (uint8_t)n_mix++;
+            mp->slot[n_ops++] = n_mix++;
         } else if (L.kind == L_COUPLING) {
             if (n_cp >= NF_MAX_COUPLINGS) return fail(NF_ERR_UNSUPPORTED, "more than %d couplings", NF_MAX_COUPLINGS);
             NfCouplingP& C = mp->cp[n_cp];
@@ -179,13 +179,13 @@ int build_program(const nf_model* m, int first, int last, NfModelParams* mp, flo
                 C.has_mix = 0;
             }
             mp->op[n_ops] = NF_KOP_COUPLING;
-            mp->slot[n_ops++] = (uint8_t)n_cp++;
+            mp->slot[n_ops++] = n_cp++;
         } else if (L.kind == L_SCALE) {
             if (n_sc >= NF_MAX_SCALE) return fail(NF_ERR_UNSUPPORTED, "more than %d scale layers", NF_MAX_SCALE);
             memcpy(mp->sc[n_sc].t, L.table, sizeof(L.table));
             if (L.n_rows > n_rows) n_rows = L.n_rows;
             mp->op[n_ops] = L.scale_kind == NF_SCALE_SDN ? NF_KOP_SDN : NF_KOP_GAIN;
-            mp->slot[n_ops++] = (uint8_t)n_sc++;
+            mp->slot[n_ops++] = n_sc++;
         }
     }
     mp->n_layers = n_ops;
@@ -416,6 +416,7 @@ int nf_log_prob(const nf_model* m, const float* x, const float* y, const int32_t
                 float* nll, float* sdz, float* z, void* stream) {
     int rc = check_ready(m);
     if (rc) return rc;
+    if (n == 0) return NF_OK;
     if (!x || !nll) return fail(NF_ERR_INVALID, "x and nll are required");
     NfChainArgs a = {};
     a.in = x; a.y = y; a.rows = rows; a.out = z; a.nll = nll; a.sdz = sdz; a.n = n; a.default_row = default_row; a.temp = 1.f;
@@ -426,6 +427,7 @@ int nf_inverse(const nf_model* m, const float* x, const float* y, const int32_t*
                float* z, float* logdet, void* stream) {
     int rc = check_ready(m);
     if (rc) return rc;
+    if (n == 0) return NF_OK;
     if (!x || !z) return fail(NF_ERR_INVALID, "x and z are required");
     NfChainArgs a = {};
     a.in = x; a.y = y; a.rows = rows; a.out = z; a.logdet = logdet; a.n = n; a.default_row = default_row; a.temp = 1.f;
@@ -436,6 +438,7 @@ int nf_forward(const nf_model* m, const float* z, const float* y, const int32_t*
                float* x, float* logdet, void* stream) {
     int rc = check_ready(m);
     if (rc) return rc;
+    if (n == 0) return NF_OK;
     if (!z || !x) return fail(NF_ERR_INVALID, "z and x are required");
     NfChainArgs a = {};
     a.in = z; a.y = y; a.rows = rows; a.out = x; a.logdet = logdet; a.n = n; a.default_row = default_row; a.temp = 1.f;
@@ -446,6 +449,7 @@ int nf_sample(const nf_model* m, const float* y, const int32_t* rows, int32_t de
               const float* eps, uint64_t seed, uint64_t offset, uint64_t patch_base, float* x, void* stream) {
     int rc = check_ready(m);
     if (rc) return rc;
+    if (n == 0) return NF_OK;
     if (!x) return fail(NF_ERR_INVALID, "x is required");
     NfChainArgs a = {};
     a.in = eps; a.y = y; a.rows = rows; a.out = x; a.n = n; a.default_row = default_row; a.temp = temp;
@@ -458,6 +462,7 @@ int nf_run_layers(const nf_model* m, int first, int last, int direction, const f
     int rc = check_ready(m);
     if (rc) return rc;
     if (first < 0 || last > (int)m->layers.size() || first >= last) return fail(NF_ERR_INVALID, "bad layer range [%d,%d)", first, last);
+    if (n == 0) return NF_OK;
     if (!in || !out) return fail(NF_ERR_INVALID, "in and out are required");
     if (direction != 0 && direction != 1) return fail(NF_ERR_INVALID, "direction must be 0 (inverse) or 1 (forward)");
     NfChainArgs a = {};

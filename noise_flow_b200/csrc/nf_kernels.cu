@@ -101,140 +101,25 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsign
     return o;
 }
 
-// ------------------------------------------------------------------------------------------------
-// one affine coupling (+ fused 1x1 mix) as a single pipelined pass over the 32 rows of the patch
-// ------------------------------------------------------------------------------------------------
-template <int SLOT, bool INV>
-__device__ __forceinline__ void coupling_pass(const NfModelParams& mp, WarpSmem& s, const int lane, float& ldj) {
-    const NfCouplingP& P = mp.cp[SLOT];
-    const bool has_mix = P.has_mix != 0;
+}  // namespace nf
+#include "nf_coupling.cuh"
+namespace nf {
 
-    // edge-indicator bias of conv2d_zeros by (row class, this lane's column class)
-    float b3t[4], b3m[4], b3b[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        b3t[o] = lane == 0 ? P.b3[0][0][o] : (lane == 31 ? P.b3[0][2][o] : P.b3[0][1][o]);
-        b3m[o] = lane == 0 ? P.b3[1][0][o] : (lane == 31 ? P.b3[1][2][o] : P.b3[1][1][o]);
-        b3b[o] = lane == 0 ? P.b3[2][0][o] : (lane == 31 ? P.b3[2][2][o] : P.b3[2][1][o]);
-    }
-
-    const float2 zero2 = make_float2(0.f, 0.f);
-    float2 c1a[4], c1b[4];   // conv-1 accumulators: output rows i-1 (a) and i (b) while consuming input row i
-    float2 c3a[4], c3b[4];   // conv-3 accumulators, same roles
-#pragma unroll
-    for (int o = 0; o < 4; ++o) { c1a[o] = c1b[o] = c3a[o] = c3b[o] = zero2; }
-
-#pragma unroll 1
-    for (int t = 0; t < 36; ++t) {
-        // ---------------- stage A: row t -> (mix) -> publish x0 = first two channels
-        if (t < 32) {
-            float4 z = s.z[t * 32 + lane];
-            if (INV && has_mix) {
-                z = mix4(z, P.a);
-                s.z[t * 32 + lane] = z;
-            }
-            s.xr[t & 1][lane + 1] = make_float2(z.x, z.y);
-        }
-        // ---------------- stage B: consume x0 row i = t-1, emit h2 row i-1
-        if (t >= 1 && t <= 33) {
-            const int i = t - 1;
-            float2 c1c[4];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) c1c[o] = zero2;
-            if (i <= 31) {
-                float2 xin[3];
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) xin[dx] = s.xr[i & 1][lane + dx];
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-                    for (int o = 0; o < 4; ++o) {
-                        c1a[o] = ffma2(xin[dx], ld2(&P.w1[2][dx][o][0]), c1a[o]);
-                        c1b[o] = ffma2(xin[dx], ld2(&P.w1[1][dx][o][0]), c1b[o]);
-                        c1c[o] = ffma2(xin[dx], ld2(&P.w1[0][dx][o][0]), c1c[o]);
-                    }
-                }
-            }
-            if (i >= 1) {
-                float h1[4];
-#pragma unroll
-                for (int o = 0; o < 4; ++o) h1[o] = fmaxf(c1a[o].x + c1a[o].y + P.b1[o], 0.f);
-                const float2 h01 = make_float2(h1[0], h1[1]), h23 = make_float2(h1[2], h1[3]);
-                float h2[4];
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    float2 u = ffma2(h01, ld2(&P.w2[o][0]), zero2);
-                    u = ffma2(h23, ld2(&P.w2[o][2]), u);
-                    h2[o] = fmaxf(u.x + u.y + P.b2[o], 0.f);
-                }
-                s.hr[(i - 1) & 1][lane + 1] = make_float4(h2[0], h2[1], h2[2], h2[3]);
-            }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) { c1a[o] = c1b[o]; c1b[o] = c1c[o]; }
-        }
-        // ---------------- stage C: consume h2 row j = t-3, finish output row j-1
-        if (t >= 3) {
-            const int j = t - 3;
-            float2 c3c[4];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) c3c[o] = zero2;
-            if (j <= 31) {
-                float4 hin[3];
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) hin[dx] = s.hr[j & 1][lane + dx];
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const float2 lo = make_float2(hin[dx].x, hin[dx].y), hi = make_float2(hin[dx].z, hin[dx].w);
-#pragma unroll
-                    for (int o = 0; o < 4; ++o) {
-                        c3a[o] = ffma2(lo, ld2(&P.w3[2][dx][o][0]), c3a[o]);
-                        c3a[o] = ffma2(hi, ld2(&P.w3[2][dx][o][2]), c3a[o]);
-                        c3b[o] = ffma2(lo, ld2(&P.w3[1][dx][o][0]), c3b[o]);
-                        c3b[o] = ffma2(hi, ld2(&P.w3[1][dx][o][2]), c3b[o]);
-                        c3c[o] = ffma2(lo, ld2(&P.w3[0][dx][o][0]), c3c[o]);
-                        c3c[o] = ffma2(hi, ld2(&P.w3[0][dx][o][2]), c3c[o]);
-                    }
-                }
-            }
-            if (j >= 1) {
-                const int q = j - 1;
-                float h3[4];
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const float b = q == 0 ? b3t[o] : (q == 31 ? b3b[o] : b3m[o]);
-                    h3[o] = c3a[o].x + c3a[o].y + b;
-                }
-                // shift = h3[0:2], log_scale = scale * tanh(h3[2:4])      (layers.py:362 / :342)
-                const float ls0 = P.scale * fast_tanh(h3[2]);
-                const float ls1 = P.scale * fast_tanh(h3[3]);
-                float4 z = s.z[q * 32 + lane];
-                if (INV) {
-                    z.z = fmaf(z.z, fast_exp(ls0), h3[0]);                 // layers.py:363-367
-                    z.w = fmaf(z.w, fast_exp(ls1), h3[1]);
-                    ldj += ls0 + ls1;                                      // layers.py:372
-                } else {
-                    z.z = (z.z - h3[0]) * fast_exp(-ls0);                  // layers.py:343-347
-                    z.w = (z.w - h3[1]) * fast_exp(-ls1);
-                    ldj -= ls0 + ls1;                                      // layers.py:352
-                    if (has_mix) z = mix4(z, P.ainv);                      // layers.py:113-114
-                }
-                s.z[q * 32 + lane] = z;
-            }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) { c3a[o] = c3b[o]; c3b[o] = c3c[o]; }
-        }
-        __syncwarp();
-    }
-}
-
+// Couplings 0..NF_FAST_SLOTS-1 get a templated copy of the pass: every weight then has a
+// compile-time offset in the parameter block (LDCU.128 with an immediate address feeding FFMA2
+// uniform-register operands; a run-time slot index makes ptxas fall back to per-thread LDC).  One loop
+// body per coupling means the resident warps must not drift apart: run_layer() ends with a
+// __syncthreads so all warps of the CTA (= of the SM) execute the same body at the same time -- without
+// it the 12 warps sat in 8 different bodies and the kernel was instruction-cache bound (ncu, round 1:
+// stall_no_instruction 1.6 per issue, icc hit rate 83 %).
+#define NF_FAST_SLOTS 8
 template <bool INV>
 __device__ __forceinline__ void coupling_dispatch(const NfModelParams& mp, WarpSmem& s, int lane, float& ldj, int slot) {
     switch (slot) {
-#define NF_CASE(K) case K: coupling_pass<K, INV>(mp, s, lane, ldj); break;
+#define NF_CASE(K) case K: coupling_pass<INV>(mp.cp[K], s, lane, ldj); break;
         NF_CASE(0) NF_CASE(1) NF_CASE(2) NF_CASE(3) NF_CASE(4) NF_CASE(5) NF_CASE(6) NF_CASE(7)
-        NF_CASE(8) NF_CASE(9) NF_CASE(10) NF_CASE(11) NF_CASE(12) NF_CASE(13) NF_CASE(14) NF_CASE(15)
 #undef NF_CASE
-        default: break;
+        default: coupling_pass<INV>(mp.cp[slot], s, lane, ldj); break;   // run-time slot: per-thread LDC weight fetches
     }
 }
 
@@ -295,7 +180,7 @@ __device__ __forceinline__ void run_layer(const NfModelParams& mp, const NfChain
             break;
         default: break;
     }
-    __syncwarp();
+    __syncthreads();   // layer boundary: keeps the CTA's warps in the same loop body (I-cache), orders smem
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -315,8 +200,13 @@ nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
     }
     __syncwarp();
 
+    // The patch loop runs on a CTA-uniform counter so that ptxas keeps the layer program and the weight
+    // fetches on the uniform datapath; trailing warps without a patch of their own recompute the last
+    // patch and only their stores are predicated off.
     const long long stride = (long long)gridDim.x * warps_per_cta;
-    for (long long p = (long long)blockIdx.x * warps_per_cta + warp; p < a.n; p += stride) {
+    for (long long base = (long long)blockIdx.x * warps_per_cta; base < a.n; base += stride) {
+        const bool active = base + warp < a.n;
+        const long long p = active ? base + warp : a.n - 1;
         int row = a.rows ? a.rows[p] : a.default_row;
         row = min(max(row, 0), NF_MAX_ROWS - 1);
 
@@ -348,7 +238,7 @@ nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
 
         // ---- epilogue: store the patch, reduce log-det / prior / latent statistics
         float s1 = 0.f, s2 = 0.f;
-        float4* dst = a.out ? reinterpret_cast<float4*>(a.out) + p * NF_PIXELS : nullptr;
+        float4* dst = (a.out && active) ? reinterpret_cast<float4*>(a.out) + p * NF_PIXELS : nullptr;
 #pragma unroll 8
         for (int r = 0; r < 32; ++r) {
             const float4 z = s.z[r * 32 + lane];
@@ -358,7 +248,7 @@ nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
         }
         ldj = warp_sum(ldj);
         if (a.nll || a.sdz) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
-        if (lane == 0) {
+        if (lane == 0 && active) {
             const float logdet = ldj + (INV ? a.ldj_const : -a.ldj_const);
             if (a.logdet) a.logdet[p] = logdet;
             if (a.nll) {   // -(logdet + sum -0.5 (log 2pi + z^2))       noise_flow_model.py:474-475,537-539

@@ -30,7 +30,7 @@ enum NfKernelOp : int32_t {
 // direction) by the invertible 1x1 conv / channel permutation that the reference places before
 // every 'unc' coupling (noise_flow_model.py:79-104).  Weight layouts are [.. out][in] so that an
 // (in0,in1) pair is one float2 -> packed fma.rn.f32x2 over input-channel pairs.
-struct NfCouplingP {
+struct alignas(16) NfCouplingP {
     float a[4][4];          // mix, inverse direction:  out[o] = sum_i z[i] * a[o][i]   (= A[i][o])
     float ainv[4][4];       // mix, forward direction:  out[o] = sum_i z[i] * ainv[o][i] (= A_inv[i][o])
     float w1[3][3][4][2];   // conv 3x3 SAME 2->4, BN1 folded: [dy][dx][o][i]
@@ -60,8 +60,8 @@ struct NfModelParams {
     int32_t n_layers;
     int32_t n_rows;
     int32_t pad_[2];
-    uint8_t op[NF_MAX_LAYERS];     // NfKernelOp, in data->latent (inverse) order
-    uint8_t slot[NF_MAX_LAYERS];
+    int32_t op[NF_MAX_LAYERS];     // NfKernelOp, in data->latent (inverse) order (int32: uniform LDCU indexing)
+    int32_t slot[NF_MAX_LAYERS];
     NfCouplingP cp[NF_MAX_COUPLINGS];
     NfMixP mix[NF_MAX_MIX];
     NfScaleP sc[NF_MAX_SCALE];

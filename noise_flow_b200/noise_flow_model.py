@@ -123,7 +123,10 @@ class NoiseFlow(object):
                     missing names are initialised exactly as the reference initialises them.
     ``first_call``  which graph function is traced first and therefore fixes the ``real_nvp_conv_template[_k]``
                     checkpoint names (``tf.make_template`` names scopes at first call): ``'inverse'`` for a
-                    training script (loss first), ``'forward'`` for ``NoiseFlowWrapper`` (sample only).
+                    training script (loss first, train_noise_flow.py:302) -- the default, and the order every
+                    checkpoint is written under; ``'forward'`` reproduces a sample-only graph
+                    (``NoiseFlowWrapper``).  The order is fixed here, explicitly; it does NOT depend on which
+                    method of this object happens to be called first.
     """
 
     def __init__(self, x_shape, is_training, hps=None, variables: Optional[Dict[str, np.ndarray]] = None,
@@ -259,7 +262,7 @@ class NoiseFlow(object):
     def forward(self, z, eps_std=None, yy=None, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None):
         """noise_flow_model.py:430-447 (``eps_std`` only matters for multi-level models, as in the reference)."""
         self._check_training(is_training)
-        self.build("forward")
+        self.build()
         z, yy = self._dev(z, "z"), self._dev(yy, "yy")
         n = z.shape[0]
         rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
@@ -279,7 +282,7 @@ class NoiseFlow(object):
         Philox4x32-10 keyed by ``seed`` (default: the constructor seed) and ``offset`` (default: a per-model
         call counter, so successive calls give fresh noise like ``tf.random_normal``)."""
         self._check_training(is_training)
-        self.build("forward")
+        self.build()
         y = self._dev(y, "y")
         yy = self._dev(yy, "yy") if yy is not None else None
         n = y.shape[0]

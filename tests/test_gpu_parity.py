@@ -241,7 +241,7 @@ def test_squeeze_unsqueeze_bit_exact(stype, factor):
 
 def test_wrapper_drop_in(golden_dir, shipped):
     """NoiseFlowWrapper(path, temp).sample_noise_nf(batch_x, b1, b2, iso, cam) -> np.float32 [N,32,32,4]."""
-    from noise_flow_b200 import NoiseFlowWrapper
+    from noise_flow_b200.NoiseFlowWrapper import NoiseFlowWrapper   # same import path shape as the reference
     hps, ck = shipped
     w = NoiseFlowWrapper(os.path.join(golden_dir, "NoiseFlow"), sampling_temperature=0.6)
     assert w.is_cond and w.temp == 0.6 and w.x_shape == [None, 32, 32, 4]
