@@ -14,8 +14,9 @@
  * thread-local human-readable message.  Nothing here throws, exits or prints.  Entry points are
  * re-entrant: a finalized model may be used concurrently from many host threads (the reference is
  * driven by 16-32 Python threads sharing one session: train_noise_flow.py:38-47,
- * train_dncnn_noiseflow.py:195-198); mutation (nf_model_add_*, nf_model_set_*) must not race with
- * launches on the same handle.
+ * train_dncnn_noiseflow.py:195-198).  nf_model_set_* may run concurrently with launches (every launch
+ * snapshots the parameter block under a lock and carries it by value); nf_model_add_* / finalize /
+ * destroy must not race with anything on the same handle.
  *
  * Tensor layout: NHWC float32, patch = [32][32][4] (sidd patches: train_noise_flow.py:287-288).
  * Naming follows the reference: "inverse" = data -> latent (likelihood direction),
@@ -126,6 +127,21 @@ int nf_run_layers(const nf_model* m, int first, int last, int direction, const f
 /* tf.reduce_mean pieces (noise_flow_model.py:478,484), deterministic fp64:
  * sums[0] = sum nll, sums[1] = sum sdz, sums[2] = n  (device double[3]; either input may be NULL). */
 int nf_reduce_sums(const float* nll, const float* sdz, int64_t n, double* sums, void* stream);
+
+/* The whole chain with BATCH-STATISTICS BatchNorm -- the reference's is_training == True path
+ * (batch_norm, layers.py:388-398), which is what NoiseFlowWrapper.sample_noise_nf feeds
+ * (NoiseFlowWrapper.py:85-86) and what train_thread runs (train_noise_flow.py:64-71).  Patches are not
+ * independent in this mode, so the chain executes layer by layer: every coupling is probed twice (batch mean /
+ * population variance of its conv-1 and conv-2 outputs) and then applied with those statistics.
+ * direction 0: x -> z, outputs as nf_log_prob / nf_inverse; direction 1: z = in * temp (in == NULL: Philox
+ * as nf_sample) -> x.  `out` ([n][32][32][4], required) doubles as the in-place state buffer; stats_ws is a
+ * device double[8] scratch.  batch_stats_host (optional, host) receives [n_couplings][16] =
+ * {mean1[4], var1[4], mean2[4], var2[4]} per coupling in add order so that the caller can apply the
+ * moving-average update train_m -= 0.1 * (train_m - m) (layers.py:394-395).  Synchronises `stream`. */
+int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, const float* y, const int32_t* rows,
+                         int32_t default_row, int64_t n, float temp, uint64_t seed, uint64_t offset,
+                         uint64_t patch_base, float* out, float* logdet, float* nll, float* sdz, double* stats_ws,
+                         float* batch_stats_host, void* stream);
 
 /* squeeze2d / unsqueeze2d (borealisflows/utils.py:30-86): bit-exact index permutation.
  * squeeze_type: 0 = 'chessboard' (also the unknown-type fallback), 1 = 'patch'.

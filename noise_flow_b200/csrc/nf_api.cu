@@ -7,7 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdarg.h>
+#include <algorithm>
 #include <mutex>
+#include <utility>
 #include <new>
 #include <vector>
 
@@ -42,6 +44,11 @@ struct Layer {
     double log_abs_det = 0.0;   // per pixel (conv1x1), 0 for permutations
     // coupling (folded)
     NfCouplingP cp = {};
+    // reference-shaped copy, kept so that BatchNorm can be re-folded with batch statistics (is_training)
+    struct Raw {
+        float l1_w[72], l1_b[4], bn1_mean[4], bn1_var[4], l2_w[16], l2_b[4], bn2_mean[4], bn2_var[4];
+        float last_w[180], last_b[4], last_logs[4], rescaling_scale, bn_eps;
+    } raw = {};
     // scale
     int scale_kind = 0, full_sum = 1, n_rows = 0;
     float table[NF_MAX_ROWS][4] = {};
@@ -58,6 +65,7 @@ struct nf_model {
     NfModelParams full = {};     // fused program of the whole chain
     float full_ldj_const = 0.f;
     std::mutex pool_mu;          // guards the _host staging pool
+    mutable std::mutex prog_mu;  // guards `layers` / `full` against a concurrent nf_model_set_* (launches snapshot)
     struct Staging {
         float *x = nullptr, *y = nullptr, *z = nullptr, *nll = nullptr, *sdz = nullptr;
         int32_t* rows = nullptr;
@@ -120,6 +128,27 @@ int fold_coupling(const nf_coupling_weights* w, NfCouplingP* out) {
     return NF_OK;
 }
 
+void keep_raw(Layer& L, const nf_coupling_weights* w) {
+    memcpy(L.raw.l1_w, w->l1_w, sizeof(L.raw.l1_w));       memcpy(L.raw.l1_b, w->l1_b, sizeof(L.raw.l1_b));
+    memcpy(L.raw.bn1_mean, w->bn1_mean, 16);               memcpy(L.raw.bn1_var, w->bn1_var, 16);
+    memcpy(L.raw.l2_w, w->l2_w, sizeof(L.raw.l2_w));       memcpy(L.raw.l2_b, w->l2_b, sizeof(L.raw.l2_b));
+    memcpy(L.raw.bn2_mean, w->bn2_mean, 16);               memcpy(L.raw.bn2_var, w->bn2_var, 16);
+    memcpy(L.raw.last_w, w->last_w, sizeof(L.raw.last_w)); memcpy(L.raw.last_b, w->last_b, sizeof(L.raw.last_b));
+    memcpy(L.raw.last_logs, w->last_logs, 16);
+    L.raw.rescaling_scale = w->rescaling_scale;
+    L.raw.bn_eps = w->bn_eps;
+}
+
+// Re-fold a coupling with explicit BatchNorm statistics: bn = {mean1[4], var1[4], mean2[4], var2[4]}.
+int refold_with_stats(const Layer& L, const float* bn, NfCouplingP* out) {
+    nf_coupling_weights w;
+    w.l1_w = L.raw.l1_w; w.l1_b = L.raw.l1_b; w.bn1_mean = bn; w.bn1_var = bn + 4;
+    w.l2_w = L.raw.l2_w; w.l2_b = L.raw.l2_b; w.bn2_mean = bn + 8; w.bn2_var = bn + 12;
+    w.last_w = L.raw.last_w; w.last_b = L.raw.last_b; w.last_logs = L.raw.last_logs;
+    w.rescaling_scale = L.raw.rescaling_scale; w.bn_eps = L.raw.bn_eps;
+    return fold_coupling(&w, out);
+}
+
 void identity4(float m[4][4]) {
     for (int o = 0; o < 4; ++o)
         for (int i = 0; i < 4; ++i) m[o][i] = o == i ? 1.f : 0.f;
@@ -148,7 +177,8 @@ int set_scale_table(Layer& L, const float* table, int n_rows) {
 
 // Build the kernel program for the bijectors [first, last): a conv1x1 / permutation that is
 // immediately followed (data->latent order) by a coupling inside the range is fused into it.
-int build_program(const nf_model* m, int first, int last, NfModelParams* mp, float* ldj_const) {
+int build_program(const nf_model* m, int first, int last, NfModelParams* mp, float* ldj_const,
+                  int bn_layer = -1, const float* bn_stats = nullptr) {
     memset(mp, 0, sizeof(*mp));
     double ldj = 0.0;
     int n_cp = 0, n_mix = 0, n_sc = 0, n_ops = 0, n_rows = 0;
@@ -168,6 +198,10 @@ int build_program(const nf_model* m, int first, int last, NfModelParams* mp, flo
             if (n_cp >= NF_MAX_COUPLINGS) return fail(NF_ERR_UNSUPPORTED, "more than %d couplings", NF_MAX_COUPLINGS);
             NfCouplingP& C = mp->cp[n_cp];
             C = L.cp;
+            if (l == bn_layer) {   // batch-statistics BatchNorm for this coupling
+                int rcf = refold_with_stats(L, bn_stats, &C);
+                if (rcf) return rcf;
+            }
             const bool fused = l > first && (m->layers[l - 1].kind == L_CONV1X1 || m->layers[l - 1].kind == L_PERMUTE);
             if (fused) {
                 memcpy(C.a, m->layers[l - 1].a, sizeof(C.a));
@@ -215,17 +249,26 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
     if (a.default_row < 0 || a.default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
     cudaError_t e;
     if (first == 0 && last == (int)m->layers.size()) {
+        NfModelParams mp;   // snapshot under the lock: parameters travel by value with the launch
+        {
+            std::lock_guard<std::mutex> lock(m->prog_mu);
+            mp = m->full;
+            a.ldj_const = m->full_ldj_const;
+        }
         a.first_layer = 0;
-        a.last_layer = m->full.n_layers;
-        a.ldj_const = m->full_ldj_const;
-        if (a.in && nf::program_is_scale_only(m->full, 0, m->full.n_layers))
-            e = nf::launch_scale_stream(m->full, a, inverse, m->sm_count, stream);   // HBM-bound streaming path
+        a.last_layer = mp.n_layers;
+        if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
+            e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);   // HBM-bound streaming path
         else
-            e = nf::launch_chain(m->full, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
+            e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
     } else {
         NfModelParams mp;
         float ldj = 0.f;
-        int rc = build_program(m, first, last, &mp, &ldj);
+        int rc;
+        {
+            std::lock_guard<std::mutex> lock(m->prog_mu);
+            rc = build_program(m, first, last, &mp, &ldj);
+        }
         if (rc) return rc;
         a.first_layer = 0;
         a.last_layer = mp.n_layers;
@@ -341,6 +384,7 @@ int nf_model_add_affine_coupling(nf_model* m, const nf_coupling_weights* w) {
     Layer L;
     L.kind = L_COUPLING;
     int rc = fold_coupling(w, &L.cp);
+    if (!rc) keep_raw(L, w);
     if (rc) return rc;
     m->layers.push_back(L);
     m->finalized = false;
@@ -364,7 +408,11 @@ int nf_model_add_scale(nf_model* m, int kind, int logdet_full_sum, const float* 
 int nf_model_finalize(nf_model* m) {
     if (!m) return fail(NF_ERR_INVALID, "null model");
     if (m->layers.empty()) return fail(NF_ERR_STATE, "model has no layers");
-    int rc = build_program(m, 0, (int)m->layers.size(), &m->full, &m->full_ldj_const);
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(m->prog_mu);
+        rc = build_program(m, 0, (int)m->layers.size(), &m->full, &m->full_ldj_const);
+    }
     if (rc) return rc;
     if (m->sm_count == 0) {
         int sms = 0;
@@ -383,21 +431,34 @@ static int refinalize(nf_model* m) { return m->finalized ? nf_model_finalize(m) 
 int nf_model_set_conv1x1(nf_model* m, int layer, const float* A, const float* A_inv, float log_abs_det) {
     if (!m || layer < 0 || layer >= (int)m->layers.size() || m->layers[layer].kind != L_CONV1X1)
         return fail(NF_ERR_INVALID, "layer %d is not a conv1x1", layer);
-    int rc = fill_conv1x1(m->layers[layer], A, A_inv, log_abs_det);
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(m->prog_mu);
+        rc = fill_conv1x1(m->layers[layer], A, A_inv, log_abs_det);
+    }
     return rc ? rc : refinalize(m);
 }
 
 int nf_model_set_affine_coupling(nf_model* m, int layer, const nf_coupling_weights* w) {
     if (!m || layer < 0 || layer >= (int)m->layers.size() || m->layers[layer].kind != L_COUPLING)
         return fail(NF_ERR_INVALID, "layer %d is not an affine coupling", layer);
-    int rc = fold_coupling(w, &m->layers[layer].cp);
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(m->prog_mu);
+        rc = fold_coupling(w, &m->layers[layer].cp);
+        if (!rc) keep_raw(m->layers[layer], w);
+    }
     return rc ? rc : refinalize(m);
 }
 
 int nf_model_set_scale(nf_model* m, int layer, const float* table, int n_rows) {
     if (!m || layer < 0 || layer >= (int)m->layers.size() || m->layers[layer].kind != L_SCALE)
         return fail(NF_ERR_INVALID, "layer %d is not a scale layer", layer);
-    int rc = set_scale_table(m->layers[layer], table, n_rows);
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(m->prog_mu);
+        rc = set_scale_table(m->layers[layer], table, n_rows);
+    }
     return rc ? rc : refinalize(m);
 }
 
@@ -587,6 +648,104 @@ int nf_sample_host(const nf_model* cm, const float* y_host, const int32_t* rows_
         NF_CUDA(cudaEventRecord(s.done, s.stream));
     }
     for (auto& s : m->st) NF_CUDA(cudaStreamSynchronize(s.stream));
+    return NF_OK;
+}
+
+// ---- batch-statistics BatchNorm: layer-by-layer execution ----------------------------------------------
+// Reference: batch_norm(training=True) normalises every coupling-net activation with the statistics of the
+// CURRENT batch (layers.py:388-398), which makes patches interdependent: 16 batch-wide reductions per
+// pass.  Each coupling therefore runs as probe(conv-1 stats) -> probe(conv-2 stats) -> apply.
+int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, const float* y, const int32_t* rows,
+                         int32_t default_row, int64_t n, float temp, uint64_t seed, uint64_t offset, uint64_t patch_base,
+                         float* out, float* logdet, float* nll, float* sdz, double* stats_ws, float* batch_stats_host,
+                         void* stream_) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (direction != 0 && direction != 1) return fail(NF_ERR_INVALID, "direction must be 0 (inverse) or 1 (forward)");
+    if (n == 0) return NF_OK;
+    if (n < 0 || !out || !stats_ws) return fail(NF_ERR_INVALID, "out and stats_ws are required");
+    if (direction == 0 && !in) return fail(NF_ERR_INVALID, "in is required for the inverse direction");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool inverse = direction == 0;
+    const int L = (int)m->layers.size();
+    // groups of bijectors that form one kernel op: [mix, coupling] pairs, or single layers
+    std::vector<std::pair<int, int>> groups;
+    for (int l = 0; l < L;) {
+        const bool mix = m->layers[l].kind == L_CONV1X1 || m->layers[l].kind == L_PERMUTE;
+        if (mix && l + 1 < L && m->layers[l + 1].kind == L_COUPLING) { groups.push_back({l, l + 2}); l += 2; }
+        else { groups.push_back({l, l + 1}); l += 1; }
+    }
+    if (!inverse) std::reverse(groups.begin(), groups.end());
+    float* run_ld = logdet ? logdet : nll;   // running log-det (nll doubles as scratch until the last launch)
+    const bool want_ld = run_ld != nullptr;
+    const double cnt = (double)n * NF_PIXELS;
+    int n_cp = 0;
+    for (int l = 0; l < L; ++l) n_cp += m->layers[l].kind == L_COUPLING;
+    bool first = true;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        const int lo = groups[g].first, hi = groups[g].second;
+        const int cl = m->layers[hi - 1].kind == L_COUPLING ? hi - 1 : -1;
+        float bn[16];
+        if (cl >= 0) {
+            for (int k = 0; k < 4; ++k) { bn[k] = 0.f; bn[8 + k] = 0.f; }
+            const float ident = 1.0f - m->layers[cl].raw.bn_eps;   // identity fold: 1/sqrt(var + eps) == 1
+            for (int k = 0; k < 4; ++k) { bn[4 + k] = ident; bn[12 + k] = ident; }
+            for (int stage = 1; stage <= 2; ++stage) {
+                NfModelParams mp;
+                float ldjc = 0.f;
+                {
+                    std::lock_guard<std::mutex> lock(m->prog_mu);
+                    rc = build_program(m, lo, hi, &mp, &ldjc, cl, bn);
+                }
+                if (rc) return rc;
+                NF_CUDA(cudaMemsetAsync(stats_ws, 0, 8 * sizeof(double), stream));
+                NfChainArgs a = {};
+                a.in = first ? in : out; a.y = y; a.rows = rows; a.n = n; a.default_row = default_row;
+                a.temp = first ? temp : 1.f; a.seed = seed; a.offset = offset; a.patch_base = patch_base;
+                a.first_layer = 0; a.last_layer = mp.n_layers; a.bn_stats = stats_ws; a.bn_stage = stage;
+                if (!a.y && range_has_sdn(m, lo, hi)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
+                cudaError_t e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
+                if (e != cudaSuccess) return fail(NF_ERR_CUDA, "probe launch: %s", cudaGetErrorString(e));
+                double h[8];
+                NF_CUDA(cudaMemcpyAsync(h, stats_ws, sizeof(h), cudaMemcpyDeviceToHost, stream));
+                NF_CUDA(cudaStreamSynchronize(stream));
+                for (int k = 0; k < 4; ++k) {
+                    const double mean = h[k] / cnt;
+                    double var = h[4 + k] / cnt - mean * mean;   // population variance (tf.nn.moments)
+                    if (var < 0.0) var = 0.0;
+                    bn[(stage - 1) * 8 + k] = (float)mean;
+                    bn[(stage - 1) * 8 + 4 + k] = (float)var;
+                }
+            }
+            if (batch_stats_host) {
+                int idx = 0;
+                for (int l = 0; l < cl; ++l) idx += m->layers[l].kind == L_COUPLING;
+                memcpy(batch_stats_host + 16 * idx, bn, sizeof(bn));
+            }
+        }
+        NfModelParams mp;
+        float ldjc = 0.f;
+        {
+            std::lock_guard<std::mutex> lock(m->prog_mu);
+            rc = build_program(m, lo, hi, &mp, &ldjc, cl, cl >= 0 ? bn : nullptr);
+        }
+        if (rc) return rc;
+        const bool last = g + 1 == groups.size();
+        NfChainArgs a = {};
+        a.in = first ? in : out; a.y = y; a.rows = rows; a.out = out; a.n = n; a.default_row = default_row;
+        a.temp = first ? temp : 1.f; a.seed = seed; a.offset = offset; a.patch_base = patch_base;
+        a.first_layer = 0; a.last_layer = mp.n_layers; a.ldj_const = ldjc;
+        a.logdet_in = (want_ld && !first) ? run_ld : nullptr;
+        if (last) { a.logdet = logdet; a.nll = inverse ? nll : nullptr; a.sdz = inverse ? sdz : nullptr; }
+        else a.logdet = want_ld ? run_ld : nullptr;
+        if (!a.y && range_has_sdn(m, lo, hi)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
+        if (a.default_row < 0 || a.default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
+        cudaError_t e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
+        if (e != cudaSuccess) return fail(NF_ERR_CUDA, "chain launch: %s", cudaGetErrorString(e));
+        first = false;
+    }
+    NF_CUDA(cudaStreamSynchronize(stream));
+    (void)n_cp;
     return NF_OK;
 }
 

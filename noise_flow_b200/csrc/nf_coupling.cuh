@@ -34,16 +34,20 @@ __device__ __forceinline__ B3 load_b3(const CP& P, int lane) {
     return b;
 }
 
-template <bool INV, bool GUARDED, class CP>
+// STATS: 0 = normal step.  1 / 2 = batch-statistics probe (reference batch_norm(training=True),
+// layers.py:388-398): accumulate sum and sum-of-squares of the conv-1 (1) or conv-2 (2) output BEFORE its
+// BatchNorm into stats[0..3] / stats[4..7]; nothing is published and stage C does not run.  The caller folds
+// the BatchNorm under probe as the identity, so the folded activation IS the raw pre-BN activation.
+template <bool INV, bool GUARDED, int STATS = 0, class CP>
 __device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const int lane, const int t, const bool has_mix,
                                               Acc4& b_old, Acc4& b_mid, Acc4& c_old, Acc4& c_mid, const B3& b3,
-                                              float& ldj) {
+                                              float& ldj, float* stats = nullptr) {
     const float2 zero2 = make_float2(0.f, 0.f);
     const bool do_a = !GUARDED || t < 32;
     const bool b_fma = !GUARDED || (t >= 1 && t <= 32);
     const bool b_emit = !GUARDED || (t >= 2 && t <= 33);
-    const bool c_fma = !GUARDED || (t >= 3 && t <= 34);
-    const bool c_emit = !GUARDED || t >= 4;
+    const bool c_fma = STATS == 0 && (!GUARDED || (t >= 3 && t <= 34));
+    const bool c_emit = STATS == 0 && (!GUARDED || t >= 4);
     // ---------------- stage A
     if (do_a) {
         float4 z = s.z[t * 32 + lane];
@@ -85,16 +89,22 @@ __device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const in
         const int r = t - 2;
         float h1[4];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) h1[o] = fmaxf(fin.v[o].x + fin.v[o].y + P.b1[o], 0.f);   // BN folded, ReLU
+        for (int o = 0; o < 4; ++o) {
+            const float c1 = fin.v[o].x + fin.v[o].y + P.b1[o];
+            if (STATS == 1) { stats[o] += c1; stats[4 + o] = fmaf(c1, c1, stats[4 + o]); }
+            h1[o] = fmaxf(c1, 0.f);                                                          // BN folded, ReLU
+        }
         const float2 h01 = make_float2(h1[0], h1[1]), h23 = make_float2(h1[2], h1[3]);
         float h2[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
             float2 u = ffma2(h01, ld2(&P.w2[o][0]), zero2);
             u = ffma2(h23, ld2(&P.w2[o][2]), u);
-            h2[o] = fmaxf(u.x + u.y + P.b2[o], 0.f);
+            const float c2 = u.x + u.y + P.b2[o];
+            if (STATS == 2) { stats[o] += c2; stats[4 + o] = fmaf(c2, c2, stats[4 + o]); }
+            h2[o] = fmaxf(c2, 0.f);
         }
-        s.hr[r & 1][lane + 1] = make_float4(h2[0], h2[1], h2[2], h2[3]);
+        if (STATS == 0) s.hr[r & 1][lane + 1] = make_float4(h2[0], h2[1], h2[2], h2[3]);
     }
     // ---------------- stage C
     Acc4 cfin = c_old;
@@ -161,6 +171,20 @@ __device__ __forceinline__ void coupling_pass(const CP& P, WarpSmem& s, const in
         if (t >= 5 && t < 32) coupling_step<INV, false>(P, s, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj);
         else                  coupling_step<INV, true>(P, s, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj);
     }
+}
+
+// Batch-statistics probe of one coupling: rows 0..31 of the conv-1 / conv-2 pre-BN activation.
+template <bool INV, int STAGE, class CP>
+__device__ __forceinline__ void coupling_stats_pass(const CP& P, WarpSmem& s, const int lane, float* stats) {
+    const bool has_mix = P.has_mix != 0;
+    B3 b3 = {};
+    Acc4 b_old, b_mid, c_old, c_mid;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) b_old.v[o] = b_mid.v[o] = c_old.v[o] = c_mid.v[o] = make_float2(0.f, 0.f);
+    float ldj = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < 34; ++t)
+        coupling_step<INV, true, STAGE>(P, s, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, stats);
 }
 
 }  // namespace nf

@@ -167,8 +167,15 @@ __device__ __forceinline__ void gain_pass(float g, float ginv, float ldj_inv, Wa
 
 template <bool INV>
 __device__ __forceinline__ void run_layer(const NfModelParams& mp, const NfChainArgs& a, WarpSmem& s, int lane,
-                                          int l, long long p, int row, float& ldj) {
+                                          int l, long long p, int row, float& ldj, float* stats) {
     const int op = mp.op[l], slot = mp.slot[l];
+    const bool probe = a.bn_stage != 0 && op == NF_KOP_COUPLING && l == (INV ? a.last_layer - 1 : a.first_layer);
+    if (probe) {   // batch-statistics BatchNorm: measure, do not transform (single compact copy, run-time slot)
+        if (a.bn_stage == 1) coupling_stats_pass<INV, 1>(mp.cp[slot], s, lane, stats);
+        else                 coupling_stats_pass<INV, 2>(mp.cp[slot], s, lane, stats);
+        __syncthreads();
+        return;
+    }
     switch (op) {
         case NF_KOP_COUPLING: coupling_dispatch<INV>(mp, s, lane, ldj, slot); break;
         case NF_KOP_MIX: mix_pass<INV>(mp.mix[slot], s, lane); break;
@@ -230,12 +237,22 @@ nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
         __syncwarp();
 
         float ldj = 0.f;
+        float stats[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (INV) {
-            for (int l = a.first_layer; l < a.last_layer; ++l) run_layer<true>(mp, a, s, lane, l, p, row, ldj);
+            for (int l = a.first_layer; l < a.last_layer; ++l) run_layer<true>(mp, a, s, lane, l, p, row, ldj, stats);
         } else {
-            for (int l = a.last_layer - 1; l >= a.first_layer; --l) run_layer<false>(mp, a, s, lane, l, p, row, ldj);
+            for (int l = a.last_layer - 1; l >= a.first_layer; --l) run_layer<false>(mp, a, s, lane, l, p, row, ldj, stats);
         }
 
+        if (a.bn_stage != 0) {   // probe launch: publish this patch's per-channel sums, nothing else
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float v = warp_sum(stats[k]);
+                if (lane == 0 && active) atomicAdd(a.bn_stats + k, (double)v);
+            }
+            __syncwarp();
+            continue;
+        }
         // ---- epilogue: store the patch, reduce log-det / prior / latent statistics
         float s1 = 0.f, s2 = 0.f;
         float4* dst = (a.out && active) ? reinterpret_cast<float4*>(a.out) + p * NF_PIXELS : nullptr;
@@ -249,7 +266,7 @@ nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
         ldj = warp_sum(ldj);
         if (a.nll || a.sdz) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
         if (lane == 0 && active) {
-            const float logdet = ldj + (INV ? a.ldj_const : -a.ldj_const);
+            const float logdet = ldj + (INV ? a.ldj_const : -a.ldj_const) + (a.logdet_in ? a.logdet_in[p] : 0.f);
             if (a.logdet) a.logdet[p] = logdet;
             if (a.nll) {   // -(logdet + sum -0.5 (log 2pi + z^2))       noise_flow_model.py:474-475,537-539
                 const float logp = -0.5f * (NF_DIMS * 1.8378770664093453f + s2);

@@ -83,4 +83,10 @@ struct NfChainArgs {
     int32_t default_row;
     float ldj_const;          // host-computed constant log-det of the range (1x1 convs)
     float temp;               // forward: z = in * temp
+    // batch-statistics BatchNorm support (layer-by-layer execution, see nf_chain_batch_stats in nf_api.cu)
+    const float* logdet_in;   // [n] log-det accumulated by earlier launches (may be null)
+    double* bn_stats;         // double[8]: per-channel sum and sum of squares of a pre-BN activation
+    int32_t bn_stage;         // 0 = normal run; 1 / 2 = the LAST op of the range is a coupling: accumulate the
+                              // statistics of its conv-1 / conv-2 output (before BatchNorm) and stop there
+    int32_t pad_;
 };

@@ -86,7 +86,7 @@ class _Engine:
             tab = np.ascontiguousarray(self.spec.scale_table(self.spec.layers[idx], extra), np.float32)
             _lib.check(self.lib.nf_model_set_scale(self.handle, idx, _fp(tab), tab.shape[0]), "nf_model_set_scale")
 
-    def refresh_parameters(self):
+    def refresh_parameters(self, extra=None):
         """Re-upload every layer from the variable store (after an optimizer step / BN update)."""
         lib, h = self.lib, self.handle
         for idx, l in enumerate(self.spec.layers):
@@ -98,7 +98,7 @@ class _Engine:
                 st, keep = self._coupling_struct(l)
                 _lib.check(lib.nf_model_set_affine_coupling(h, idx, C.byref(st)), "nf_model_set_affine_coupling")
                 del keep
-        self.update_scale_tables(None)
+        self.update_scale_tables(extra)
 
     def __del__(self):
         try:
@@ -176,21 +176,51 @@ class NoiseFlow(object):
     def refresh_parameters(self):
         if self._engine is not None:
             with self._lock:
-                self._engine.refresh_parameters()
+                self._engine.refresh_parameters(self._extra_rows)
 
     def set_launch(self, warps_per_cta: int = 12, num_ctas: int = 0):
         self.build()
         _lib.check(self._engine.lib.nf_model_set_launch(self._engine.handle, warps_per_cta, num_ctas), "nf_model_set_launch")
 
     # ------------------------------------------------------------------ helpers
-    def _check_training(self, is_training):
+    def _check_training(self, is_training) -> bool:
+        """Resolve the reference's ``is_training`` placeholder (constructor value unless overridden per call)."""
         t = self._is_training if is_training is None else is_training
         if callable(t):
             t = t()
-        if bool(t):
-            raise NotImplementedError(
-                "batch-statistics BatchNorm (is_training=True, reference layers.py:388-398) is not implemented by "
-                "the fused kernels yet; pass is_training=False for the moving-statistics path")
+        return bool(t)
+
+    def _batch_stats_chain(self, direction, inp, yy, rows, drow, n, temp=1.0, seed=0, offset=0, patch_base=0,
+                           want_nll=False, want_logdet=False):
+        """``is_training == True``: BatchNorm normalises with the statistics of THIS batch (layers.py:388-398) and,
+        as a side effect, moves the stored statistics towards them: ``train_m -= 0.1 * (train_m - m)`` (:394-395).
+        The chain runs layer by layer (two probe launches + one apply launch per coupling)."""
+        e = self._engine
+        out = torch.empty((n, 32, 32, 4), device=self.device, dtype=torch.float32)
+        ws = torch.zeros(8, device=self.device, dtype=torch.float64)
+        nll = torch.empty(n, device=self.device, dtype=torch.float32) if want_nll else None
+        sdz = torch.empty(n, device=self.device, dtype=torch.float32) if want_nll else None
+        ld = torch.empty(n, device=self.device, dtype=torch.float32) if want_logdet else None
+        cps = [l for l in self.spec.layers if l.kind == "coupling"]
+        bstats = np.zeros((max(len(cps), 1), 16), dtype=np.float32)
+        p = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(e.lib.nf_chain_batch_stats(
+                e.handle, direction, p(inp), p(yy), p(rows), drow, n, float(temp), int(seed), int(offset),
+                int(patch_base), out.data_ptr(), p(ld), p(nll), p(sdz), ws.data_ptr(),
+                bstats.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)), "nf_chain_batch_stats")
+        if n > 0:
+            with self._lock:   # moving-average update (decay 0.1), then re-fold the moving-statistics engine
+                v = self.spec.store.vars
+                for k, l in enumerate(cps):
+                    s = l.data["template"]
+                    for j, name in enumerate(("bn_nvp_conv_1/mean", "bn_nvp_conv_1/var", "bn_nvp_conv_2/mean",
+                                              "bn_nvp_conv_2/var")):
+                        cur = v["%s/%s" % (s, name)]
+                        cur -= np.float32(0.1) * (cur - bstats[k, 4 * j:4 * j + 4])
+                self._engine.refresh_parameters(self._extra_rows)
+        self.last_batch_stats = bstats
+        return out, ld, nll, sdz
 
     def _dev(self, a, name):
         if a is None:
@@ -242,11 +272,17 @@ class NoiseFlow(object):
     # ------------------------------------------------------------------ reference API
     def inverse(self, x, objective, yy=None, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None):
         """noise_flow_model.py:394-428 -> ``(z, objective + sum of log-dets)``."""
-        self._check_training(is_training)
+        training = self._check_training(is_training)
         self.build("inverse")
         x, yy = self._dev(x, "x"), self._dev(yy, "yy")
         n = x.shape[0]
         rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
+        if training:
+            z, ld, _, _ = self._batch_stats_chain(0, x, yy, rows, drow, n, want_logdet=True)
+            if objective is None:
+                return z, ld
+            obj = objective if isinstance(objective, torch.Tensor) else torch.as_tensor(np.asarray(objective))
+            return z, obj.to(self.device, torch.float32) + ld
         z = torch.empty_like(x)
         ld = torch.empty(n, device=self.device, dtype=torch.float32)
         e = self._engine
@@ -261,11 +297,13 @@ class NoiseFlow(object):
 
     def forward(self, z, eps_std=None, yy=None, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None):
         """noise_flow_model.py:430-447 (``eps_std`` only matters for multi-level models, as in the reference)."""
-        self._check_training(is_training)
+        training = self._check_training(is_training)
         self.build()
         z, yy = self._dev(z, "z"), self._dev(yy, "yy")
         n = z.shape[0]
         rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
+        if training:
+            return self._batch_stats_chain(1, z, yy, rows, drow, n)[0]
         x = torch.empty_like(z)
         e = self._engine
         with torch.cuda.device(self.device):
@@ -281,7 +319,7 @@ class NoiseFlow(object):
         ``eps`` injects the standard-normal draw (parity tests); otherwise it is drawn in-kernel with
         Philox4x32-10 keyed by ``seed`` (default: the constructor seed) and ``offset`` (default: a per-model
         call counter, so successive calls give fresh noise like ``tf.random_normal``)."""
-        self._check_training(is_training)
+        training = self._check_training(is_training)
         self.build()
         y = self._dev(y, "y")
         yy = self._dev(yy, "yy") if yy is not None else None
@@ -293,6 +331,9 @@ class NoiseFlow(object):
             with self._lock:
                 offset = self._sample_calls
                 self._sample_calls += 1
+        if training:
+            return self._batch_stats_chain(1, eps, yy, rows, drow, n, temp, self._seed if seed is None else seed,
+                                           offset, patch_base)[0]
         x = torch.empty_like(y)
         e = self._engine
         with torch.cuda.device(self.device):
@@ -305,18 +346,26 @@ class NoiseFlow(object):
 
     def _loss(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, reuse=False, is_training=None, return_z=False):
         """noise_flow_model.py:458-480 -> ``(nll[N], sd_z)``."""
-        self._check_training(is_training)
+        training = self._check_training(is_training)
         self.build("inverse")
         x = self._dev(x, "x")
         cond = getattr(self.hps, "sidd_cond", "mix")
         yy = self._dev(y, "y") if (cond is not None and cond != "uncond") else None     # :464-467
         n = x.shape[0]
         rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
+        sums = torch.empty(3, device=self.device, dtype=torch.float64)
+        e = self._engine
+        if training:
+            z, _, nll, sdz = self._batch_stats_chain(0, x, yy, rows, drow, n, want_nll=True)
+            with torch.cuda.device(self.device):
+                _lib.check(e.lib.nf_reduce_sums(nll.data_ptr(), sdz.data_ptr(), n, sums.data_ptr(),
+                                                _stream_ptr(self.device)), "nf_reduce_sums")
+            self.last_sums = sums
+            sd_z = (sums[1] / max(n, 1)).to(torch.float32)
+            return (nll, sd_z, z) if return_z else (nll, sd_z)
         nll = torch.empty(n, device=self.device, dtype=torch.float32)
         sdz = torch.empty(n, device=self.device, dtype=torch.float32)
         z = torch.empty_like(x) if return_z else None
-        sums = torch.empty(3, device=self.device, dtype=torch.float64)
-        e = self._engine
         with torch.cuda.device(self.device):
             st = _stream_ptr(self.device)
             _lib.check(e.lib.nf_log_prob(e.handle, x.data_ptr(), yy.data_ptr() if yy is not None else None,

@@ -253,7 +253,7 @@ def test_wrapper_drop_in(golden_dir, shipped):
     # reference graph-construction order (sample traced first) vs training order: distinct, both match the oracle
     eps = np.random.RandomState(41).randn(5, 32, 32, 4).astype(np.float32)
     for order, first in (("reference", "forward"), ("training", "inverse")):
-        ww = NoiseFlowWrapper(os.path.join(golden_dir, "NoiseFlow"), 0.6, template_order=order)
+        ww = NoiseFlowWrapper(os.path.join(golden_dir, "NoiseFlow"), 0.6, template_order=order, bn_mode="moving")
         xs = ww.nf_model.sample(y, 0.6, y, [0.0], [0.0], [100], [2], eps=eps).cpu().numpy()
         xo = make_oracle(hps, ck, first_call=first).sample(eps, 0.6, y, iso=[100.0], cam=[2.0]).numpy()
         assert np.abs(xs - xo).max() < 2e-6 * (1 + 100 * np.abs(xo).max()), order
@@ -291,8 +291,6 @@ def test_error_paths_fail_loudly(shipped):
     nf = _nf(hps, ck)
     with pytest.raises(ValueError):
         nf._loss(np.zeros((2, 16, 16, 4), np.float32), np.zeros((2, 16, 16, 4), np.float32))
-    with pytest.raises(NotImplementedError):
-        nf._loss(*synth_batch(2), iso=[100.0], cam=[2.0], is_training=True)
 
 
 def test_empty_and_single_patch(shipped):
@@ -332,3 +330,49 @@ def test_full_size_properties(shipped):
     idx = [0, 12345, 65535]
     n_o, _ = make_oracle(hps, ck)._loss(x[idx].cpu().numpy(), y[idx].cpu().numpy(), iso=[100.0], cam=[2.0])
     assert np.abs(nll[idx].cpu().numpy() - n_o.numpy()).max() / 4096 < 2e-5
+
+
+# ------------------------------------------------------------------------------------------ batch-statistics BatchNorm
+@pytest.mark.parametrize("n", [1, 7])
+def test_training_mode_batch_stat_bn_matches_oracle(shipped, n):
+    """is_training=True (layers.py:388-398): batch statistics, incl. the moving-average side effect (:394-395)."""
+    hps, ck = shipped
+    x, y = synth_batch(n, seed=59)
+    nf = _nf(hps, ck, first_call="inverse")
+    orc = make_oracle(hps, ck)
+    nll, sd_z, z = nf._loss(x, y, iso=[100.0], cam=[2.0], is_training=True, return_z=True)
+    nll_o, sd_o = orc._loss(x, y, iso=[100.0], cam=[2.0], is_training=True)
+    assert np.abs(nll.cpu().numpy() - nll_o.numpy()).max() / 4096 < NLL_TOL_PER_DIM
+    assert _close(z.cpu().numpy(), orc.last_z.numpy(), rel=1e-4)
+    for k, v in nf.variables.items():                       # moving statistics moved exactly like the reference's
+        if "/bn_nvp_conv_" in k:
+            ref = orc.store.vars[k].numpy()
+            assert np.abs(v - ref).max() < 1e-4 * (1 + np.abs(ref).max()), k
+            assert np.abs(v - ck[k]).max() > 0
+    # the refreshed moving-statistics engine now agrees with the oracle's updated store too
+    nll2, _ = nf._loss(x, y, iso=[100.0], cam=[2.0], is_training=False)
+    nll2_o, _ = orc._loss(x, y, iso=[100.0], cam=[2.0], is_training=False)
+    assert np.abs(nll2.cpu().numpy() - nll2_o.numpy()).max() / 4096 < NLL_TOL_PER_DIM
+
+
+def test_training_mode_sampling_and_wrapper_default(golden_dir, shipped):
+    """NoiseFlowWrapper.sample_noise_nf feeds is_training=True (NoiseFlowWrapper.py:85-86)."""
+    from noise_flow_b200.NoiseFlowWrapper import NoiseFlowWrapper
+    hps, ck = shipped
+    _, y = synth_batch(6, seed=61)
+    eps = np.random.RandomState(67).randn(6, 32, 32, 4).astype(np.float32)
+    w = NoiseFlowWrapper(os.path.join(golden_dir, "NoiseFlow"), 0.6)       # defaults: reference order, batch BN
+    assert w.bn_mode == "batch" and w.template_order == "reference"
+    xs = w.nf_model.sample(y, 0.6, y, [0.0], [0.0], [800], [2], eps=eps).cpu().numpy()
+    orc = make_oracle(hps, ck, first_call="forward")
+    xo = orc.sample(eps, 0.6, y, iso=[800.0], cam=[2.0], is_training=True).numpy()
+    assert np.abs(xs - xo).max() < 1e-4 * (1 + np.abs(xo).max())
+    out = w.sample_noise_nf(y, 0.0, 0.0, 800, 2)                            # Philox noise, numpy in / numpy out
+    assert out.shape == (6, 32, 32, 4) and out.dtype == np.float32 and np.isfinite(out).all()
+    # forward / inverse API in training mode
+    nf = _nf(hps, ck, first_call="inverse")
+    orc2 = make_oracle(hps, ck)
+    z = eps * 0.7
+    xf = nf.forward(z, None, yy=y, iso=[100.0], cam=[2.0], is_training=True).cpu().numpy()
+    xfo = orc2.forward(z, None, yy=y, iso=[100.0], cam=[2.0], is_training=True).numpy()
+    assert np.abs(xf - xfo).max() < 1e-4 * (1 + np.abs(xfo).max())
