@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--warps", type=int, default=0, help="resident patches per CTA (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tc", type=int, default=0, help="1: tensor-core (tcgen05) coupling convolutions")
+    ap.add_argument("--arch", default=None, help="override hps.arch, e.g. \"sdn5|gain4\" (HBM-bound streaming kernel)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -180,9 +182,13 @@ def main():
     from noise_flow_b200 import NoiseFlow, _lib
     from noise_flow_b200.distributed import allreduce_sums
     hps, ck = load_model_files()
+    if args.arch:
+        hps.arch = args.arch
     nf = NoiseFlow([32, 32, 4], False, hps, variables=ck, first_call="inverse", device=dev)
     if args.warps:
         nf.set_launch(args.warps, 0)
+    if args.tc:
+        nf.set_tensor_cores(True)
     lib, eng = _lib.load(), nf._engine
     B = args.batch
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -303,13 +309,13 @@ def main():
            "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "%s S-Ax4-G-Ax4 (shipped weights, arch %s), batch %d 32x32x4 patches per GPU, "
+           "config": {"workload": "%s Noise Flow (shipped weights, arch %s), batch %d 32x32x4 patches per GPU, "
                                   "cam S6 / ISO 100" % (args.mode, hps.arch, B),
                       "per_gpu_batch": B, "global_batch": world * B, "parallelism": "dp%d" % world,
                       "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (2 * B * 16384 / 2 ** 30),
                       "mean_nll_per_dim": mean_nll},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "peak_source": peak_src, "kernel": "nf_chain_kernel",
+                        "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else "nf_chain_kernel",
                         "kernel_ms": kms, "alg_bytes_per_patch": alg,
                         "note": "binding roof is the FP32 FMA pipe (see roofline_fp32), not HBM"},
            "roofline_fp32": {"bound": "fp32_fma", "achieved": B * CONV_FLOP_PER_PATCH / (kms * 1e-3) / 1e12,

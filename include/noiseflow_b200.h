@@ -97,6 +97,10 @@ int nf_model_set_affine_coupling(nf_model* m, int layer, const nf_coupling_weigh
 int nf_model_set_scale(nf_model* m, int layer, const float* table, int n_rows);
 /* Launch tuning: resident patches (warps) per CTA in [1, 12] and CTA count (0 = one per SM). */
 int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas);
+/* enable != 0: run the two 3x3 convolutions of every coupling net on the tensor cores (tcgen05.mma with bf16
+ * hi/lo-split operands, fp32 accumulation in TMEM; csrc/nf_tc.cu) for full-chain calls with explicit inputs;
+ * other calls (partial ranges, in-kernel Philox, batch-statistics probes) keep the fp32 CUDA-core kernel. */
+int nf_model_set_tensor_cores(nf_model* m, int enable);
 
 /* ---- hot path (device pointers) ---------------------------------------------------------------- */
 /* rows: per-patch conditioning-table row (int32, device) or NULL -> default_row for every patch.

@@ -23,6 +23,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path
 UNITS = [
     ("nf_kernels.cu", ["-use_fast_math"]),
     ("nf_stream.cu", ["-use_fast_math"]),
+    ("nf_tc.cu", ["-use_fast_math"]),
     ("nf_api.cu", []),
 ]
 

@@ -60,6 +60,7 @@ struct nf_model {
     std::vector<Layer> layers;
     bool finalized = false;
     int warps_per_cta = NF_MAX_WARPS_PER_CTA;
+    int use_tc = 0;              // 1: coupling convolutions on the tensor cores (nf_tc.cu) where supported
     int num_ctas = 0;
     int sm_count = 0;
     NfModelParams full = {};     // fused program of the whole chain
@@ -259,6 +260,8 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
         a.last_layer = mp.n_layers;
         if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
             e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);   // HBM-bound streaming path
+        else if (m->use_tc && nf::tc_program_supported(mp, a))
+            e = nf::launch_chain_tc(mp, a, inverse, num_ctas_for(m), stream);   // tcgen05 path
         else
             e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
     } else {
@@ -275,6 +278,8 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
         a.ldj_const = ldj;
         if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
             e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);
+        else if (m->use_tc && nf::tc_program_supported(mp, a))
+            e = nf::launch_chain_tc(mp, a, inverse, num_ctas_for(m), stream);
         else
             e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
     }
@@ -469,6 +474,12 @@ int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas) {
     if (num_ctas < 0) return fail(NF_ERR_INVALID, "num_ctas must be >= 0");
     m->warps_per_cta = warps_per_cta;
     m->num_ctas = num_ctas;
+    return NF_OK;
+}
+
+int nf_model_set_tensor_cores(nf_model* m, int enable) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    m->use_tc = enable ? 1 : 0;
     return NF_OK;
 }
 

@@ -8,6 +8,10 @@
 #define NF_MAX_CTA_THREADS (NF_MAX_WARPS_PER_CTA * 32)
 #define NF_MAX_CTA_SMEM (NF_MAX_WARPS_PER_CTA * NF_WARP_SMEM_BYTES)      // 216192 B <= 227 KB
 
+// tensor-core path (nf_tc.cu)
+#define NF_TC_GROUPS 3   // patches in flight per CTA (4 warps each); 3 x 144 TMEM columns <= 512
+#define NF_TC_SLOTS 8    // couplings whose B tiles are resident in shared memory
+
 namespace nf {
 cudaError_t launch_chain(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, int warps_per_cta,
                          cudaStream_t stream);
@@ -17,4 +21,6 @@ cudaError_t launch_squeeze(const float* in, float* out, long long n, int H, int 
 bool program_is_scale_only(const NfModelParams& mp, int first, int last);
 cudaError_t launch_scale_stream(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms,
                                 cudaStream_t stream);
+bool tc_program_supported(const NfModelParams& mp, const NfChainArgs& a);
+cudaError_t launch_chain_tc(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, cudaStream_t stream);
 }  // namespace nf

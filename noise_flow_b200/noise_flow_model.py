@@ -182,6 +182,13 @@ class NoiseFlow(object):
         self.build()
         _lib.check(self._engine.lib.nf_model_set_launch(self._engine.handle, warps_per_cta, num_ctas), "nf_model_set_launch")
 
+    def set_tensor_cores(self, enable: bool = True):
+        """Run the coupling-net 3x3 convolutions on the tensor cores (tcgen05, bf16 hi/lo split operands)."""
+        self.build()
+        _lib.check(self._engine.lib.nf_model_set_tensor_cores(self._engine.handle, 1 if enable else 0),
+                   "nf_model_set_tensor_cores")
+        return self
+
     # ------------------------------------------------------------------ helpers
     def _check_training(self, is_training) -> bool:
         """Resolve the reference's ``is_training`` placeholder (constructor value unless overridden per call)."""
