@@ -144,7 +144,7 @@ def run_reference(args):
                             "sample": "%d steps x %d patches" % (args.steps, per_step)},
            "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     return 0
 
 
@@ -178,6 +178,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
     from noise_flow_b200 import NoiseFlow, _lib
     from noise_flow_b200.distributed import allreduce_sums
@@ -326,11 +328,19 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_oracle_rate(hps, ck)
         out["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    try:
+        rc = main()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        rc = 1
+    sys.stdout.flush()
+    sys.exit(rc)

@@ -170,15 +170,17 @@ __device__ __forceinline__ void tc_coupling(const NfCouplingP& P, TcSmem& S, TcG
     // tap offsets (pixels) in ascending order; pair (2j, 2j+1); the 10th "tap" is a dummy with zero weights
     auto issue = [&](int conv) {
         tc_fence_after();
-#pragma unroll 1
-        for (int t = 0; t < TC_TILES; ++t) {
+        // tap pairs outermost, row tiles innermost: consecutive MMAs hit different accumulators, so the
+        // tensor pipe is not serialised on the accumulate dependency (46 cycles per dependent MMA, tools/tc_probe.cu)
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int ta = 2 * j, tb = 2 * j + 1;
-                const int offa = (ta / 3 - 1) * 34 + (ta % 3 - 1);
-                const int offb = tb <= 8 ? (tb / 3 - 1) * 34 + (tb % 3 - 1) : offa;
+        for (int j = 0; j < 5; ++j) {
+            const int ta = 2 * j, tb = 2 * j + 1;
+            const int offa = (ta / 3 - 1) * 34 + (ta % 3 - 1);
+            const int offb = tb <= 8 ? (tb / 3 - 1) * 34 + (tb % 3 - 1) : offa;
+            const uint64_t bd = make_desc(wb_addr + (uint32_t)(conv * 5 + j) * 512u, 128u, 256u);
+#pragma unroll 1
+            for (int t = 0; t < TC_TILES; ++t) {
                 const uint64_t ad = make_desc(img_addr + (uint32_t)(TC_P0 + 128 * t + offa) * 16u, (uint32_t)(offb - offa) * 16u, 128u);
-                const uint64_t bd = make_desc(wb_addr + (uint32_t)(conv * 5 + j) * 512u, 128u, 256u);
                 mma_bf16(tmem_g + 16u * t, ad, bd, j > 0 ? 1u : 0u);
             }
         }

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o gpurun_out/tc_probe tools/tc_probe.cu && timeout 60 gpurun_out/tc_probe 2>&1 | tee gpurun_out/tc_probe.log
-timeout 300 python -m pytest tests/test_gpu_tensor_core.py -x -q -s 2>&1 | tail -25 | tee gpurun_out/pytest_tc.log
+timeout 300 python -m pytest tests/test_gpu_tensor_core.py -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_tc.log
 timeout 120 python bench.py --tc 1 --no-cpu-baseline --no-e2e --steps 20 > gpurun_out/bench_tc.json 2> gpurun_out/bench_tc.err
 python - <<'PY'
 import json

@@ -48,7 +48,7 @@ struct Args {
     const __nv_bfloat16* b_raw;   // 512 B in the canonical B layout (host builds it)
     float* out;                   // [128][16]
     long long* cycles;            // timing result
-    int n_pix, off, lbo_a, sbo_a, lbo_b, sbo_b, reps, M, N;
+    int n_pix, off, lbo_a, sbo_a, lbo_b, sbo_b, reps, M, N, n_acc;
 };
 
 __global__ void __launch_bounds__(128, 1) tc_probe(Args g) {
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128, 1) tc_probe(Args g) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base)), "r"(32u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // st.shared data -> visible to the tensor-core (async) proxy
@@ -79,7 +79,26 @@ __global__ void __launch_bounds__(128, 1) tc_probe(Args g) {
     long long t0 = 0, t1 = 0;
     if (tid == 0) {
         t0 = clock64();
-        for (int r = 0; r < g.reps; ++r) mma_f16(tmem, adesc, bdesc, idesc, r > 0 ? 1u : 0u);
+        if (g.reps == 1) {
+            mma_f16(tmem, adesc, bdesc, idesc, 0u);
+        } else if (g.n_acc == 1) {          // dependent chain, unrolled x8 (no per-MMA index math)
+            mma_f16(tmem, adesc, bdesc, idesc, 0u);
+            for (int r = 0; r < g.reps / 8; ++r) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mma_f16(tmem, adesc, bdesc, idesc, 1u);
+            }
+        } else if (g.n_acc == 8) {          // 8 independent accumulators round-robin, unrolled
+            for (int r = 0; r < g.reps / 8; ++r) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mma_f16(tmem + 16u * u, adesc, bdesc, idesc, r > 0 ? 1u : 0u);
+            }
+        } else {                            // 8 accumulators + a descriptor increment per MMA (row-tile walk)
+            for (int r = 0; r < g.reps / 8; ++r) {
+                uint64_t ad = adesc;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { mma_f16(tmem + 16u * u, ad, bdesc, idesc, r > 0 ? 1u : 0u); ad += 8; }
+            }
+        }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
     }
     mbar_wait(smem_u32(&mbar), 0);
@@ -96,7 +115,7 @@ __global__ void __launch_bounds__(128, 1) tc_probe(Args g) {
         for (int c = 0; c < 16; ++c) g.out[(warp * 32 + lane) * 16 + c] = __uint_as_float(r[c]);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(32u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u) : "memory");
 }
 
 static float bf(const __nv_bfloat16& v) { return __bfloat162float(v); }
@@ -121,7 +140,7 @@ int main() {
     CK(cudaMemcpy(da, a.data(), a.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(db, braw.data(), 512, cudaMemcpyHostToDevice));
     const size_t smem = ((n_pix * 16 + 127) / 128) * 128 + 1024;   // B tile (512 B) + slack for the N=32 timing run
     for (int variant = 0; variant < 1; ++variant) {   // variant 1 (LBO/SBO swapped) faults: confirmed on B200, round 1
-        Args g = {da, db, dout, dcyc, n_pix, off, 0, 0, 0, 0, 1, M, N};
+        Args g = {da, db, dout, dcyc, n_pix, off, 0, 0, 0, 0, 1, M, N, 1};
         // variant 0: LBO = K-chunk stride (tap), SBO = 8-row-group stride (128 B); variant 1: swapped
         if (variant == 0) { g.lbo_a = tap * 16; g.sbo_a = 128; g.lbo_b = lbo_b; g.sbo_b = sbo_b; }
         else              { g.lbo_a = 128; g.sbo_a = tap * 16; g.lbo_b = sbo_b; g.sbo_b = lbo_b; }
@@ -141,15 +160,14 @@ int main() {
         printf("variant %d (%s): max |D - expected| = %.3e (max |expected| %.3f)  out[0][0..3] = %.4f %.4f %.4f %.4f\n", variant,
                variant == 0 ? "LBO=K-chunk stride, SBO=8-row stride" : "swapped", err, ref_max, out[0], out[1], out[2], out[3]);
     }
-    // timing: M=128,N=16 and M=64,N=8, K=16 per MMA, 4096 accumulating MMAs from one thread
-    for (int cfg = 0; cfg < 3; ++cfg) {
-        const int Mv = cfg == 1 ? 64 : 128, Nv = cfg == 1 ? 8 : (cfg == 2 ? 32 : 16);
-        Args g = {da, db, dout, dcyc, n_pix, off, tap * 16, 128, lbo_b, sbo_b, 4096, Mv, Nv};
+    // timing: 4096 MMAs from one thread, round-robin over n_acc independent accumulators (TMEM column blocks)
+    for (int n_acc = 1; n_acc <= 16; n_acc *= (n_acc == 1 ? 8 : 2)) {
+        Args g = {da, db, dout, dcyc, n_pix, off, tap * 16, 128, lbo_b, sbo_b, 4096, 128, 16, n_acc};
         tc_probe<<<1, 128, smem>>>(g);
         CK(cudaDeviceSynchronize());
         long long cyc = 0;
         CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
-        printf("timing M=%d N=%d K=16: %.2f cycles per MMA (4096 back-to-back, 1 CTA)\n", Mv, Nv, cyc / 4096.0);
+        printf("timing M=128 N=16 K=16, mode %2d (1 = dependent chain, 8 = 8 accumulators, 16 = 8 acc + desc walk): %.2f cycles per MMA\n", n_acc, cyc / 4096.0);
     }
     return 0;
 }
