@@ -95,7 +95,7 @@ int nf_model_num_layers(const nf_model* m);
 int nf_model_set_conv1x1(nf_model* m, int layer, const float* A, const float* A_inv, float log_abs_det);
 int nf_model_set_affine_coupling(nf_model* m, int layer, const nf_coupling_weights* w);
 int nf_model_set_scale(nf_model* m, int layer, const float* table, int n_rows);
-/* Launch tuning: resident patches (warps) per CTA in [1, 12] and CTA count (0 = one per SM). */
+/* Launch tuning: resident patches (warps) per CTA in [1, 16] and CTA count (0 = one per SM). */
 int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas);
 /* enable != 0: run the two 3x3 convolutions of every coupling net on the tensor cores (tcgen05.mma with bf16
  * hi/lo-split operands, fp32 accumulation in TMEM; csrc/nf_tc.cu) for full-chain calls with explicit inputs;

@@ -39,21 +39,29 @@ __device__ __forceinline__ B3 load_b3(const CP& P, int lane) {
 // BatchNorm into stats[0..3] / stats[4..7]; nothing is published and stage C does not run.  The caller folds
 // the BatchNorm under probe as the identity, so the folded activation IS the raw pre-BN activation.
 template <bool INV, bool GUARDED, int STATS = 0, class CP>
-__device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const int lane, const int t, const bool has_mix,
-                                              Acc4& b_old, Acc4& b_mid, Acc4& c_old, Acc4& c_mid, const B3& b3,
-                                              float& ldj, float* stats = nullptr) {
+__device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const ZStore& zs, const int lane, const int t,
+                                              const bool has_mix, Acc4& b_old, Acc4& b_mid, Acc4& c_old, Acc4& c_mid,
+                                              const B3& b3, float& ldj, float* stats = nullptr) {
     const float2 zero2 = make_float2(0.f, 0.f);
     const bool do_a = !GUARDED || t < 32;
     const bool b_fma = !GUARDED || (t >= 1 && t <= 32);
     const bool b_emit = !GUARDED || (t >= 2 && t <= 33);
     const bool c_fma = STATS == 0 && (!GUARDED || (t >= 3 && t <= 34));
     const bool c_emit = STATS == 0 && (!GUARDED || t >= 4);
+    // z rows of this step: row t (stage A) and row t-4 (stage C), fetched together (one wait for both).
+    // commit() (= tcgen05.wait::st when z lives in TMEM) sits HERE, not after the stores: the stores of the previous
+    // step were issued a few hundred cycles ago, so the wait is free, and row t-4 was last written 4 steps back.
+    zs.commit();
+    float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zc = za;
+    if (do_a && c_emit) zs.load2(t, t - 4, za, zc);
+    else if (do_a) za = zs.load(t);
+    else if (c_emit) zc = zs.load(t - 4);
     // ---------------- stage A
     if (do_a) {
-        float4 z = s.z[t * 32 + lane];
+        float4 z = za;
         if (INV && has_mix) {
             z = mix4(z, P.a);                                   // Conv2d1x1._inverse, layers.py:117-119
-            s.z[t * 32 + lane] = z;
+            zs.store(t, z);
         }
         s.xr[t & 1][lane + 1] = make_float2(z.x, z.y);
     }
@@ -143,7 +151,7 @@ __device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const in
         // shift = h3[0:2], log_scale = scale * tanh(h3[2:4])                    (layers.py:362 / :342)
         const float ls0 = P.scale * fast_tanh(h3[2]);
         const float ls1 = P.scale * fast_tanh(h3[3]);
-        float4 z = s.z[q * 32 + lane];
+        float4 z = zc;
         if (INV) {
             z.z = fmaf(z.z, fast_exp(ls0), h3[0]);                               // layers.py:363-367
             z.w = fmaf(z.w, fast_exp(ls1), h3[1]);
@@ -154,13 +162,13 @@ __device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const in
             ldj -= ls0 + ls1;                                                    // layers.py:352
             if (has_mix) z = mix4(z, P.ainv);                                    // Conv2d1x1._forward, layers.py:113-114
         }
-        s.z[q * 32 + lane] = z;
+        zs.store(q, z);
     }
     __syncwarp();
 }
 
 template <bool INV, class CP>
-__device__ __forceinline__ void coupling_pass(const CP& P, WarpSmem& s, const int lane, float& ldj) {
+__device__ __forceinline__ void coupling_pass(const CP& P, WarpSmem& s, const ZStore& zs, const int lane, float& ldj) {
     const bool has_mix = P.has_mix != 0;
     const B3 b3 = load_b3(P, lane);
     Acc4 b_old, b_mid, c_old, c_mid;
@@ -168,14 +176,14 @@ __device__ __forceinline__ void coupling_pass(const CP& P, WarpSmem& s, const in
     for (int o = 0; o < 4; ++o) b_old.v[o] = b_mid.v[o] = c_old.v[o] = c_mid.v[o] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int t = 0; t < 36; ++t) {
-        if (t >= 5 && t < 32) coupling_step<INV, false>(P, s, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj);
-        else                  coupling_step<INV, true>(P, s, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj);
+        if (t >= 5 && t < 32) coupling_step<INV, false>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj);
+        else                  coupling_step<INV, true>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj);
     }
 }
 
 // Batch-statistics probe of one coupling: rows 0..31 of the conv-1 / conv-2 pre-BN activation.
 template <bool INV, int STAGE, class CP>
-__device__ __forceinline__ void coupling_stats_pass(const CP& P, WarpSmem& s, const int lane, float* stats) {
+__device__ __forceinline__ void coupling_stats_pass(const CP& P, WarpSmem& s, const ZStore& zs, const int lane, float* stats) {
     const bool has_mix = P.has_mix != 0;
     B3 b3 = {};
     Acc4 b_old, b_mid, c_old, c_mid;
@@ -184,7 +192,7 @@ __device__ __forceinline__ void coupling_stats_pass(const CP& P, WarpSmem& s, co
     float ldj = 0.f;
 #pragma unroll 1
     for (int t = 0; t < 34; ++t)
-        coupling_step<INV, true, STAGE>(P, s, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, stats);
+        coupling_step<INV, true, STAGE>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, stats);
 }
 
 }  // namespace nf

@@ -27,10 +27,56 @@
 
 namespace nf {
 
+// Where a warp keeps its resident patch z[32 rows][32 lanes] (float4 per pixel; lane = image column):
+//  NF_Z_IN_TMEM = 1: in TENSOR MEMORY.  z is lane-private (a lane only ever touches its own column), which is
+//      exactly TMEM's access model: warp w owns lanes 32*(w%4).., 128 columns (32 rows x 4 channels) at column
+//      128*(w/4); one tcgen05.ld/st .32x32b.x4 moves one image row for the whole warp.  The 256 KB of TMEM hold
+//      16 patches per SM, shared memory only carries the two small row rings, so 16 warps are resident per SM
+//      instead of the 12 that fit when z lives in shared memory (216 KB).
+//  NF_Z_IN_TMEM = 0: in shared memory (z[row*32 + lane]).
 struct __align__(16) WarpSmem {
+#if !NF_Z_IN_TMEM
     float4 z[NF_PIXELS];   // z[row * 32 + lane]
+#endif
     float4 hr[2][34];      // h2 row ring: [1..32] = columns, [0] and [33] = zero halo
     float2 xr[2][34];      // x0 row ring
+};
+
+struct ZStore {
+#if NF_Z_IN_TMEM
+    uint32_t taddr;   // (first TMEM lane of this warp << 16) | first column of this warp's patch
+    __device__ __forceinline__ void issue_ld(int r, uint32_t (&v)[4]) const {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr + (uint32_t)(r * 4)));
+    }
+    __device__ __forceinline__ float4 load(int r) const {
+        uint32_t v[4];
+        issue_ld(r, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        return make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+    }
+    __device__ __forceinline__ void load2(int r1, int r2, float4& a, float4& b) const {
+        uint32_t v[4], w[4];
+        issue_ld(r1, v);
+        issue_ld(r2, w);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        a = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+        b = make_float4(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), __uint_as_float(w[3]));
+    }
+    __device__ __forceinline__ void store(int r, float4 z) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                     :: "r"(taddr + (uint32_t)(r * 4)), "r"(__float_as_uint(z.x)), "r"(__float_as_uint(z.y)),
+                        "r"(__float_as_uint(z.z)), "r"(__float_as_uint(z.w)) : "memory");
+    }
+    __device__ __forceinline__ void commit() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#else
+    float4* z;
+    int lane;
+    __device__ __forceinline__ float4 load(int r) const { return z[r * 32 + lane]; }
+    __device__ __forceinline__ void load2(int r1, int r2, float4& a, float4& b) const { a = z[r1 * 32 + lane]; b = z[r2 * 32 + lane]; }
+    __device__ __forceinline__ void store(int r, float4 v) const { z[r * 32 + lane] = v; }
+    __device__ __forceinline__ void commit() const {}
+#endif
 };
 static_assert(sizeof(WarpSmem) == NF_WARP_SMEM_BYTES, "WarpSmem size");
 
@@ -114,76 +160,82 @@ namespace nf {
 // stall_no_instruction 1.6 per issue, icc hit rate 83 %).
 #define NF_FAST_SLOTS 8
 template <bool INV>
-__device__ __forceinline__ void coupling_dispatch(const NfModelParams& mp, WarpSmem& s, int lane, float& ldj, int slot) {
+__device__ __forceinline__ void coupling_dispatch(const NfModelParams& mp, WarpSmem& s, const ZStore& zs, int lane, float& ldj, int slot) {
     switch (slot) {
-#define NF_CASE(K) case K: coupling_pass<INV>(mp.cp[K], s, lane, ldj); break;
+#define NF_CASE(K) case K: coupling_pass<INV>(mp.cp[K], s, zs, lane, ldj); break;
         NF_CASE(0) NF_CASE(1) NF_CASE(2) NF_CASE(3) NF_CASE(4) NF_CASE(5) NF_CASE(6) NF_CASE(7)
 #undef NF_CASE
-        default: coupling_pass<INV>(mp.cp[slot], s, lane, ldj); break;   // run-time slot: per-thread LDC weight fetches
+        default: coupling_pass<INV>(mp.cp[slot], s, zs, lane, ldj); break;   // run-time slot: per-thread LDC weight fetches
     }
 }
 
 // stand-alone 4x4 channel mix (Conv2d1x1 / tfb.Permute not followed by a coupling)
 template <bool INV>
-__device__ __forceinline__ void mix_pass(const NfMixP& M, WarpSmem& s, int lane) {
+__device__ __forceinline__ void mix_pass(const NfMixP& M, const ZStore& zs) {
     float m[4][4];
 #pragma unroll
     for (int o = 0; o < 4; ++o)
 #pragma unroll
         for (int i = 0; i < 4; ++i) m[o][i] = INV ? M.a[o][i] : M.ainv[o][i];
 #pragma unroll 4
-    for (int r = 0; r < 32; ++r) s.z[r * 32 + lane] = mix4(s.z[r * 32 + lane], m);
+    zs.commit();
+    for (int r = 0; r < 32; ++r) zs.store(r, mix4(zs.load(r), m));
+    zs.commit();
 }
 
 // scale layers: sdn* (scale^2 = a*y + b) and gain* (scale = g)
 template <bool INV>
-__device__ __forceinline__ void sdn_pass(const float4* __restrict__ yp, float a, float b, WarpSmem& s, int lane, float& ldj) {
+__device__ __forceinline__ void sdn_pass(const float4* __restrict__ yp, float a, float b, const ZStore& zs, int lane, float& ldj) {
     float acc = 0.f;
+    zs.commit();
 #pragma unroll 8
     for (int r = 0; r < 32; ++r) {
         const float4 y = __ldg(yp + r * 32 + lane);
-        float4 z = s.z[r * 32 + lane];
+        float4 z = zs.load(r);
         const float v0 = fmaf(a, y.x, b), v1 = fmaf(a, y.y, b), v2 = fmaf(a, y.z, b), v3 = fmaf(a, y.w, b);
         const float r0 = rsqrtf(v0), r1 = rsqrtf(v1), r2 = rsqrtf(v2), r3 = rsqrtf(v3);
         if (INV) { z.x *= r0; z.y *= r1; z.z *= r2; z.w *= r3; }                       // SdnEx5.py:125-126
         else     { z.x *= v0 * r0; z.y *= v1 * r1; z.z *= v2 * r2; z.w *= v3 * r3; }   // SdnEx5.py:106-107
         acc += (__logf(v0) + __logf(v1)) + (__logf(v2) + __logf(v3));
-        s.z[r * 32 + lane] = z;
+        zs.store(r, z);
     }
+    zs.commit();
     ldj += INV ? -0.5f * acc : 0.5f * acc;                                              // SdnEx5.py:129 / :110
 }
 
 template <bool INV>
-__device__ __forceinline__ void gain_pass(float g, float ginv, float ldj_inv, WarpSmem& s, int lane, float& ldj) {
+__device__ __forceinline__ void gain_pass(float g, float ginv, float ldj_inv, const ZStore& zs, int lane, float& ldj) {
     const float m = INV ? ginv : g;
+    zs.commit();
 #pragma unroll 8
     for (int r = 0; r < 32; ++r) {
-        float4 z = s.z[r * 32 + lane];
+        float4 z = zs.load(r);
         z.x *= m; z.y *= m; z.z *= m; z.w *= m;
-        s.z[r * 32 + lane] = z;
+        zs.store(r, z);
     }
+    zs.commit();
     if (lane == 0) ldj += INV ? ldj_inv : -ldj_inv;
 }
 
 template <bool INV>
-__device__ __forceinline__ void run_layer(const NfModelParams& mp, const NfChainArgs& a, WarpSmem& s, int lane,
-                                          int l, long long p, int row, float& ldj, float* stats) {
+__device__ __forceinline__ void run_layer(const NfModelParams& mp, const NfChainArgs& a, WarpSmem& s, const ZStore& zs,
+                                          int lane, int l, long long p, int row, float& ldj, float* stats) {
     const int op = mp.op[l], slot = mp.slot[l];
     const bool probe = a.bn_stage != 0 && op == NF_KOP_COUPLING && l == (INV ? a.last_layer - 1 : a.first_layer);
     if (probe) {   // batch-statistics BatchNorm: measure, do not transform (single compact copy, run-time slot)
-        if (a.bn_stage == 1) coupling_stats_pass<INV, 1>(mp.cp[slot], s, lane, stats);
-        else                 coupling_stats_pass<INV, 2>(mp.cp[slot], s, lane, stats);
+        if (a.bn_stage == 1) coupling_stats_pass<INV, 1>(mp.cp[slot], s, zs, lane, stats);
+        else                 coupling_stats_pass<INV, 2>(mp.cp[slot], s, zs, lane, stats);
         __syncthreads();
         return;
     }
     switch (op) {
-        case NF_KOP_COUPLING: coupling_dispatch<INV>(mp, s, lane, ldj, slot); break;
-        case NF_KOP_MIX: mix_pass<INV>(mp.mix[slot], s, lane); break;
+        case NF_KOP_COUPLING: coupling_dispatch<INV>(mp, s, zs, lane, ldj, slot); break;
+        case NF_KOP_MIX: mix_pass<INV>(mp.mix[slot], zs); break;
         case NF_KOP_SDN:
-            sdn_pass<INV>(reinterpret_cast<const float4*>(a.y) + p * NF_PIXELS, mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], s, lane, ldj);
+            sdn_pass<INV>(reinterpret_cast<const float4*>(a.y) + p * NF_PIXELS, mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], zs, lane, ldj);
             break;
         case NF_KOP_GAIN:
-            gain_pass<INV>(mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], mp.sc[slot].t[row][2], s, lane, ldj);
+            gain_pass<INV>(mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], mp.sc[slot].t[row][2], zs, lane, ldj);
             break;
         default: break;
     }
@@ -201,6 +253,20 @@ nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
     const int warps_per_cta = blockDim.x >> 5;
     WarpSmem& s = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
 
+#if NF_Z_IN_TMEM
+    __shared__ uint32_t tmem_base_smem;
+    if (warp == 0) {   // the whole tensor memory of this SM: 512 columns x 128 lanes = 16 resident patches
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_smem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const ZStore zs = {tmem_base_smem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128)};
+#else
+    const ZStore zs = {s.z, lane};
+#endif
     if (lane < 2) {   // zero halo columns of the row rings (never written again)
         s.hr[0][lane * 33] = s.hr[1][lane * 33] = make_float4(0.f, 0.f, 0.f, 0.f);
         s.xr[0][lane * 33] = s.xr[1][lane * 33] = make_float2(0.f, 0.f);
@@ -224,24 +290,27 @@ nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
             for (int r = 0; r < 32; ++r) {
                 float4 v = __ldcs(src + r * 32 + lane);
                 if (!INV) { v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp; }   // noise_flow_model.py:501
-                s.z[r * 32 + lane] = v;
+                zs.store(r, v);
             }
         } else {
 #pragma unroll 2
             for (int r = 0; r < 32; ++r) {
                 float4 v = philox_normal4(a.seed, a.offset, a.patch_base + (unsigned long long)p, (unsigned int)(r * 32 + lane));
                 v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp;
-                s.z[r * 32 + lane] = v;
+                zs.store(r, v);
             }
         }
+        zs.commit();
         __syncwarp();
 
         float ldj = 0.f;
         float stats[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // (every pass below starts from committed z: load phase, scale / mix passes commit at their end, and a
+        //  coupling pass commits at the top of each step and is followed by the commit of the next pass or epilogue)
         if (INV) {
-            for (int l = a.first_layer; l < a.last_layer; ++l) run_layer<true>(mp, a, s, lane, l, p, row, ldj, stats);
+            for (int l = a.first_layer; l < a.last_layer; ++l) run_layer<true>(mp, a, s, zs, lane, l, p, row, ldj, stats);
         } else {
-            for (int l = a.last_layer - 1; l >= a.first_layer; --l) run_layer<false>(mp, a, s, lane, l, p, row, ldj, stats);
+            for (int l = a.last_layer - 1; l >= a.first_layer; --l) run_layer<false>(mp, a, s, zs, lane, l, p, row, ldj, stats);
         }
 
         if (a.bn_stage != 0) {   // probe launch: publish this patch's per-channel sums, nothing else
@@ -254,11 +323,12 @@ nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
             continue;
         }
         // ---- epilogue: store the patch, reduce log-det / prior / latent statistics
+        zs.commit();
         float s1 = 0.f, s2 = 0.f;
         float4* dst = (a.out && active) ? reinterpret_cast<float4*>(a.out) + p * NF_PIXELS : nullptr;
 #pragma unroll 8
         for (int r = 0; r < 32; ++r) {
-            const float4 z = s.z[r * 32 + lane];
+            const float4 z = zs.load(r);
             if (dst) __stcs(dst + r * 32 + lane, z);
             s1 += (z.x + z.y) + (z.z + z.w);
             s2 = fmaf(z.x, z.x, fmaf(z.y, z.y, fmaf(z.z, z.z, fmaf(z.w, z.w, s2))));
@@ -279,6 +349,11 @@ nf_chain_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
         }
         __syncwarp();
     }
+#if NF_Z_IN_TMEM
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_smem), "r"(512u) : "memory");
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

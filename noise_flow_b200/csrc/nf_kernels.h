@@ -3,10 +3,18 @@
 #include <cuda_runtime.h>
 #include "nf_params.h"
 
+#ifndef NF_Z_IN_TMEM
+#define NF_Z_IN_TMEM 1   // resident patches live in tensor memory (16 per SM); 0: in shared memory (12 per SM)
+#endif
+#if NF_Z_IN_TMEM
+#define NF_WARP_SMEM_BYTES (2 * 34 * 16 + 2 * 34 * 8)                    // row rings only: 1632 B per resident patch
+#define NF_MAX_WARPS_PER_CTA 16                                          // 16 x 128 columns = the 512 TMEM columns
+#else
 #define NF_WARP_SMEM_BYTES (NF_PIXELS * 16 + 2 * 34 * 16 + 2 * 34 * 8)   // 18016 B per resident patch
 #define NF_MAX_WARPS_PER_CTA 12
+#endif
 #define NF_MAX_CTA_THREADS (NF_MAX_WARPS_PER_CTA * 32)
-#define NF_MAX_CTA_SMEM (NF_MAX_WARPS_PER_CTA * NF_WARP_SMEM_BYTES)      // 216192 B <= 227 KB
+#define NF_MAX_CTA_SMEM (NF_MAX_WARPS_PER_CTA * NF_WARP_SMEM_BYTES)
 
 // tensor-core path (nf_tc.cu)
 #define NF_TC_GROUPS 3   // patches in flight per CTA (4 warps each); 3 x 144 TMEM columns <= 512

@@ -174,7 +174,7 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.nf_model_num_layers(h) == 1
     # launching before finalize is a state error, not a crash
     assert lib.nf_log_prob(h, 1, 1, None, 0, 1, 1, None, None, None) == -4
-    assert lib.nf_model_set_launch(h, 13, 0) == -1 and lib.nf_model_set_launch(h, 8, 0) == 0
+    assert lib.nf_model_set_launch(h, 17, 0) == -1 and lib.nf_model_set_launch(h, 8, 0) == 0
     assert lib.nf_model_destroy(h) == 0
 
 
