@@ -153,6 +153,18 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
 int nf_squeeze2d(const float* x, int64_t n, int H, int W, int C, int factor, int squeeze_type, float* out, void* stream);
 int nf_unsqueeze2d(const float* x, int64_t n, int H, int W, int C, int factor, int squeeze_type, float* out, void* stream);
 
+/* ---- evaluation metrics the reference computes right after the path ------------------------------ */
+/* calc_baselines (sidd/PatchStatsCalculator.py:92-123): per-patch NLL of x under N(0, var_gauss) and under the
+ * camera NLF N(0, y*nlf0 + nlf1); the reference reports their batch means next to the flow's NLL. */
+int nf_baseline_nll(const float* x, const float* y, float nlf0, float nlf1, float var_gauss, int64_t n,
+                    float* nll_gauss, float* nll_sdn, void* stream);
+/* np.histogram(data, edges) as used by get_histogram (sidd/sidd_utils.py:1266-1274) for the marginal KL
+ * divergence (:1044-1052, kl_div_3_data :1247-1263): counts[b] += #{edges[b] <= v < edges[b+1]} (last bin
+ * closed), comparisons in double -> bit-identical to numpy.  edges: device double[n_bins + 1], counts: device
+ * uint64[n_bins], accumulated (zero it first). */
+int nf_histogram(const float* data, int64_t count, const double* edges, int n_bins, unsigned long long* counts,
+                 void* stream);
+
 /* ---- host-buffer entry points (what NoiseFlowWrapper.sample_noise_nf / sess.run replace) -------- */
 /* Host pointers; copies are chunked and double-buffered on two internal streams.  Buffers from
  * nf_host_alloc (pinned) overlap copies with compute; pageable memory works but serialises.

@@ -568,6 +568,32 @@ int nf_unsqueeze2d(const float* x, int64_t n, int H, int W, int C, int factor, i
     return squeeze_common(x, n, H, W, C, factor, squeeze_type, out, stream, 1);
 }
 
+// ---- evaluation metrics next to the path ---------------------------------------------------------------
+static int cached_sm_count() {
+    static int sms = 0;
+    if (!sms) { int v = 0; if (nf_device_info(&v, nullptr, nullptr, nullptr) == NF_OK) sms = v; }
+    return sms ? sms : 148;
+}
+
+int nf_baseline_nll(const float* x, const float* y, float nlf0, float nlf1, float var_gauss, int64_t n, float* nll_gauss,
+                    float* nll_sdn, void* stream) {
+    if (n == 0) return NF_OK;
+    if (n < 0 || !x || !y || (!nll_gauss && !nll_sdn)) return fail(NF_ERR_INVALID, "x, y and an output are required");
+    if (!(var_gauss > 0.f)) return fail(NF_ERR_INVALID, "var_gauss must be positive");
+    cudaError_t e = nf::launch_baseline_nll(x, y, nlf0, nlf1, var_gauss, n, nll_gauss, nll_sdn, cached_sm_count(), (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(NF_ERR_CUDA, "baseline kernel launch: %s", cudaGetErrorString(e));
+    return NF_OK;
+}
+
+int nf_histogram(const float* data, int64_t count, const double* edges, int n_bins, unsigned long long* counts, void* stream) {
+    if (count == 0) return NF_OK;
+    if (count < 0 || !data || !edges || !counts) return fail(NF_ERR_INVALID, "null pointer or negative count");
+    if (n_bins < 1 || n_bins > 4096) return fail(NF_ERR_INVALID, "n_bins must be in [1, 4096]");
+    cudaError_t e = nf::launch_histogram(data, count, edges, n_bins, counts, cached_sm_count(), (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(NF_ERR_CUDA, "histogram kernel launch: %s", cudaGetErrorString(e));
+    return NF_OK;
+}
+
 // ---- host-buffer pipeline ---------------------------------------------------------------------------
 static const int64_t kChunk = 4096;   // patches per staged chunk: 64 MiB per tensor
 

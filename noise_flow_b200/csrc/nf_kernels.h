@@ -29,6 +29,10 @@ cudaError_t launch_squeeze(const float* in, float* out, long long n, int H, int 
 bool program_is_scale_only(const NfModelParams& mp, int first, int last);
 cudaError_t launch_scale_stream(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms,
                                 cudaStream_t stream);
+cudaError_t launch_baseline_nll(const float* x, const float* y, float nlf0, float nlf1, float var_gauss, long long n,
+                                float* nll_gauss, float* nll_sdn, int num_sms, cudaStream_t stream);
+cudaError_t launch_histogram(const float* data, long long count, const double* edges, int n_bins, unsigned long long* counts,
+                             int num_sms, cudaStream_t stream);
 bool tc_program_supported(const NfModelParams& mp, const NfChainArgs& a);
 cudaError_t launch_chain_tc(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, cudaStream_t stream);
 }  // namespace nf

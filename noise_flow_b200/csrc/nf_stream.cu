@@ -114,3 +114,98 @@ cudaError_t launch_scale_stream(const NfModelParams& mp, const NfChainArgs& args
 }
 
 }  // namespace nf
+
+// ================================================================================================
+// Evaluation metrics that sit right after the hot path in the reference's drivers:
+//   * Gaussian / camera-NLF NLL baselines  (sidd/PatchStatsCalculator.py:92-123, calc_baselines)
+//   * histograms for the marginal KL divergence (sidd/sidd_utils.py:1044-1052, 1266-1274)
+// Both are single streaming passes: HBM-bound, no shared state between patches except the histogram.
+// ================================================================================================
+namespace nf {
+
+// nll_gauss[p] = sum 0.5*(log 2pi + log vg + x^2/vg),  nll_sdn[p] = same with v = y*nlf0 + nlf1
+__global__ void __launch_bounds__(256)
+nf_baseline_nll_kernel(const float4* __restrict__ x, const float4* __restrict__ y, float nlf0, float nlf1, float var_gauss,
+                       long long n, float* __restrict__ nll_gauss, float* __restrict__ nll_sdn) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float log_vg = __logf(var_gauss), inv_vg = 1.f / var_gauss;
+    for (long long p = warp; p < n; p += nwarps) {
+        float sx2 = 0.f, ssdn = 0.f;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+            float4 xv[8], yv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                xv[j] = __ldcs(x + p * NF_PIXELS + (r0 + j) * 32 + lane);
+                yv[j] = __ldcs(y + p * NF_PIXELS + (r0 + j) * 32 + lane);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xs[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w}, ys[4] = {yv[j].x, yv[j].y, yv[j].z, yv[j].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float v = fmaf(ys[c], nlf0, nlf1), x2 = xs[c] * xs[c];
+                    sx2 += x2;
+                    ssdn += __logf(v) + __fdividef(x2, v);
+                }
+            }
+        }
+        sx2 = wsum(sx2);
+        ssdn = wsum(ssdn);
+        if (lane == 0) {
+            const float c = NF_DIMS * 1.8378770664093453f;
+            if (nll_gauss) nll_gauss[p] = 0.5f * (c + NF_DIMS * log_vg + sx2 * inv_vg);
+            if (nll_sdn) nll_sdn[p] = 0.5f * (c + ssdn);
+        }
+    }
+}
+
+// counts[b] += #{ data in [edges[b], edges[b+1]) }, last bin closed on the right (np.histogram semantics);
+// comparisons in double against the caller's double edges -> bit-identical bin decisions to numpy.
+__global__ void __launch_bounds__(256)
+nf_histogram_kernel(const float* __restrict__ data, long long count, const double* __restrict__ edges, int n_bins,
+                    unsigned long long* __restrict__ counts) {
+    extern __shared__ unsigned int sh_hist[];
+    double* sh_edges = reinterpret_cast<double*>(sh_hist + ((n_bins + 1) & ~1));
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) sh_hist[i] = 0u;
+    for (int i = threadIdx.x; i <= n_bins; i += blockDim.x) sh_edges[i] = edges[i];
+    __syncthreads();
+    const double lo = sh_edges[0], hi = sh_edges[n_bins];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)data[i];
+        if (!(v >= lo) || !(v <= hi)) continue;      // outside the range (or NaN): not counted
+        int a = 0, b = n_bins;                        // largest a with edges[a] <= v
+        while (b - a > 1) {
+            const int m = (a + b) >> 1;
+            if (v >= sh_edges[m]) a = m; else b = m;
+        }
+        atomicAdd(&sh_hist[a], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(&counts[i], (unsigned long long)sh_hist[i]);
+}
+
+cudaError_t launch_baseline_nll(const float* x, const float* y, float nlf0, float nlf1, float var_gauss, long long n,
+                                float* nll_gauss, float* nll_sdn, int num_sms, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    long long ctas = (n + 7) / 8;
+    if (ctas > (long long)num_sms * 8) ctas = (long long)num_sms * 8;
+    nf_baseline_nll_kernel<<<(unsigned)ctas, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y),
+                                                               nlf0, nlf1, var_gauss, n, nll_gauss, nll_sdn);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_histogram(const float* data, long long count, const double* edges, int n_bins, unsigned long long* counts,
+                             int num_sms, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    long long ctas = (count + 256 * 16 - 1) / (256 * 16);
+    if (ctas > (long long)num_sms * 8) ctas = (long long)num_sms * 8;
+    const size_t smem = (size_t)((n_bins + 1) & ~1) * 4 + (size_t)(n_bins + 1) * 8;
+    nf_histogram_kernel<<<(unsigned)ctas, 256, smem, stream>>>(data, count, edges, n_bins, counts);
+    return cudaGetLastError();
+}
+
+}  // namespace nf

@@ -753,3 +753,31 @@ def philox_normal(seed: int, offset: int, n_patches: int, first_patch: int = 0) 
         out[..., a] = rad * np.cos(ang)
         out[..., a + 1] = rad * np.sin(ang)
     return out.reshape(n_patches, 32, 32, 4)
+
+
+# =============================================================================================
+# evaluation metrics next to the path (sidd/PatchStatsCalculator.py:92-123, sidd/sidd_utils.py:1202-1274)
+# =============================================================================================
+def calc_baselines(x, y, nlf0, nlf1, var_gauss):
+    """PatchStatsCalculator.py:100-115: per-patch Gaussian and camera-NLF NLL (before the batch mean)."""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    vr = y * nlf0 + nlf1                                                              # :104
+    nll_g = 0.5 * (np.log(2 * np.pi) + np.log(var_gauss) + x ** 2 / var_gauss)        # :107-108
+    nll_s = 0.5 * (np.log(2 * np.pi) + np.log(vr) + x ** 2 / vr)                      # :112-113
+    return nll_g.sum(axis=(1, 2, 3)), nll_s.sum(axis=(1, 2, 3))
+
+
+def get_histogram(data, bin_edges):
+    """sidd_utils.py:1266-1274."""
+    n = np.prod(data.shape)
+    hist, _ = np.histogram(data, bin_edges)
+    return hist / n
+
+
+def kl_div_forward(p, q):
+    """sidd_utils.py:1202-1209."""
+    idx = ~(np.isnan(p) | np.isinf(p) | np.isnan(q) | np.isinf(q))
+    p, q = p[idx], q[idx]
+    idx = (p > 0) & (q > 0)
+    p, q = p[idx], q[idx]
+    return np.sum(p * np.log(p / q))
