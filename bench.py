@@ -305,6 +305,8 @@ def main():
             traffic = json.load(open(tp)).get("%s_%d" % (args.mode, B))
         except Exception:
             traffic = None
+    n_couplings = hps.arch.split("|").count("unc")
+    conv_flop = CONV_FLOP_PER_PATCH * n_couplings / 8.0
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     out = {"metric": "patches_per_sec_nll" if args.mode == "log_prob" else "patches_per_sec_sample",
@@ -319,10 +321,11 @@ def main():
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else "nf_chain_kernel",
                         "kernel_ms": kms, "alg_bytes_per_patch": alg,
-                        "note": "binding roof is the FP32 FMA pipe (see roofline_fp32), not HBM"},
-           "roofline_fp32": {"bound": "fp32_fma", "achieved": B * CONV_FLOP_PER_PATCH / (kms * 1e-3) / 1e12,
+                        "note": ("binding roof is the FP32 FMA pipe (see roofline_fp32), not HBM" if n_couplings else
+                                 "scale-layer-only chain: streaming kernel, HBM-bound")},
+           "roofline_fp32": {"bound": "fp32_fma", "achieved": B * conv_flop / (kms * 1e-3) / 1e12,
                              "peak": fp32_peak, "unit": "TFLOP/s",
-                             "frac": B * CONV_FLOP_PER_PATCH / (kms * 1e-3) / 1e12 / fp32_peak,
+                             "frac": B * conv_flop / (kms * 1e-3) / 1e12 / fp32_peak,
                              "peak_source": "148 SMs x 128 FMA/clk x 2 x median SM clock under load"},
            "e2e": e2e, "gpu_launches": world * args.steps * (2 if args.mode == "log_prob" else 1), "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
