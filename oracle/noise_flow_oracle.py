@@ -112,11 +112,13 @@ def unsqueeze2d(x, factor=2, squeeze_type="chessboard"):
 # borealisflows/matrix_param.py
 # =============================================================================================
 def fill_triangular(v, upper=False):
-    """TFP ``fill_triangular`` (the op matrix_param.py:44 calls), vector [m] -> [n,n], m=n(n+1)/2.
+    """TFP ``fill_triangular`` (the op matrix_param.py:44 calls), vector [m] -> [n,n], m = n(n+1)/2.
 
-    Published algorithm (tensorflow_probability/python/internal/distribution_util.py, v0.5):
-    ``x_tail = x[n:]``; lower: ``concat([x, reverse(x_tail)])`` reshaped [n,n] then band_part lower;
-    upper: ``concat([x_tail... ])`` variant: ``concat([x, reverse(x_tail)])`` -> reshape -> upper.
+    Published algorithm (tensorflow_probability/python/internal/distribution_util.py, v0.5; TFP is an un-vendored
+    dependency of the reference): with ``tail = x[n:]``,
+    lower: ``reshape(concat([tail, reverse(x)]), [n, n])`` then keep the lower triangle;
+    upper: ``reshape(concat([x, reverse(tail)]), [n, n])`` then keep the upper triangle.
+    Docstring example of the library: [1..6] -> [[4,0,0],[6,5,0],[3,2,1]] (lower), [[1,2,3],[0,5,6],[0,0,4]] (upper).
     """
     v = np.asarray(v)
     m = v.shape[-1]

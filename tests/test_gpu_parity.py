@@ -376,3 +376,40 @@ def test_training_mode_sampling_and_wrapper_default(golden_dir, shipped):
     xf = nf.forward(z, None, yy=y, iso=[100.0], cam=[2.0], is_training=True).cpu().numpy()
     xfo = orc2.forward(z, None, yy=y, iso=[100.0], cam=[2.0], is_training=True).numpy()
     assert np.abs(xf - xfo).max() < 1e-4 * (1 + np.abs(xfo).max())
+
+
+def test_many_python_threads_share_one_model(shipped):
+    """The reference drives one session from 16-32 Python threads (train_noise_flow.py:38-47,
+    train_dncnn_noiseflow.py:195-198): concurrent calls on one model must equal the serial results."""
+    import threading
+    hps, ck = shipped
+    nf = _nf(hps, ck, first_call="inverse")
+    jobs = []
+    for k in range(16):
+        x, y = synth_batch(64 + k, cam=2, iso=100, seed=100 + k)
+        eps = np.random.RandomState(200 + k).randn(64 + k, 32, 32, 4).astype(np.float32)
+        jobs.append((x, y, eps))
+    serial = [(nf._loss(x, y, iso=[100.0], cam=[2.0])[0].cpu().numpy(),
+               nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], eps=e).cpu().numpy()) for x, y, e in jobs]
+    out = [None] * len(jobs)
+    errs = []
+
+    def work(k):
+        try:
+            x, y, e = jobs[k]
+            s = torch.cuda.Stream(device="cuda:0")
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    a = nf._loss(x, y, iso=[100.0], cam=[2.0])[0]
+                    b = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], eps=e)
+                s.synchronize()
+            out[k] = (a.cpu().numpy(), b.cpu().numpy())
+        except Exception as ex:   # pragma: no cover
+            errs.append(ex)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for k in range(len(jobs)):
+        assert np.array_equal(out[k][0], serial[k][0]) and np.array_equal(out[k][1], serial[k][1]), k
