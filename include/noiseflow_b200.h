@@ -147,6 +147,25 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
                          uint64_t patch_base, float* out, float* logdet, float* nll, float* sdz, double* stats_ws,
                          float* batch_stats_host, void* stream);
 
+/* ---- training step support: loss and its gradient (train_noise_flow.py:187-198, 50-77) -------------------- */
+/* Gradient layout on the host: one block per bijector in add order, offsets[l] .. offsets[l+1] (doubles):
+ *   conv1x1  : 16  d loss / d A[in][out]           (chain to the LU variables on the host)
+ *   coupling : 285 [l_1/W 72][l_1/b 4][l_2/W 16][l_2/b 4][l_last/W 180][l_last/b 4][l_last/logs 4][rescaling_scale 1]
+ *              in exactly the checkpoint's tensor layouts
+ *   scale    : 2 * n_rows  d loss / d (a, b) (sdn) or d loss / d (g, -) (gain) per conditioning row
+ *   permute  : 0 */
+int nf_grad_layout(const nf_model* m, int64_t* offsets /* n_layers + 1 */);
+int nf_train_workspace_floats(const nf_model* m, int64_t n, int64_t* n_floats);
+/* loss = mean_n nll_n (NoiseFlow.loss, noise_flow_model.py:482-484) and d loss / d(every trainable variable).
+ * batch_stats != 0: BatchNorm on batch statistics (is_training=True) incl. its backward reductions; 0: moving
+ * statistics.  workspace: device floats (nf_train_workspace_floats); dscratch: device double[512]; grads_host:
+ * host doubles (nf_grad_layout); batch_stats_host (optional) as nf_chain_batch_stats; sums_host (optional) as
+ * nf_reduce_sums.  Activations are recomputed from the stored layer inputs; the gradients are accumulated in
+ * fp64.  Synchronises `stream`. */
+int nf_loss_and_grad(const nf_model* m, const float* x, const float* y, const int32_t* rows, int32_t default_row,
+                     int64_t n, int batch_stats, float* workspace, double* dscratch, double* grads_host,
+                     float* batch_stats_host, double* sums_host, void* stream);
+
 /* squeeze2d / unsqueeze2d (borealisflows/utils.py:30-86): bit-exact index permutation.
  * squeeze_type: 0 = 'chessboard' (also the unknown-type fallback), 1 = 'patch'.
  * H, W, C always describe the UN-squeezed tensor [n][H][W][C]. */

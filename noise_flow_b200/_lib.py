@@ -53,6 +53,10 @@ SIGNATURES = {
     "nf_chain_batch_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                        C.c_float, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nf_grad_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "nf_train_workspace_floats": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "nf_loss_and_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nf_reduce_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nf_baseline_nll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),

@@ -16,6 +16,7 @@
 #include "../../include/noiseflow_b200.h"
 #include "nf_kernels.h"
 #include "nf_params.h"
+#include "nf_train.h"
 
 namespace {
 
@@ -783,6 +784,213 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
     }
     NF_CUDA(cudaStreamSynchronize(stream));
     (void)n_cp;
+    return NF_OK;
+}
+
+// ---- training: loss + gradient of every trainable variable ---------------------------------------------
+namespace {
+struct Group { int lo, hi, cl; };   // bijectors [lo, hi) form one kernel op; cl = index of its coupling or -1
+
+std::vector<Group> make_groups(const nf_model* m) {
+    std::vector<Group> g;
+    const int L = (int)m->layers.size();
+    for (int l = 0; l < L;) {
+        const bool mix = m->layers[l].kind == L_CONV1X1 || m->layers[l].kind == L_PERMUTE;
+        if (mix && l + 1 < L && m->layers[l + 1].kind == L_COUPLING) { g.push_back({l, l + 2, l + 1}); l += 2; }
+        else { g.push_back({l, l + 1, m->layers[l].kind == L_COUPLING ? l : -1}); l += 1; }
+    }
+    return g;
+}
+
+void fill_train_coupling(const nf_model* m, const Group& g, const float* bn, NfTrainCoupling* P) {
+    const Layer& L = m->layers[g.cl];
+    memset(P, 0, sizeof(*P));
+    const bool fused = g.hi - g.lo == 2;
+    P->has_mix = fused ? 1 : 0;
+    for (int i = 0; i < 4; ++i)
+        for (int o = 0; o < 4; ++o) P->A[i][o] = fused ? m->layers[g.lo].a[o][i] : (i == o ? 1.f : 0.f);   // a[o][i] = A[i][o]
+    memcpy(P->w1, L.raw.l1_w, sizeof(P->w1));
+    memcpy(P->w2, L.raw.l2_w, sizeof(P->w2));
+    memcpy(P->w3, L.raw.last_w, sizeof(P->w3));
+    for (int k = 0; k < 4; ++k) {
+        P->b1[k] = L.raw.l1_b[k]; P->b2[k] = L.raw.l2_b[k]; P->b3[k] = L.raw.last_b[k]; P->logs[k] = L.raw.last_logs[k];
+        P->m1[k] = bn[k];      P->is1[k] = (float)(1.0 / sqrt((double)bn[4 + k] + (double)L.raw.bn_eps));
+        P->m2[k] = bn[8 + k];  P->is2[k] = (float)(1.0 / sqrt((double)bn[12 + k] + (double)L.raw.bn_eps));
+    }
+    P->scale = L.raw.rescaling_scale;
+}
+
+int64_t layer_grad_size(const Layer& L) {
+    switch (L.kind) {
+        case L_CONV1X1: return 16;
+        case L_COUPLING: return NF_G_HOST_COUPLING;
+        case L_SCALE: return 2 * (int64_t)L.n_rows;
+        default: return 0;
+    }
+}
+}  // namespace
+
+int nf_grad_layout(const nf_model* m, int64_t* offsets) {
+    if (!m || !offsets) return fail(NF_ERR_INVALID, "null argument");
+    int64_t off = 0;
+    for (size_t l = 0; l < m->layers.size(); ++l) { offsets[l] = off; off += layer_grad_size(m->layers[l]); }
+    offsets[m->layers.size()] = off;
+    return NF_OK;
+}
+
+int nf_train_workspace_floats(const nf_model* m, int64_t n, int64_t* n_floats) {
+    if (!m || !n_floats || n < 0) return fail(NF_ERR_INVALID, "bad argument");
+    const int64_t G = (int64_t)make_groups(m).size();
+    *n_floats = (G + 4) * n * NF_DIMS + 2 * n;
+    return NF_OK;
+}
+
+int nf_loss_and_grad(const nf_model* m, const float* x, const float* y, const int32_t* rows, int32_t default_row, int64_t n,
+                     int batch_stats, float* workspace, double* dscratch, double* grads_host, float* batch_stats_host,
+                     double* sums_host, void* stream_) {
+    int rc = check_ready(m);
+    if (rc) return rc;
+    if (n <= 0 || !x || !workspace || !dscratch || !grads_host) return fail(NF_ERR_INVALID, "x, workspace, dscratch, grads_host are required and n > 0");
+    if (default_row < 0 || default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const std::vector<Group> groups = make_groups(m);
+    const int G = (int)groups.size();
+    const int64_t S = n * NF_DIMS;
+    auto slot = [&](int k) { return workspace + (int64_t)k * S; };
+    float *gA = slot(G), *gB = slot(G + 1), *scratch = slot(G + 2), *gzp = slot(G + 3);
+    float *d_nll = slot(G + 4), *d_sdz = d_nll + n;
+    double *d_cg = dscratch, *d_stats = dscratch + 320, *d_sums = dscratch + 328, *d_sg = dscratch + 336;
+    const double cnt = (double)n * NF_PIXELS;
+    const int sms = num_ctas_for(m);
+    std::vector<int64_t> goff(m->layers.size() + 1);
+    nf_grad_layout(m, goff.data());
+    memset(grads_host, 0, sizeof(double) * (size_t)goff.back());
+    std::vector<float> bn_all((size_t)G * 16, 0.f);
+
+    // ------------------------------------------------------------ forward, keeping every op's input
+    for (int g = 0; g < G; ++g) {
+        const Group& gr = groups[g];
+        const float* in = g == 0 ? x : slot(g - 1);
+        float* out = slot(g);
+        float* bn = &bn_all[(size_t)g * 16];
+        if (!y && range_has_sdn(m, gr.lo, gr.hi)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
+        if (gr.cl >= 0) {
+            const Layer& L = m->layers[gr.cl];
+            if (batch_stats) {
+                for (int k = 0; k < 4; ++k) { bn[k] = 0.f; bn[8 + k] = 0.f; bn[4 + k] = bn[12 + k] = 1.0f - L.raw.bn_eps; }
+                for (int stage = 1; stage <= 2; ++stage) {
+                    NfModelParams mp;
+                    float ldjc = 0.f;
+                    { std::lock_guard<std::mutex> lock(m->prog_mu); rc = build_program(m, gr.lo, gr.hi, &mp, &ldjc, gr.cl, bn); }
+                    if (rc) return rc;
+                    NF_CUDA(cudaMemsetAsync(d_stats, 0, 8 * sizeof(double), stream));
+                    NfChainArgs a = {};
+                    a.in = in; a.y = y; a.rows = rows; a.n = n; a.default_row = default_row; a.temp = 1.f;
+                    a.first_layer = 0; a.last_layer = mp.n_layers; a.bn_stats = d_stats; a.bn_stage = stage;
+                    cudaError_t e = nf::launch_chain(mp, a, true, sms, m->warps_per_cta, stream);
+                    if (e != cudaSuccess) return fail(NF_ERR_CUDA, "probe launch: %s", cudaGetErrorString(e));
+                    double h[8];
+                    NF_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, stream));
+                    NF_CUDA(cudaStreamSynchronize(stream));
+                    for (int k = 0; k < 4; ++k) {
+                        const double mean = h[k] / cnt;
+                        double var = h[4 + k] / cnt - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        bn[(stage - 1) * 8 + k] = (float)mean;
+                        bn[(stage - 1) * 8 + 4 + k] = (float)var;
+                    }
+                }
+            } else {
+                memcpy(bn, L.raw.bn1_mean, 16); memcpy(bn + 4, L.raw.bn1_var, 16);
+                memcpy(bn + 8, L.raw.bn2_mean, 16); memcpy(bn + 12, L.raw.bn2_var, 16);
+            }
+            if (batch_stats_host) {
+                int idx = 0;
+                for (int l = 0; l < gr.cl; ++l) idx += m->layers[l].kind == L_COUPLING;
+                memcpy(batch_stats_host + 16 * idx, bn, 16 * sizeof(float));
+            }
+        }
+        NfModelParams mp;
+        float ldjc = 0.f;
+        { std::lock_guard<std::mutex> lock(m->prog_mu); rc = build_program(m, gr.lo, gr.hi, &mp, &ldjc, gr.cl, gr.cl >= 0 ? bn : nullptr); }
+        if (rc) return rc;
+        NfChainArgs a = {};
+        a.in = in; a.y = y; a.rows = rows; a.out = out; a.n = n; a.default_row = default_row; a.temp = 1.f;
+        a.first_layer = 0; a.last_layer = mp.n_layers; a.ldj_const = ldjc;
+        a.logdet_in = g > 0 ? d_nll : nullptr;
+        if (g + 1 == G) { a.nll = d_nll; a.sdz = d_sdz; } else a.logdet = d_nll;
+        cudaError_t e = nf::launch_chain(mp, a, true, sms, m->warps_per_cta, stream);
+        if (e != cudaSuccess) return fail(NF_ERR_CUDA, "forward launch: %s", cudaGetErrorString(e));
+    }
+    if (sums_host) {
+        cudaError_t e = nf::launch_reduce(d_nll, d_sdz, n, d_sums, stream);
+        if (e != cudaSuccess) return fail(NF_ERR_CUDA, "reduce launch: %s", cudaGetErrorString(e));
+        NF_CUDA(cudaMemcpyAsync(sums_host, d_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    // ------------------------------------------------------------ backward
+    {
+        cudaError_t e = nf::launch_train_prior(slot(G - 1), gA, n, sms, stream);
+        if (e != cudaSuccess) return fail(NF_ERR_CUDA, "prior launch: %s", cudaGetErrorString(e));
+    }
+    for (int g = G - 1; g >= 0; --g) {
+        const Group& gr = groups[g];
+        const float* zin = g == 0 ? x : slot(g - 1);
+        const float* zout = slot(g);
+        cudaError_t e = cudaSuccess;
+        if (gr.cl >= 0) {
+            NfTrainCoupling P;
+            fill_train_coupling(m, gr, &bn_all[(size_t)g * 16], &P);
+            NF_CUDA(cudaMemsetAsync(d_cg, 0, NF_G_COUPLING_DOUBLES * sizeof(double), stream));
+            e = nf::launch_train_b1(P, zin, gA, gzp, scratch, n, d_cg, sms, stream);
+            if (e != cudaSuccess) return fail(NF_ERR_CUDA, "B1 launch: %s", cudaGetErrorString(e));
+            double h[8];
+            NfBnTerms t2 = {}, t1 = {};
+            if (batch_stats) {
+                NF_CUDA(cudaMemcpyAsync(h, d_cg + NF_G_BN2, sizeof(h), cudaMemcpyDeviceToHost, stream));
+                NF_CUDA(cudaStreamSynchronize(stream));
+                for (int k = 0; k < 8; ++k) t2.v[k] = (float)(h[k] / cnt);
+            }
+            e = nf::launch_train_b2(P, zin, scratch, n, t2, d_cg, sms, stream);
+            if (e != cudaSuccess) return fail(NF_ERR_CUDA, "B2 launch: %s", cudaGetErrorString(e));
+            if (batch_stats) {
+                NF_CUDA(cudaMemcpyAsync(h, d_cg + NF_G_BN1, sizeof(h), cudaMemcpyDeviceToHost, stream));
+                NF_CUDA(cudaStreamSynchronize(stream));
+                for (int k = 0; k < 8; ++k) t1.v[k] = (float)(h[k] / cnt);
+            }
+            e = nf::launch_train_b3(P, zin, scratch, gzp, gB, n, t1, d_cg, sms, stream);
+            if (e != cudaSuccess) return fail(NF_ERR_CUDA, "B3 launch: %s", cudaGetErrorString(e));
+            double hg[NF_G_COUPLING_DOUBLES];
+            NF_CUDA(cudaMemcpyAsync(hg, d_cg, sizeof(hg), cudaMemcpyDeviceToHost, stream));
+            NF_CUDA(cudaStreamSynchronize(stream));
+            memcpy(grads_host + goff[gr.cl], hg + NF_G_W1, NF_G_HOST_COUPLING * sizeof(double));   // W1..scale are contiguous
+            if (gr.hi - gr.lo == 2 && m->layers[gr.lo].kind == L_CONV1X1) memcpy(grads_host + goff[gr.lo], hg + NF_G_A, 16 * sizeof(double));
+        } else {
+            const Layer& L = m->layers[gr.lo];
+            if (L.kind == L_SCALE) {
+                NfTrainScale T = {};
+                for (int r = 0; r < NF_MAX_ROWS; ++r) { T.t[r][0] = L.table[r][0]; T.t[r][1] = L.table[r][1]; }
+                T.is_sdn = L.scale_kind == NF_SCALE_SDN; T.full_sum = L.full_sum;
+                NF_CUDA(cudaMemsetAsync(d_sg, 0, 2 * NF_MAX_ROWS * sizeof(double), stream));
+                e = nf::launch_train_scale(zout, y, gA, gB, rows, default_row, n, T, d_sg, sms, stream);
+                if (e != cudaSuccess) return fail(NF_ERR_CUDA, "scale backward launch: %s", cudaGetErrorString(e));
+                NF_CUDA(cudaMemcpyAsync(grads_host + goff[gr.lo], d_sg, 2 * (size_t)L.n_rows * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                NF_CUDA(cudaStreamSynchronize(stream));
+            } else {   // stand-alone conv1x1 / permutation
+                NfTrainMix M;
+                for (int i = 0; i < 4; ++i)
+                    for (int o = 0; o < 4; ++o) M.A[i][o] = L.a[o][i];
+                NF_CUDA(cudaMemsetAsync(d_cg, 0, 16 * sizeof(double), stream));
+                e = nf::launch_train_mix(zin, gA, gB, n, M, d_cg, sms, stream);
+                if (e != cudaSuccess) return fail(NF_ERR_CUDA, "mix backward launch: %s", cudaGetErrorString(e));
+                if (L.kind == L_CONV1X1) {
+                    NF_CUDA(cudaMemcpyAsync(grads_host + goff[gr.lo], d_cg, 16 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                    NF_CUDA(cudaStreamSynchronize(stream));
+                }
+            }
+        }
+        float* t = gA; gA = gB; gB = t;
+    }
+    NF_CUDA(cudaStreamSynchronize(stream));
     return NF_OK;
 }
 

@@ -1,0 +1,58 @@
+// Parameter blocks and gradient layout of the backward kernels (nf_train.cu); host side in nf_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "nf_params.h"
+
+// Raw (un-folded) parameters of one coupling as the reference stores them, plus the BatchNorm statistics in
+// force for this step (batch statistics when is_training, moving statistics otherwise) as mean / 1/sqrt(var+eps).
+struct NfTrainCoupling {
+    float A[4][4];            // fused 1x1 conv, [in][out] (identity when has_mix == 0)
+    float w1[3][3][2][4];     // TF layout [kh][kw][in][out]
+    float w2[4][4];           // [in][out]
+    float w3[3][3][5][4];     // in = 4 hidden channels + edge indicator
+    float b1[4], m1[4], is1[4];
+    float b2[4], m2[4], is2[4];
+    float b3[4], logs[4];
+    float scale;
+    int32_t has_mix;
+    float pad_[2];
+};
+
+struct NfBnTerms { float v[8]; };    // [0..3] = mean(g_hat), [4..7] = mean(g_hat * x_hat); zeros for moving statistics
+
+struct NfTrainScale {
+    float t[NF_MAX_ROWS][2];          // sdn: (a, b); gain: (g, -)
+    int32_t is_sdn, full_sum;
+};
+
+struct NfTrainMix { float A[4][4]; };   // [in][out]
+
+// device gradient block of one coupling (doubles)
+#define NF_G_A 0        // 16  d loss / d A[in][out]
+#define NF_G_W1 16      // 72
+#define NF_G_B1 88      // 4
+#define NF_G_W2 92      // 16
+#define NF_G_B2 108     // 4
+#define NF_G_W3 112     // 180
+#define NF_G_B3 292     // 4
+#define NF_G_LOGS 296   // 4
+#define NF_G_SCALE 300  // 1
+#define NF_G_BN2 304    // 8: sum g_c2hat, sum g_c2hat * c2hat
+#define NF_G_BN1 312    // 8
+#define NF_G_COUPLING_DOUBLES 320
+// host gradient block of one coupling: [W1 72][b1 4][W2 16][b2 4][W3 180][b3 4][logs 4][scale 1]
+#define NF_G_HOST_COUPLING 285
+
+namespace nf {
+cudaError_t launch_train_b1(const NfTrainCoupling& P, const float* zin, const float* gout, float* gzp, float* scratch, long long n,
+                            double* grads, int num_sms, cudaStream_t s);
+cudaError_t launch_train_b2(const NfTrainCoupling& P, const float* zin, float* scratch, long long n, const NfBnTerms& bn2,
+                            double* grads, int num_sms, cudaStream_t s);
+cudaError_t launch_train_b3(const NfTrainCoupling& P, const float* zin, const float* scratch, const float* gzp, float* gin,
+                            long long n, const NfBnTerms& bn1, double* grads, int num_sms, cudaStream_t s);
+cudaError_t launch_train_scale(const float* zout, const float* y, const float* gout, float* gin, const int* rows, int default_row,
+                               long long n, const NfTrainScale& T, double* grads, int num_sms, cudaStream_t s);
+cudaError_t launch_train_mix(const float* zin, const float* gout, float* gin, long long n, const NfTrainMix& M, double* grads,
+                             int num_sms, cudaStream_t s);
+cudaError_t launch_train_prior(const float* z, float* g, long long n, int num_sms, cudaStream_t s);
+}  // namespace nf

@@ -217,17 +217,22 @@ class NoiseFlow(object):
                 int(patch_base), out.data_ptr(), p(ld), p(nll), p(sdz), ws.data_ptr(),
                 bstats.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)), "nf_chain_batch_stats")
         if n > 0:
-            with self._lock:   # moving-average update (decay 0.1), then re-fold the moving-statistics engine
-                v = self.spec.store.vars
-                for k, l in enumerate(cps):
-                    s = l.data["template"]
-                    for j, name in enumerate(("bn_nvp_conv_1/mean", "bn_nvp_conv_1/var", "bn_nvp_conv_2/mean",
-                                              "bn_nvp_conv_2/var")):
-                        cur = v["%s/%s" % (s, name)]
-                        cur -= np.float32(0.1) * (cur - bstats[k, 4 * j:4 * j + 4])
-                self._engine.refresh_parameters(self._extra_rows)
-        self.last_batch_stats = bstats
+            self._apply_bn_moving_update(bstats)
         return out, ld, nll, sdz
+
+    def _apply_bn_moving_update(self, bstats):
+        """``train_m -= 0.1 * (train_m - m)`` (layers.py:394-395) for every coupling, then re-fold the engine."""
+        cps = [l for l in self.spec.layers if l.kind == "coupling"]
+        with self._lock:
+            v = self.spec.store.vars
+            for k, l in enumerate(cps):
+                s = l.data["template"]
+                for j, name in enumerate(("bn_nvp_conv_1/mean", "bn_nvp_conv_1/var", "bn_nvp_conv_2/mean",
+                                          "bn_nvp_conv_2/var")):
+                    cur = v["%s/%s" % (s, name)]
+                    cur -= np.float32(0.1) * (cur - bstats[k, 4 * j:4 * j + 4])
+            self._engine.refresh_parameters(self._extra_rows)
+        self.last_batch_stats = bstats
 
     def _dev(self, a, name):
         if a is None:

@@ -1,0 +1,238 @@
+"""Train-step support for the reference's driver (``train_noise_flow.py:187-198,50-77``): gradient of the batch-mean
+NLL with respect to every trainable TF variable, Adam with TensorFlow's update rule, and the data-parallel
+reduction.
+
+The device does the heavy part (``nf_loss_and_grad``: forward with batch-statistics BatchNorm, three backward passes
+per coupling, fp64 gradient accumulation).  What is left for the host is the chain rule through the two tiny
+parameterisations that live on the host anyway -- the 4x4 LU construction (``matrix_param.py:117-138``) and the
+per-(camera, ISO) scale scalars (``cond_utils.py``) -- done here with torch autograd on a handful of scalars.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .params import GAIN_TOKENS, ISO_VALS, SDN_TOKENS, vec2stricttri
+
+_T64 = torch.float64
+
+
+# ------------------------------------------------------------------------------------------------ host chain rules
+def _tri_index(n: int, upper: bool) -> np.ndarray:
+    m = n * (n - 1) // 2
+    return vec2stricttri(np.arange(1, m + 1, dtype=np.float64), upper).astype(np.int64)
+
+
+def lu_chain(v: Dict[str, np.ndarray], vscope: str, pname: str, dA: np.ndarray) -> Dict[str, np.ndarray]:
+    """d loss / d (L_vec, U_vec, log_S) from d loss / d A for ``A = P L U`` (matrix_param.py:117-130)."""
+    names = {k: "%s/%s_matpar_lu_%s" % (vscope, k, pname) for k in ("P", "L_vec", "U_vec", "log_S", "sign_S")}
+    p = torch.as_tensor(v[names["P"]], dtype=_T64)
+    sign_s = torch.as_tensor(v[names["sign_S"]], dtype=_T64)
+    l_vec = torch.as_tensor(v[names["L_vec"]], dtype=_T64).requires_grad_(True)
+    u_vec = torch.as_tensor(v[names["U_vec"]], dtype=_T64).requires_grad_(True)
+    log_s = torch.as_tensor(v[names["log_S"]], dtype=_T64).requires_grad_(True)
+    n = p.shape[0]
+    li, ui = torch.as_tensor(_tri_index(n, False)), torch.as_tensor(_tri_index(n, True))
+    l = torch.cat([l_vec.new_zeros(1), l_vec])[li] + torch.eye(n, dtype=_T64)
+    u = torch.cat([u_vec.new_zeros(1), u_vec])[ui] + torch.diag(sign_s * torch.exp(log_s))
+    a = p @ (l @ u)
+    (a * torch.as_tensor(dA, dtype=_T64)).sum().backward()
+    return {names["L_vec"]: l_vec.grad.numpy(), names["U_vec"]: u_vec.grad.numpy(), names["log_S"]: log_s.grad.numpy()}
+
+
+def _scale_row_torch(token, tv, hps, cam, iso):
+    """Differentiable twin of ``params.scale_row`` for the trainable tokens: returns (a, b) or (g, None)."""
+    gain_init = float(getattr(hps, "gain_init", 0.0))
+    sig = torch.sigmoid
+
+    def ladder(fmt):
+        key = int(iso) if float(iso) in ISO_VALS else 800
+        return tv["model/" + fmt % key][0]
+
+    def onehot(gp):
+        for k, val in enumerate(ISO_VALS):
+            if float(iso) == val:
+                return gp[k]
+        return gp.new_zeros(())
+
+    if token == "sdn":
+        return sig(tv["model/b1"][0]), sig(tv["model/b2"][0])
+    if token == "sdn1":
+        r_gain = torch.exp(1e-2 * ladder("r_gain_param_%05d")) * iso
+        return sig(tv["model/b1"][0]) / r_gain, sig(tv["model/b2"][0])
+    if token in ("sdn2", "sdn3"):
+        gain = torch.exp(1e-1 * ladder("gain_param_%05d")) * iso
+        b1, b2 = sig(tv["model/b1"][0]), sig(tv["model/b2"][0])
+        return (b1, gain * b2) if token == "sdn2" else (gain * b1, gain * gain * b2)
+    if token == "sdn4":
+        s = "model/sdn_gain"
+        gain = torch.exp(onehot(tv[s + "/gain_params"])) * iso
+        return torch.exp(tv[s + "/beta1"][0]) / gain, torch.exp(tv[s + "/beta2"][0])
+    if token in ("sdn5", "sdn6"):
+        c_i = hps.param_inits[0]
+        s = "model/sdn_gain"
+        ocp = torch.exp(c_i * tv[s + "/cam_params"][:, int(cam)])
+        gsel = onehot(tv[s + "/gain_params"])
+        beta1, beta2 = tv[s + "/beta1"][0], tv[s + "/beta2"][0]
+        if token == "sdn5":
+            gain = torch.exp(c_i * gsel * ocp[2]) * iso
+            return torch.exp(c_i * beta1 * ocp[0]) / gain, torch.exp(c_i * beta2 * ocp[1])
+        gain = torch.exp(c_i * gsel * ocp[0]) * iso
+        return torch.exp(c_i * beta1) / gain, torch.exp(c_i * beta2)
+    if token == "gain":
+        return sig(tv["model/g1"][0]) * iso + sig(tv["model/g2"][0]), None
+    if token == "gain1":
+        return torch.exp(1e-5 * tv["model/g1"][0]) * iso + torch.exp(1e-5 * tv["model/g2"][0]), None
+    if token == "gain2":
+        return torch.exp(1e-1 * ladder("gain_param_%05d")) * iso, None
+    if token == "gain3":
+        return torch.exp(1e-5 * ladder("gain_param_%05d")), None
+    if token == "gain4":
+        return tv["model/sdn_gain/gain_val"][0], None
+    return None, None      # camsdn: no trainable parameters
+
+
+def scale_chain(spec, layer, dtable: np.ndarray, extra_rows) -> Dict[str, np.ndarray]:
+    """d loss / d (scale-layer variables) from d loss / d (table rows)."""
+    rows = [(float(cam), iso) for cam in range(5) for iso in ISO_VALS] + [(r[0], r[1]) for r in (extra_rows or [])]
+    used = [k for k in range(min(len(rows), dtable.shape[0])) if dtable[k].any()]
+    if not used or layer.token == "camsdn":
+        return {}
+    names = [k for k in spec.store.vars if k.startswith("model/") and "real_nvp_conv_template" not in k]
+    tv = {k: torch.as_tensor(spec.store.vars[k], dtype=_T64).clone().requires_grad_(True) for k in names}
+    total = None
+    for k in used:
+        a, b = _scale_row_torch(layer.token, tv, spec.hps, rows[k][0], rows[k][1])
+        if a is None:
+            continue
+        term = a * float(dtable[k, 0])
+        if b is not None:
+            term = term + b * float(dtable[k, 1])
+        total = term if total is None else total + term
+    if total is None or not total.requires_grad:
+        return {}
+    total.backward()
+    return {k: t.grad.numpy() for k, t in tv.items() if t.grad is not None}
+
+
+# ------------------------------------------------------------------------------------------------ loss + gradients
+def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_training=True):
+    """``(loss, sd_z, grads)``: ``loss = mean_n nll_n`` (``NoiseFlow.loss``) and ``grads[tf_variable_name]`` (float64
+    numpy, same shapes as the variables) for every trainable variable.  With ``is_training`` (the reference's train
+    thread, ``train_noise_flow.py:64-71``) BatchNorm runs on batch statistics and the moving statistics are updated."""
+    nf.build("inverse")
+    eng, spec = nf._engine, nf.spec
+    lib = eng.lib
+    x = nf._dev(x, "x")
+    cond = getattr(nf.hps, "sidd_cond", "mix")
+    yy = nf._dev(y, "y") if (cond is not None and cond != "uncond") else None
+    n = x.shape[0]
+    if n == 0:
+        raise ValueError("empty batch")
+    rows, drow = nf._rows(n, nlf0, nlf1, iso, cam)
+    n_layers = len(spec.layers)
+    offs = (C.c_int64 * (n_layers + 1))()
+    _lib.check(lib.nf_grad_layout(eng.handle, offs), "nf_grad_layout")
+    nws = C.c_int64()
+    _lib.check(lib.nf_train_workspace_floats(eng.handle, n, C.byref(nws)), "nf_train_workspace_floats")
+    ws = torch.empty(nws.value, device=nf.device, dtype=torch.float32)
+    dscr = torch.zeros(512, device=nf.device, dtype=torch.float64)
+    flat = np.zeros(max(int(offs[n_layers]), 1), dtype=np.float64)
+    cps = [l for l in spec.layers if l.kind == "coupling"]
+    bstats = np.zeros((max(len(cps), 1), 16), dtype=np.float32)
+    sums = (C.c_double * 3)()
+    p = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(nf.device):
+        _lib.check(lib.nf_loss_and_grad(eng.handle, x.data_ptr(), p(yy), p(rows), drow, n, 1 if is_training else 0,
+                                        ws.data_ptr(), dscr.data_ptr(), flat.ctypes.data_as(C.c_void_p),
+                                        bstats.ctypes.data_as(C.c_void_p), sums,
+                                        int(torch.cuda.current_stream(nf.device).cuda_stream)), "nf_loss_and_grad")
+    grads: Dict[str, np.ndarray] = {}
+    v = spec.store.vars
+
+    def add(name, g):
+        g = np.asarray(g, dtype=np.float64).reshape(v[name].shape)
+        grads[name] = grads[name] + g if name in grads else g
+
+    for idx, l in enumerate(spec.layers):
+        blk = flat[offs[idx]:offs[idx + 1]]
+        if l.kind == "conv1x1":
+            for k, g in lu_chain(v, l.data["vscope"], l.data["pname"], blk.reshape(4, 4)).items():
+                add(k, g)
+            # the layer's own log-det, H*W*sum(log_S) per patch (layers.py:129-130), enters the loss as -ldj
+            add("%s/log_S_matpar_lu_%s" % (l.data["vscope"], l.data["pname"]), np.full(4, -1024.0))
+        elif l.kind == "coupling":
+            s = l.data["template"]
+            o = 0
+            for name, size in (("/l_1/W", 72), ("/l_1/b", 4), ("/l_2/W", 16), ("/l_2/b", 4), ("/l_last/W", 180),
+                               ("/l_last/b", 4), ("/l_last/logs", 4)):
+                add(s + name, blk[o:o + size])
+                o += size
+            add(l.scope + "/rescaling_scale0", blk[o])
+        elif l.kind == "scale":
+            for k, g in scale_chain(spec, l, blk.reshape(-1, 2), nf._extra_rows).items():
+                add(k, g)
+    for name, trainable in spec.store.trainable.items():      # variables the loss does not depend on
+        if trainable and name not in grads:
+            grads[name] = np.zeros(v[name].shape, dtype=np.float64)
+    if is_training:
+        nf._apply_bn_moving_update(bstats)
+    loss = sums[0] / n
+    sd_z = sums[1] / n
+    return loss, sd_z, grads
+
+
+# ------------------------------------------------------------------------------------------------ Adam (TF semantics)
+class AdamOptimizer:
+    """``tf.train.AdamOptimizer(learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8)`` (train_noise_flow.py:191-194):
+    ``lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)``; ``m = b1 m + (1-b1) g``; ``v = b2 v + (1-b2) g^2``;
+    ``var -= lr_t * m / (sqrt(v) + eps)``."""
+
+    def __init__(self, learning_rate=1e-4, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta1, beta2, epsilon
+        self.t = 0
+        self.m: Dict[str, np.ndarray] = {}
+        self.v: Dict[str, np.ndarray] = {}
+
+    def apply_gradients(self, variables: Dict[str, np.ndarray], grads: Dict[str, np.ndarray]):
+        self.t += 1
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        for k, g in grads.items():
+            g = np.asarray(g, dtype=np.float64)
+            m = self.m.setdefault(k, np.zeros_like(g))
+            vv = self.v.setdefault(k, np.zeros_like(g))
+            m += (1.0 - self.b1) * (g - m)
+            vv += (1.0 - self.b2) * (g * g - vv)
+            variables[k] = (variables[k].astype(np.float64) - lr_t * m / (np.sqrt(vv) + self.eps)).astype(np.float32)
+
+
+def train_step(nf, optimizer: AdamOptimizer, x, y, nlf0=None, nlf1=None, iso=None, cam=None, group=None):
+    """One ``sess.run([train_op, loss, sd_z], is_training=True)`` (train_noise_flow.py:50-77) on this rank's shard.
+    With ``torch.distributed`` initialised, gradients and ``[sum nll, sum sd_z, n]`` are summed over ranks with ONE
+    all-reduce (gradients are then divided by the world size: every rank's loss is the mean over ITS shard, and
+    BatchNorm statistics stay per rank, which is the reference's per-``sess.run`` semantics)."""
+    import torch.distributed as dist
+    loss, sd_z, grads = loss_and_grad(nf, x, y, nlf0, nlf1, iso, cam, is_training=True)
+    names = sorted(grads)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        n = int(np.asarray(x).shape[0]) if not isinstance(x, torch.Tensor) else x.shape[0]
+        flat = np.concatenate([grads[k].reshape(-1) for k in names] + [np.array([loss * n, sd_z * n, float(n)])])
+        t = torch.as_tensor(flat, dtype=torch.float64, device=nf.device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        flat = t.cpu().numpy()
+        o = 0
+        for k in names:
+            sz = grads[k].size
+            grads[k] = flat[o:o + sz].reshape(grads[k].shape) / world
+            o += sz
+        loss, sd_z = flat[o] / flat[o + 2], flat[o + 1] / flat[o + 2]
+    trainable = {k: g for k, g in grads.items() if nf.spec.store.trainable.get(k, False)}
+    optimizer.apply_gradients(nf.spec.store.vars, trainable)
+    nf.refresh_parameters()
+    return loss, sd_z
