@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="patches per GPU per step")
-    ap.add_argument("--mode", default="log_prob", choices=["log_prob", "sample"])
+    ap.add_argument("--mode", default="log_prob", choices=["log_prob", "sample", "train"])
     ap.add_argument("--ref-patches", type=int, default=1024)
     ap.add_argument("--warps", type=int, default=0, help="resident patches per CTA (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -204,6 +204,8 @@ def main():
     row = 2 * 5 + 0   # S6, ISO 100
 
     def kernel_only(i):
+        if args.mode == "train":
+            return
         if args.mode == "log_prob":
             _lib.check(lib.nf_log_prob(eng.handle, x.data_ptr(), y.data_ptr(), None, row, B, nll.data_ptr(),
                                        sdz.data_ptr(), None, stream))
@@ -211,7 +213,15 @@ def main():
             _lib.check(lib.nf_sample(eng.handle, y.data_ptr(), None, row, B, 0.6, None, 7, i, rank * B,
                                      xs.data_ptr(), stream))
 
+    train_opt = None
+    if args.mode == "train":
+        from noise_flow_b200.train import AdamOptimizer, train_step
+        train_opt = AdamOptimizer(learning_rate=1e-4)
+
     def step(i):
+        if args.mode == "train":     # BASELINE config 5: one Adam step (batch-stat BN forward + backward + update)
+            train_step(nf, train_opt, x, y, iso=[100.0], cam=[2.0])
+            return
         kernel_only(i)
         if args.mode == "log_prob":
             _lib.check(lib.nf_reduce_sums(nll.data_ptr(), sdz.data_ptr(), B, sums.data_ptr(), stream))
@@ -255,7 +265,7 @@ def main():
 
     # ---- e2e: host buffers through the C-ABI host entry point (copies inside the timed region)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.mode != "train":
         import ctypes as C
         nb = B * 4096 * 4
         hx_t = torch.empty((B, 32, 32, 4), dtype=torch.float32, pin_memory=True)
@@ -309,7 +319,10 @@ def main():
     conv_flop = CONV_FLOP_PER_PATCH * n_couplings / 8.0
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    out = {"metric": "patches_per_sec_nll" if args.mode == "log_prob" else "patches_per_sec_sample",
+    if args.mode == "train":
+        kms = ms / args.steps
+    out = {"metric": {"log_prob": "patches_per_sec_nll", "sample": "patches_per_sec_sample",
+                      "train": "patches_per_sec_adam_step"}[args.mode],
            "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
