@@ -177,8 +177,8 @@ __device__ __forceinline__ void mix_pass(const NfMixP& M, const ZStore& zs) {
     for (int o = 0; o < 4; ++o)
 #pragma unroll
         for (int i = 0; i < 4; ++i) m[o][i] = INV ? M.a[o][i] : M.ainv[o][i];
-#pragma unroll 4
     zs.commit();
+#pragma unroll 4
     for (int r = 0; r < 32; ++r) zs.store(r, mix4(zs.load(r), m));
     zs.commit();
 }
