@@ -5,7 +5,8 @@ legs may import this module.  The product (``noise_flow_b200``) never does.
 
 PARITY UNPINNED: the reference (BorealisAI/noise_flow, TF 1.12 / TFP 0.5) ships no tests and
 TensorFlow cannot run in this environment, so this restatement is pinned only by (a) the shipped
-checkpoint artefacts (tensor names / shapes / ``num_params`` / layer names), (b) closed-form
+checkpoint artefacts (tensor names / shapes / ``num_params`` / layer names) and the initial-value
+constants of the shipped ``.meta`` graph (LU assembly and 6-vector ordering, initialisers), (b) closed-form
 known answers derived from the reference's own formulas and (c) self-consistency
 (round trips, brute-force Jacobians).  See DESIGN.md "Oracle".
 
