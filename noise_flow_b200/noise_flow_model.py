@@ -220,7 +220,7 @@ class NoiseFlow(object):
             self._apply_bn_moving_update(bstats)
         return out, ld, nll, sdz
 
-    def _apply_bn_moving_update(self, bstats):
+    def _apply_bn_moving_update(self, bstats, refold=True):
         """``train_m -= 0.1 * (train_m - m)`` (layers.py:394-395) for every coupling, then re-fold the engine."""
         cps = [l for l in self.spec.layers if l.kind == "coupling"]
         with self._lock:
@@ -231,7 +231,8 @@ class NoiseFlow(object):
                                           "bn_nvp_conv_2/var")):
                     cur = v["%s/%s" % (s, name)]
                     cur -= np.float32(0.1) * (cur - bstats[k, 4 * j:4 * j + 4])
-            self._engine.refresh_parameters(self._extra_rows)
+            if refold:
+                self._engine.refresh_parameters(self._extra_rows)
         self.last_batch_stats = bstats
 
     def _dev(self, a, name):

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .params import GAIN_TOKENS, ISO_VALS, SDN_TOKENS, vec2stricttri
+from .params import GAIN_TOKENS, ISO_VALS, SDN_TOKENS, stricttri2vec, vec2stricttri
 
 _T64 = torch.float64
 
@@ -29,7 +29,26 @@ def _tri_index(n: int, upper: bool) -> np.ndarray:
 
 
 def lu_chain(v: Dict[str, np.ndarray], vscope: str, pname: str, dA: np.ndarray) -> Dict[str, np.ndarray]:
-    """d loss / d (L_vec, U_vec, log_S) from d loss / d A for ``A = P L U`` (matrix_param.py:117-130)."""
+    """d loss / d (L_vec, U_vec, log_S) from d loss / d A for ``A = P L U`` (matrix_param.py:117-130), closed form:
+    with ``U' = U + diag(sign_S exp(log_S))``:  ``dL = strict_lower(P^T G U'^T)``, ``dU' = L^T P^T G``,
+    ``dU = strict_upper(dU')``, ``dlog_S = diag(dU') * sign_S * exp(log_S)``; the 6-vectors take the entries of the
+    matrix gradients at their own positions (``stricttri2vec`` is a permutation)."""
+    names = {k: "%s/%s_matpar_lu_%s" % (vscope, k, pname) for k in ("P", "L_vec", "U_vec", "log_S", "sign_S")}
+    p = np.asarray(v[names["P"]], np.float64)
+    n = p.shape[0]
+    s_diag = np.asarray(v[names["sign_S"]], np.float64) * np.exp(np.asarray(v[names["log_S"]], np.float64))
+    l = vec2stricttri(np.asarray(v[names["L_vec"]], np.float64), upper=False) + np.eye(n)
+    u = vec2stricttri(np.asarray(v[names["U_vec"]], np.float64), upper=True) + np.diag(s_diag)
+    ptg = p.T @ np.asarray(dA, np.float64)
+    d_l = ptg @ u.T
+    d_u = l.T @ ptg
+    return {names["L_vec"]: stricttri2vec(np.tril(d_l, -1), upper=False),
+            names["U_vec"]: stricttri2vec(np.triu(d_u, 1), upper=True),
+            names["log_S"]: np.diag(d_u) * s_diag}
+
+
+def lu_chain_autograd(v: Dict[str, np.ndarray], vscope: str, pname: str, dA: np.ndarray) -> Dict[str, np.ndarray]:
+    """Same as :func:`lu_chain` through torch autograd (cross-check used by the tests)."""
     names = {k: "%s/%s_matpar_lu_%s" % (vscope, k, pname) for k in ("P", "L_vec", "U_vec", "log_S", "sign_S")}
     p = torch.as_tensor(v[names["P"]], dtype=_T64)
     sign_s = torch.as_tensor(v[names["sign_S"]], dtype=_T64)
@@ -121,11 +140,25 @@ def scale_chain(spec, layer, dtable: np.ndarray, extra_rows) -> Dict[str, np.nda
 
 
 # ------------------------------------------------------------------------------------------------ loss + gradients
-def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_training=True):
+TIMINGS = None   # set to a dict to accumulate host wall-clock seconds per phase of a step (bench.py --mode train)
+_t_last = [0.0]
+
+
+def _tick(name):
+    if TIMINGS is not None:
+        import time
+        now = time.perf_counter()
+        if name is not None:
+            TIMINGS[name] = TIMINGS.get(name, 0.0) + now - _t_last[0]
+        _t_last[0] = now
+
+
+def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_training=True, refold=True):
     """``(loss, sd_z, grads)``: ``loss = mean_n nll_n`` (``NoiseFlow.loss``) and ``grads[tf_variable_name]`` (float64
     numpy, same shapes as the variables) for every trainable variable.  With ``is_training`` (the reference's train
     thread, ``train_noise_flow.py:64-71``) BatchNorm runs on batch statistics and the moving statistics are updated."""
     nf.build("inverse")
+    _tick(None)
     eng, spec = nf._engine, nf.spec
     lib = eng.lib
     x = nf._dev(x, "x")
@@ -147,11 +180,13 @@ def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_trainin
     bstats = np.zeros((max(len(cps), 1), 16), dtype=np.float32)
     sums = (C.c_double * 3)()
     p = lambda t: t.data_ptr() if t is not None else None
+    _tick("setup")
     with torch.cuda.device(nf.device):
         _lib.check(lib.nf_loss_and_grad(eng.handle, x.data_ptr(), p(yy), p(rows), drow, n, 1 if is_training else 0,
                                         ws.data_ptr(), dscr.data_ptr(), flat.ctypes.data_as(C.c_void_p),
                                         bstats.ctypes.data_as(C.c_void_p), sums,
                                         int(torch.cuda.current_stream(nf.device).cuda_stream)), "nf_loss_and_grad")
+    _tick("nf_loss_and_grad")
     grads: Dict[str, np.ndarray] = {}
     v = spec.store.vars
 
@@ -180,8 +215,10 @@ def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_trainin
     for name, trainable in spec.store.trainable.items():      # variables the loss does not depend on
         if trainable and name not in grads:
             grads[name] = np.zeros(v[name].shape, dtype=np.float64)
+    _tick("chain_rules")
     if is_training:
-        nf._apply_bn_moving_update(bstats)
+        nf._apply_bn_moving_update(bstats, refold=refold)    # refold=False: the caller re-folds after its optimizer step
+    _tick("bn_update_refold")
     loss = sums[0] / n
     sd_z = sums[1] / n
     return loss, sd_z, grads
@@ -217,7 +254,7 @@ def train_step(nf, optimizer: AdamOptimizer, x, y, nlf0=None, nlf1=None, iso=Non
     all-reduce (gradients are then divided by the world size: every rank's loss is the mean over ITS shard, and
     BatchNorm statistics stay per rank, which is the reference's per-``sess.run`` semantics)."""
     import torch.distributed as dist
-    loss, sd_z, grads = loss_and_grad(nf, x, y, nlf0, nlf1, iso, cam, is_training=True)
+    loss, sd_z, grads = loss_and_grad(nf, x, y, nlf0, nlf1, iso, cam, is_training=True, refold=False)
     names = sorted(grads)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         world = dist.get_world_size(group)
@@ -233,6 +270,9 @@ def train_step(nf, optimizer: AdamOptimizer, x, y, nlf0=None, nlf1=None, iso=Non
             o += sz
         loss, sd_z = flat[o] / flat[o + 2], flat[o + 1] / flat[o + 2]
     trainable = {k: g for k, g in grads.items() if nf.spec.store.trainable.get(k, False)}
+    _tick("allreduce")
     optimizer.apply_gradients(nf.spec.store.vars, trainable)
+    _tick("adam")
     nf.refresh_parameters()
+    _tick("refold")
     return loss, sd_z

@@ -217,3 +217,18 @@ def test_sharded_mean_nll_world_size_2_gloo():
     assert res[0][1:3] == (0, 501) and res[1][1:3] == (501, 1001)
     for r in res:
         assert abs(r[3] - r[5]) < 1e-12 and abs(r[4] - r[6]) < 1e-12      # every rank holds the global means
+
+
+def test_lu_chain_rule_closed_form_equals_autograd(shipped):
+    """train.lu_chain (closed form of d loss / d (L_vec, U_vec, log_S) for A = P L U, matrix_param.py:117-130)
+    against torch autograd through the same parameterisation, on the shipped LU variables."""
+    from noise_flow_b200.train import lu_chain, lu_chain_autograd
+    _, ck = shipped
+    rs = np.random.RandomState(5)
+    for i in (1, 2, 3, 4, 6, 7, 8, 9):
+        dA = rs.randn(4, 4)
+        a = lu_chain(ck, "level0/bijector%d/Conv2d_1x1_%d" % (i, i), "conv2d_1x1_%d_0" % i, dA)
+        b = lu_chain_autograd(ck, "level0/bijector%d/Conv2d_1x1_%d" % (i, i), "conv2d_1x1_%d_0" % i, dA)
+        assert set(a) == set(b)
+        for k in a:
+            assert a[k].shape == ck[k].shape and np.abs(a[k] - b[k]).max() < 1e-12
