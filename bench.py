@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tc", type=int, default=0, help="1: tensor-core (tcgen05) coupling convolutions")
+    ap.add_argument("--trainer", default="device", choices=["device", "host"],
+                    help="train mode: device-resident step (nf_trainer_*) or the host-synchronous path (train_step)")
     ap.add_argument("--arch", default=None, help="override hps.arch, e.g. \"sdn5|gain4\" (HBM-bound streaming kernel)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -213,15 +215,22 @@ def main():
             _lib.check(lib.nf_sample(eng.handle, y.data_ptr(), None, row, B, 0.6, None, 7, i, rank * B,
                                      xs.data_ptr(), stream))
 
-    train_opt = None
+    train_opt = trainer = None
+    last_loss = [None]
     if args.mode == "train":
         from noise_flow_b200 import train as nf_train
-        from noise_flow_b200.train import AdamOptimizer, train_step
-        train_opt = AdamOptimizer(learning_rate=1e-4)
+        from noise_flow_b200.train import AdamOptimizer, DeviceTrainer, train_step
+        if args.trainer == "device":
+            trainer = DeviceTrainer(nf, learning_rate=1e-4, max_batch=B)
+        else:
+            train_opt = AdamOptimizer(learning_rate=1e-4)
 
     def step(i):
         if args.mode == "train":     # BASELINE config 5: one Adam step (batch-stat BN forward + backward + update)
-            train_step(nf, train_opt, x, y, iso=[100.0], cam=[2.0])
+            if trainer is not None:  # loss and sd_z come back to the host every step, as sess.run returns them
+                last_loss[0] = trainer.step(x, y, iso=[100.0], cam=[2.0])
+            else:
+                last_loss[0] = train_step(nf, train_opt, x, y, iso=[100.0], cam=[2.0])
             return
         kernel_only(i)
         if args.mode == "log_prob":
@@ -268,6 +277,31 @@ def main():
 
     # ---- e2e: host buffers through the C-ABI host entry point (copies inside the timed region)
     e2e = None
+    if not args.no_e2e and args.mode == "train" and trainer is not None:
+        # the reference's train thread feeds numpy minibatches (sidd/MiniBatchSampler.py): pinned host batch -> device,
+        # one Adam step, loss and sd_z back on the host, every step
+        hx_t = torch.empty((B, 32, 32, 4), dtype=torch.float32, pin_memory=True)
+        hy_t = torch.empty((B, 32, 32, 4), dtype=torch.float32, pin_memory=True)
+        hx_t.copy_(x); hy_t.copy_(y)
+        e_steps = args.steps
+
+        def e2e_train_step():
+            xd, yd = hx_t.to(dev, non_blocking=True), hy_t.to(dev, non_blocking=True)
+            return trainer.step(xd, yd, iso=[100.0], cam=[2.0])
+        e2e_train_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_train_step()
+        barrier()
+        edt = time.perf_counter() - t0
+        tt = torch.tensor([edt], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        edt = float(tt[0])
+        e2e = {"value": world * B * e_steps / edt, "unit": "patches/s", "h2d_bytes_per_step": 2 * B * 16384,
+               "d2h_bytes_per_step": 24, "steps": e_steps,
+               "path": "DeviceTrainer.step on a pinned host minibatch: H2D of x and y, Adam step, loss/sd_z read back"}
     if not args.no_e2e and args.mode != "train":
         import ctypes as C
         nb = B * 4096 * 4
@@ -346,10 +380,19 @@ def main():
         n_cp = max(n_couplings, 1)
         out["roofline"] = None
         out["roofline_fp32"] = None
-        out["gpu_launches"] = world * args.steps * (n_cp * 6 + (len(hps.arch.split("|")) - n_cp) * 2 + 2)
-        out["config"]["host_ms_per_step"] = {k: round(1e3 * v / args.steps, 3) for k, v in (nf_train.TIMINGS or {}).items()}
-        out["config"]["note"] = ("one sess.run([train_op, loss, sd_z]) equivalent: batch-stat BN forward (2 probes + apply per "
-                                 "coupling), backward (3 passes per coupling), host LU/scale chain rules, Adam, re-fold")
+        out["config"]["trainer"] = args.trainer
+        out["config"]["loss_per_dim_last_step"] = None if last_loss[0] is None else float(last_loss[0][0]) / 4096
+        if trainer is not None:
+            out["gpu_launches"] = world * args.steps * trainer.launches_per_step(True)
+            out["config"]["note"] = ("one sess.run([train_op, loss, sd_z]) equivalent, device-resident: LU assembly + scale tables, "
+                                     "batch-stat BN forward (3 passes per coupling), backward (3 passes per coupling), chain rules, "
+                                     "Adam, BN moving averages -- one stream, no synchronisation except the 24-byte loss read-back"
+                                     + ("; one NCCL all-reduce of the reduce buffer" if world > 1 else ""))
+        else:
+            out["gpu_launches"] = world * args.steps * (n_cp * 6 + (len(hps.arch.split("|")) - n_cp) * 2 + 2)
+            out["config"]["host_ms_per_step"] = {k: round(1e3 * v / args.steps, 3) for k, v in (nf_train.TIMINGS or {}).items()}
+            out["config"]["note"] = ("one sess.run([train_op, loss, sd_z]) equivalent: batch-stat BN forward (2 probes + apply per "
+                                     "coupling), backward (3 passes per coupling), host LU/scale chain rules, Adam, re-fold")
     if world == 1 and not args.no_cpu_baseline and args.mode != "train":
         v, cores, sample = cpu_oracle_rate(hps, ck)
         out["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample}

@@ -166,6 +166,65 @@ int nf_loss_and_grad(const nf_model* m, const float* x, const float* y, const in
                      int64_t n, int batch_stats, float* workspace, double* dscratch, double* grads_host,
                      float* batch_stats_host, double* sums_host, void* stream);
 
+/* ---- device-resident train step: sess.run([train_op, loss, sd_z]) without host round trips ---------------- */
+/* The reference's train thread (train_noise_flow.py:50-77) runs Adam on `loss` with is_training=True
+ * (:187-198).  nf_trainer keeps every TF variable, the Adam slots and the step counter in device memory and
+ * runs the whole step there: LU assembly of the 1x1 matrices (matrix_param.py:117-130), the per-(camera, ISO)
+ * scale tables (cond_utils.py:165-276,432-440), forward with batch-statistics BatchNorm (layers.py:388-398),
+ * backward (three passes per coupling), the chain rules back to the LU / scale variables, Adam with
+ * TensorFlow's update rule and the BatchNorm moving-average update (layers.py:394-395).  No call below
+ * synchronises the stream except the _get_ functions.
+ *
+ * Variables live in ONE flat float array (order chosen by the caller); every op addresses its variables by
+ * offset (-1 = absent).  Ops are listed in data -> latent order. */
+typedef enum nf_train_op_kind { NF_TOP_COUPLING = 1, NF_TOP_SCALE = 2 } nf_train_op_kind;
+typedef enum nf_train_token {       /* scale tokens whose chain rule is implemented on the device */
+    NF_TOKEN_SDN4 = 4, NF_TOKEN_SDN5 = 5, NF_TOKEN_SDN6 = 6, NF_TOKEN_GAIN4 = 14
+} nf_train_token;
+typedef struct nf_train_op {
+    int32_t kind;                 /* nf_train_op_kind */
+    /* coupling: the 1x1 conv / permutation in front of it (noise_flow_model.py:79-104) */
+    int32_t mix_kind;             /* 0 none, 1 Conv2d1x1 with LU variables, 2 fixed channel permutation */
+    int32_t off_P, off_L, off_U, off_logS, off_signS;   /* [4][4], [6], [6], [4], [4] */
+    int32_t perm[4];              /* mix_kind 2: out channel o takes in channel perm[o] (tfb.Permute) */
+    /* coupling: real_nvp_conv_template variables in checkpoint layout, rescaling_scale0, BatchNorm moving stats */
+    int32_t off_w1, off_b1, off_w2, off_b2, off_w3, off_b3, off_logs, off_scale;
+    int32_t off_bn1_mean, off_bn1_var, off_bn2_mean, off_bn2_var;
+    /* scale layer */
+    int32_t token;                /* nf_train_token */
+    int32_t off_beta1, off_beta2, off_gain_params, off_cam_params, off_gain_val;
+    float c_i;                    /* hps.param_inits[0] (sdn5 / sdn6), cond_utils.py:207,244 */
+} nf_train_op;
+
+typedef struct nf_trainer nf_trainer;   /* opaque; owns device memory: variables, Adam slots, workspace */
+
+/* tri_lower / tri_upper: for k in 0..5 the flat position r*4+c of L_vec[k] / U_vec[k] in the strict triangle
+ * (matrix_param.py:31-57, TFP fill_triangular order).  trainable: one byte per variable element.
+ * Device memory: about 16 KiB * max_batch * (n_ops + 5). */
+int nf_trainer_create(const nf_train_op* ops, int n_ops, const float* vars_host, const uint8_t* trainable,
+                      int64_t n_vars, int64_t max_batch, const int32_t* tri_lower, const int32_t* tri_upper,
+                      float bn_eps, nf_trainer** out);
+int nf_trainer_destroy(nf_trainer* t);
+/* Length (doubles) of the reduce buffer: [d loss / d var (n_vars)] [sum nll, sum sd_z, n] [batch mean1[4],
+ * var1[4], mean2[4], var2[4] per coupling].  Everything a data-parallel step has to sum over ranks, in one buffer. */
+int nf_trainer_reduce_len(const nf_trainer* t, int64_t* n_doubles);
+/* Enqueue loss + gradient of this rank's batch; fills reduce_buf (device doubles, caller-owned).  rows: per-patch
+ * standard conditioning row (cam * 5 + iso index, 0..24) or NULL -> default_row.  batch_stats as nf_loss_and_grad. */
+int nf_trainer_loss_and_grad(nf_trainer* t, const float* x, const float* y, const int32_t* rows, int32_t default_row,
+                             int64_t n, int batch_stats, double* reduce_buf, void* stream);
+/* Enqueue Adam (tf.train.AdamOptimizer semantics: lr_t = lr*sqrt(1-b2^t)/(1-b1^t), var -= lr_t*m/(sqrt(v)+eps))
+ * on reduce_buf / world_size, and (update_bn != 0) the BatchNorm moving-average update towards the rank-averaged
+ * batch statistics.  Advances the step counter. */
+int nf_trainer_apply(nf_trainer* t, const double* reduce_buf, double lr, double beta1, double beta2, double eps,
+                     int world_size, int update_bn, void* stream);
+int nf_trainer_get_vars(nf_trainer* t, float* vars_host, void* stream);          /* synchronises */
+int nf_trainer_set_vars(nf_trainer* t, const float* vars_host, void* stream);    /* synchronises */
+int nf_trainer_launches_per_step(const nf_trainer* t, int batch_stats, int* n_launches);
+/* enable != 0 (default): nf_trainer_loss_and_grad stages x / y / rows into trainer-owned buffers and replays the
+ * launch sequence as ONE CUDA graph (re-captured when n, default_row, batch_stats or reduce_buf change) on an
+ * internal stream fenced against `stream` with events; 0: plain launches on `stream`. */
+int nf_trainer_set_graph(nf_trainer* t, int enable);
+
 /* squeeze2d / unsqueeze2d (borealisflows/utils.py:30-86): bit-exact index permutation.
  * squeeze_type: 0 = 'chessboard' (also the unknown-type fallback), 1 = 'patch'.
  * H, W, C always describe the UN-squeezed tensor [n][H][W][C]. */

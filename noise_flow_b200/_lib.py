@@ -22,6 +22,18 @@ class NfCouplingWeights(C.Structure):
                [("rescaling_scale", C.c_float), ("bn_eps", C.c_float)]
 
 
+class NfTrainOp(C.Structure):
+    """``nf_train_op`` (include/noiseflow_b200.h): one op of the device-resident train program; offsets index the
+    flat variable array, -1 = absent."""
+    _fields_ = [("kind", C.c_int32), ("mix_kind", C.c_int32)] + \
+               [(n, C.c_int32) for n in ("off_P", "off_L", "off_U", "off_logS", "off_signS")] + \
+               [("perm", C.c_int32 * 4)] + \
+               [(n, C.c_int32) for n in ("off_w1", "off_b1", "off_w2", "off_b2", "off_w3", "off_b3", "off_logs", "off_scale",
+                                         "off_bn1_mean", "off_bn1_var", "off_bn2_mean", "off_bn2_var", "token",
+                                         "off_beta1", "off_beta2", "off_gain_params", "off_cam_params", "off_gain_val")] + \
+               [("c_i", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol the header declares is listed here (tests check both ways)
 SIGNATURES = {
     "nf_abi_version": (C.c_int, []),
@@ -57,6 +69,18 @@ SIGNATURES = {
     "nf_train_workspace_floats": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "nf_loss_and_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nf_trainer_create": (C.c_int, [C.POINTER(NfTrainOp), C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_float, C.POINTER(C.c_void_p)]),
+    "nf_trainer_destroy": (C.c_int, [C.c_void_p]),
+    "nf_trainer_reduce_len": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "nf_trainer_loss_and_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int,
+                                           C.c_void_p, C.c_void_p]),
+    "nf_trainer_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                                   C.c_int, C.c_void_p]),
+    "nf_trainer_get_vars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nf_trainer_set_vars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nf_trainer_launches_per_step": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "nf_trainer_set_graph": (C.c_int, [C.c_void_p, C.c_int]),
     "nf_reduce_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nf_baseline_nll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),

@@ -290,6 +290,8 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
 
 }  // namespace
 
+int nf::set_error(int code, const char* what, const char* msg) { return fail(code, "%s: %s", what, msg); }
+
 // =====================================================================================================
 extern "C" {
 

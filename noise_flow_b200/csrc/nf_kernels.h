@@ -21,6 +21,8 @@
 #define NF_TC_SLOTS 8    // couplings whose B tiles are resident in shared memory
 
 namespace nf {
+// thread-local error string behind nf_last_error() (defined in nf_api.cu); returns `code`
+int set_error(int code, const char* what, const char* msg);
 cudaError_t launch_chain(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, int warps_per_cta,
                          cudaStream_t stream);
 cudaError_t launch_reduce(const float* nll, const float* sdz, long long n, double* sums, cudaStream_t stream);

@@ -276,3 +276,224 @@ def train_step(nf, optimizer: AdamOptimizer, x, y, nlf0=None, nlf1=None, iso=Non
     nf.refresh_parameters()
     _tick("refold")
     return loss, sd_z
+
+
+# ------------------------------------------------------------------------------------------------ device-resident step
+_DEVICE_TOKENS = {"sdn4": 4, "sdn5": 5, "sdn6": 6, "gain4": 14}          # nf_train_token
+
+
+def tri_positions(upper: bool):
+    """Flat position ``r*4+c`` of ``L_vec[k]`` / ``U_vec[k]`` in the strict triangle (matrix_param.py:31-57)."""
+    pos = vec2stricttri(np.arange(1, 7, dtype=np.float64), upper).astype(np.int64)
+    out = [0] * 6
+    for r in range(4):
+        for c in range(4):
+            if pos[r, c] > 0:
+                out[pos[r, c] - 1] = r * 4 + c
+    return out
+
+
+def build_train_program(spec):
+    """``(names, offsets, n_vars, trainable_mask, ops)`` for ``nf_trainer_create``: the flat variable layout (every
+    variable of the store, in store order) and one ``nf_train_op`` per kernel op in data -> latent order.  Host-only
+    (no GPU needed).  Raises ``NotImplementedError`` for what the device-side chain rules do not cover."""
+    store = spec.store
+    names = list(store.vars.keys())
+    o, off = {}, 0
+    for k in names:
+        o[k] = off
+        off += int(store.vars[k].size)
+    n_vars = off
+    mask = np.zeros(n_vars, dtype=np.uint8)
+    for k in names:
+        if store.trainable.get(k, False):
+            mask[o[k]:o[k] + store.vars[k].size] = 1
+    ops, layers, i = [], spec.layers, 0
+    while i < len(layers):
+        l = layers[i]
+        op = _lib.NfTrainOp()
+        for f, _ in _lib.NfTrainOp._fields_:
+            if f.startswith("off_"):
+                setattr(op, f, -1)
+        if l.kind in ("conv1x1", "permute"):
+            if i + 1 >= len(layers) or layers[i + 1].kind != "coupling":
+                raise NotImplementedError("stand-alone 1x1 conv / permutation (not followed by a coupling)")
+            if l.kind == "conv1x1":
+                op.mix_kind = 1
+                s, p = l.data["vscope"], l.data["pname"]
+                for f, k in (("off_P", "P"), ("off_L", "L_vec"), ("off_U", "U_vec"), ("off_logS", "log_S"), ("off_signS", "sign_S")):
+                    setattr(op, f, o["%s/%s_matpar_lu_%s" % (s, k, p)])
+            else:
+                op.mix_kind = 2
+                # nf_model_add_permute: forward y[i] = x[perm[i]], so data -> latent sends channel i to perm[i]
+                op.perm = (C.c_int32 * 4)(*l.data["perm"])
+            i += 1
+            l = layers[i]
+        if l.kind == "coupling":
+            if spec.width != 4:
+                raise NotImplementedError("train kernels are built for width 4")
+            op.kind = 1
+            t = l.data["template"]
+            for f, k in (("off_w1", "/l_1/W"), ("off_b1", "/l_1/b"), ("off_w2", "/l_2/W"), ("off_b2", "/l_2/b"),
+                         ("off_w3", "/l_last/W"), ("off_b3", "/l_last/b"), ("off_logs", "/l_last/logs"),
+                         ("off_bn1_mean", "/bn_nvp_conv_1/mean"), ("off_bn1_var", "/bn_nvp_conv_1/var"),
+                         ("off_bn2_mean", "/bn_nvp_conv_2/mean"), ("off_bn2_var", "/bn_nvp_conv_2/var")):
+                setattr(op, f, o[t + k])
+            op.off_scale = o[l.scope + "/rescaling_scale0"]
+        elif l.kind == "scale":
+            if l.token not in _DEVICE_TOKENS:
+                raise NotImplementedError("scale token %r has no device-side chain rule (use train_step)" % l.token)
+            op.kind = 2
+            op.token = _DEVICE_TOKENS[l.token]
+            s = "model/sdn_gain"
+            if l.token == "gain4":
+                op.off_gain_val = o[s + "/gain_val"]
+            else:
+                op.off_beta1, op.off_beta2, op.off_gain_params = o[s + "/beta1"], o[s + "/beta2"], o[s + "/gain_params"]
+                if l.token in ("sdn5", "sdn6"):
+                    op.off_cam_params = o[s + "/cam_params"]
+                    op.c_i = float(spec.hps.param_inits[0])
+                if l.token == "sdn6" and tuple(spec.store.vars[s + "/cam_params"].shape) != (1, 5):
+                    raise NotImplementedError("sdn6 next to sdn5 (shared cam_params of another shape)")
+        else:
+            raise NotImplementedError(l.kind)
+        ops.append(op)
+        i += 1
+    return names, o, n_vars, mask, ops
+
+
+class DeviceTrainer:
+    """The same train step with NOTHING on the host: every TF variable, the Adam slots and the step counter live in
+    device memory inside an ``nf_trainer`` (include/noiseflow_b200.h); LU assembly, scale tables, batch-statistics
+    BatchNorm, backward, chain rules, Adam and the BatchNorm moving averages are kernels on one stream, with no
+    stream synchronisation inside a step.  ``step`` is one ``sess.run([train_op, loss, sd_z])``
+    (train_noise_flow.py:64-71); data parallel = ONE all-reduce of the trainer's reduce buffer (gradients,
+    ``[sum nll, sum sd_z, n]`` and the batch statistics that drive the moving averages).
+
+    Supported: arch strings made of ``unc`` (with ``flow_permutation`` 0 or 1) and the ``sdn4 / sdn5 / sdn6 / gain4``
+    scale layers, standard (camera, ISO) rows -- i.e. every configuration in the reference's ``job_noise_flow.sh``.
+    Anything else raises ``NotImplementedError``; :func:`train_step` (host-side chain rules) covers those.
+
+    ``sync_to_model()`` copies the trained variables back into ``nf.variables`` and re-folds the inference engine.
+    """
+
+    def __init__(self, nf, learning_rate=1e-4, beta1=0.9, beta2=0.999, epsilon=1e-8, max_batch=256, group=None,
+                 cuda_graph=True):
+        from .params import BN_EPS
+        nf.build("inverse")
+        self.nf, self.group = nf, group
+        self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(beta1), float(beta2), float(epsilon)
+        spec = nf.spec
+        self.lib = _lib.load()
+        self.names, self.offsets, self.n_vars, mask, self.ops = build_train_program(spec)
+        arr = (_lib.NfTrainOp * len(self.ops))(*self.ops)
+        tri_lo = (C.c_int32 * 6)(*tri_positions(False))
+        tri_up = (C.c_int32 * 6)(*tri_positions(True))
+        flat = self._flatten()
+        self.handle = C.c_void_p()
+        self.max_batch = int(max_batch)
+        with torch.cuda.device(nf.device):
+            _lib.check(self.lib.nf_trainer_create(arr, len(self.ops), flat.ctypes.data_as(C.c_void_p),
+                                                  mask.ctypes.data_as(C.c_void_p), self.n_vars, self.max_batch, tri_lo, tri_up,
+                                                  BN_EPS, C.byref(self.handle)), "nf_trainer_create")
+        n = C.c_int64()
+        _lib.check(self.lib.nf_trainer_reduce_len(self.handle, C.byref(n)), "nf_trainer_reduce_len")
+        self.red = torch.zeros(n.value, device=nf.device, dtype=torch.float64)
+        self.steps = 0
+        _lib.check(self.lib.nf_trainer_set_graph(self.handle, 1 if cuda_graph else 0), "nf_trainer_set_graph")
+
+    def _flatten(self):
+        v = self.nf.spec.store.vars
+        return np.concatenate([np.asarray(v[k], dtype=np.float32).reshape(-1) for k in self.names]) if self.names else np.zeros(0, np.float32)
+
+    # ---- one step
+    def _stream(self):
+        return int(torch.cuda.current_stream(self.nf.device).cuda_stream)
+
+    def loss_and_grad(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_training=True):
+        """Enqueue loss + gradients of this rank's batch into ``self.red`` (no synchronisation)."""
+        nf = self.nf
+        x = nf._dev(x, "x")
+        cond = getattr(nf.hps, "sidd_cond", "mix")
+        yy = nf._dev(y, "y") if (cond is not None and cond != "uncond") else None
+        n = x.shape[0]
+        if n < 1 or n > self.max_batch:
+            raise ValueError("batch size %d outside 1..max_batch=%d" % (n, self.max_batch))
+        rows, drow = nf._rows(n, nlf0, nlf1, iso, cam)
+        if drow >= 25 or (rows is not None and int(rows.max()) >= 25):
+            raise NotImplementedError("non-standard (camera, ISO) conditioning row (use train_step)")
+        self._keep = (x, yy, rows)       # keep the inputs alive until the stream has consumed them
+        with torch.cuda.device(nf.device):
+            _lib.check(self.lib.nf_trainer_loss_and_grad(self.handle, x.data_ptr(), yy.data_ptr() if yy is not None else None,
+                                                         rows.data_ptr() if rows is not None else None, drow, n,
+                                                         1 if is_training else 0, self.red.data_ptr(), self._stream()),
+                       "nf_trainer_loss_and_grad")
+        return n
+
+    def step(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, sync=True):
+        """One Adam step.  Returns ``(loss, sd_z)`` as Python floats (``sync=True``: one 24-byte read-back, the
+        only synchronisation) or as a device tensor ``[sum nll, sum sd_z, n]`` (``sync=False``)."""
+        import torch.distributed as dist
+        self.loss_and_grad(x, y, nlf0, nlf1, iso, cam, is_training=True)
+        world = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            world = dist.get_world_size(self.group)
+            dist.all_reduce(self.red, op=dist.ReduceOp.SUM, group=self.group)
+        with torch.cuda.device(self.nf.device):
+            _lib.check(self.lib.nf_trainer_apply(self.handle, self.red.data_ptr(), self.lr, self.b1, self.b2, self.eps, world, 1,
+                                                 self._stream()), "nf_trainer_apply")
+        self.steps += 1
+        sums = self.red[self.n_vars:self.n_vars + 3]
+        if not sync:
+            return sums.clone()
+        s = sums.cpu().numpy()
+        return float(s[0] / s[2]), float(s[1] / s[2])
+
+    def gradients(self) -> Dict[str, np.ndarray]:
+        """Gradients of the last ``loss_and_grad`` by TF variable name (synchronises; tests and debugging)."""
+        flat = self.red[:self.n_vars].cpu().numpy()
+        v = self.nf.spec.store.vars
+        return {k: flat[self.offsets[k]:self.offsets[k] + v[k].size].reshape(v[k].shape).copy() for k in self.names
+                if self.nf.spec.store.trainable.get(k, False)}
+
+    def loss(self):
+        s = self.red[self.n_vars:self.n_vars + 3].cpu().numpy()
+        return float(s[0] / s[2]), float(s[1] / s[2])
+
+    def batch_stats(self) -> np.ndarray:
+        return self.red[self.n_vars + 3:].cpu().numpy().reshape(-1, 16)
+
+    def launches_per_step(self, is_training=True) -> int:
+        n = C.c_int()
+        _lib.check(self.lib.nf_trainer_launches_per_step(self.handle, 1 if is_training else 0, C.byref(n)), "launches")
+        return n.value
+
+    # ---- variables
+    def variables(self) -> Dict[str, np.ndarray]:
+        flat = np.empty(self.n_vars, dtype=np.float32)
+        with torch.cuda.device(self.nf.device):
+            _lib.check(self.lib.nf_trainer_get_vars(self.handle, flat.ctypes.data_as(C.c_void_p), self._stream()), "nf_trainer_get_vars")
+        v = self.nf.spec.store.vars
+        return {k: flat[self.offsets[k]:self.offsets[k] + v[k].size].reshape(v[k].shape).copy() for k in self.names}
+
+    def sync_to_model(self):
+        """Device variables -> ``nf.variables`` (in place) and re-fold the inference engine."""
+        new = self.variables()
+        v = self.nf.spec.store.vars
+        with self.nf._lock:
+            for k in self.names:
+                v[k][...] = new[k]
+        self.nf.refresh_parameters()
+
+    def sync_from_model(self):
+        flat = self._flatten()
+        with torch.cuda.device(self.nf.device):
+            _lib.check(self.lib.nf_trainer_set_vars(self.handle, flat.ctypes.data_as(C.c_void_p), self._stream()), "nf_trainer_set_vars")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.nf_trainer_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass

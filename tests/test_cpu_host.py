@@ -232,3 +232,46 @@ def test_lu_chain_rule_closed_form_equals_autograd(shipped):
         assert set(a) == set(b)
         for k in a:
             assert a[k].shape == ck[k].shape and np.abs(a[k] - b[k]).max() < 1e-12
+
+
+def test_device_train_program_layout(shipped):
+    """Host half of the device-resident train step: flat variable layout and the op list of ``nf_trainer_create``."""
+    from noise_flow_b200 import make_hps
+    from noise_flow_b200.params import ModelSpec
+    from noise_flow_b200.train import build_train_program, tri_positions
+    hps, ck = shipped
+    spec = ModelSpec(hps, ck)
+    spec.assign_template_scopes("inverse")
+    spec.create_scale_variables()
+    names, off, n_vars, mask, ops = build_train_program(spec)
+    assert n_vars == 2721 and int(mask.sum()) == 2433                       # checkpoint floats / hps.txt num_params
+    assert [op.kind for op in ops] == [2, 1, 1, 1, 1, 2, 1, 1, 1, 1]        # sdn5 | 4 x (1x1 + unc) | gain4 | 4 x ...
+    assert [op.token for op in ops if op.kind == 2] == [5, 14]
+    assert all(op.mix_kind == 1 for op in ops if op.kind == 1)
+    cp = ops[1]
+    assert off["model/real_nvp_conv_template/l_1/W"] == cp.off_w1 and off["level0/bijector1/rescaling_scale0"] == cp.off_scale
+    assert not mask[cp.off_bn1_mean] and not mask[cp.off_P] and mask[cp.off_L] and mask[cp.off_logS]
+    # every offset range is disjoint from every other (no variable is addressed twice by accident)
+    seen = np.zeros(n_vars, dtype=np.int32)
+    for op in ops:
+        if op.kind == 1:
+            for f, sz in (("off_w1", 72), ("off_b1", 4), ("off_w2", 16), ("off_b2", 4), ("off_w3", 180), ("off_b3", 4),
+                          ("off_logs", 4), ("off_scale", 1), ("off_bn1_mean", 4), ("off_bn1_var", 4), ("off_bn2_mean", 4),
+                          ("off_bn2_var", 4), ("off_P", 16), ("off_L", 6), ("off_U", 6), ("off_logS", 4), ("off_signS", 4)):
+                o = getattr(op, f)
+                assert o >= 0
+                seen[o:o + sz] += 1
+    assert seen.max() == 1
+    # triangle positions = where stricttri2vec reads: SURVEY 8(a7) ordering
+    assert tri_positions(False) == [14, 13, 12, 4, 9, 8] and tri_positions(True) == [1, 2, 3, 11, 6, 7]
+    # unsupported scale tokens are refused, not silently mis-trained
+    spec2 = ModelSpec(make_hps(arch="sdn2|unc|gain2"), None)
+    spec2.assign_template_scopes("inverse")
+    spec2.create_scale_variables()
+    with pytest.raises(NotImplementedError):
+        build_train_program(spec2)
+    spec3 = ModelSpec(make_hps(arch="sdn4|unc|gain4", flow_permutation=0), None)
+    spec3.assign_template_scopes("inverse")
+    spec3.create_scale_variables()
+    ops3 = build_train_program(spec3)[4]
+    assert [op.kind for op in ops3] == [2, 1, 2] and ops3[1].mix_kind == 2 and list(ops3[1].perm) == [3, 2, 1, 0]

@@ -1,0 +1,162 @@
+"""Device-resident train step (``nf_trainer_*`` / ``train.DeviceTrainer``): gradients against torch autograd through
+the CPU oracle and against the host-synchronous path, Adam / BatchNorm moving averages against ``train_step``."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from common import synth_batch
+from test_gpu_train import _check, _oracle_loss_and_grads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("is_training", [False, True])
+def test_device_gradients_match_oracle_autograd(shipped, is_training):
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import DeviceTrainer, loss_and_grad
+    hps, ck = shipped
+    x, y = synth_batch(6, cam=2, iso=100, seed=91)
+    nf = NoiseFlow([32, 32, 4], is_training, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    tr = DeviceTrainer(nf, max_batch=8)
+    tr.loss_and_grad(x, y, iso=[100.0], cam=[2.0], is_training=is_training)
+    loss, sd_z = tr.loss()
+    grads = tr.gradients()
+    loss_o, sd_o, grads_o, _ = _oracle_loss_and_grads(hps, ck, x, y, 100.0, 2.0, is_training)
+    assert abs(loss - loss_o) / 4096 < 1e-4 and abs(sd_z - sd_o) < 1e-4
+    assert sum(g.size for g in grads.values()) == 2433
+    worst = _check(grads, grads_o, rel=5e-3)
+    print("device trainer vs oracle: max relative gradient error %.2e" % worst)
+    # and against the independently written host-synchronous path (same math, other kernels)
+    nf2 = NoiseFlow([32, 32, 4], is_training, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    loss_h, sd_h, grads_h = loss_and_grad(nf2, x, y, iso=[100.0], cam=[2.0], is_training=is_training)
+    assert abs(loss - loss_h) / 4096 < 2e-6 and abs(sd_z - sd_h) < 1e-5
+    _check(grads, grads_h, rel=2e-3)
+    if is_training:     # batch statistics that drive the moving averages
+        assert np.allclose(tr.batch_stats(), nf2.last_batch_stats, rtol=2e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("arch,perm,cam,iso", [("sdn4|unc|gain4|unc", 0, 1.0, 800.0), ("sdn6|unc|unc|gain4", 1, 3.0, 1600.0)])
+def test_device_gradients_other_archs(arch, perm, cam, iso):
+    """Fresh perturbed models: channel permutation instead of the LU 1x1 conv, sdn4 / sdn6, other (cam, ISO)."""
+    from noise_flow_b200 import NoiseFlow, make_hps
+    from noise_flow_b200.train import DeviceTrainer
+    hps = make_hps(arch=arch, flow_permutation=perm)
+    nf0 = NoiseFlow([32, 32, 4], False, copy.copy(hps), device="cuda:0", seed=3, first_call="inverse")
+    rng = np.random.RandomState(7)
+    vs = {k: v.copy() for k, v in nf0.variables.items()}
+    for k in vs:
+        if k.endswith("/l_1/W") or k.endswith("/l_2/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.5).astype(np.float32)
+        elif k.endswith("/l_last/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.1).astype(np.float32)
+        elif k.endswith("/b") or k.endswith("/logs"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.2).astype(np.float32)
+        elif "rescaling_scale" in k:
+            vs[k] = np.float32(0.5)
+        elif "cam_params" in k or "gain_params" in k:
+            vs[k] = (vs[k] + rng.randn(*vs[k].shape) * 0.05).astype(np.float32)
+    x, y = synth_batch(5, cam=2, iso=800, seed=93)
+    x = (x * 3).astype(np.float32)
+    nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+    tr = DeviceTrainer(nf, max_batch=8)
+    tr.loss_and_grad(x, y, iso=[iso], cam=[cam], is_training=True)
+    loss, _ = tr.loss()
+    loss_o, _, grads_o, _ = _oracle_loss_and_grads(hps, vs, x, y, iso, cam, True)
+    assert abs(loss - loss_o) / 4096 < 1e-4
+    _check(tr.gradients(), grads_o, rel=5e-3)
+
+
+def test_device_gradients_per_patch_rows(shipped):
+    """Per-patch (camera, ISO): the table-row gradients of several rows chain into the shared sdn5 variables."""
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import DeviceTrainer, loss_and_grad
+    hps, ck = shipped
+    x, y = synth_batch(6, cam=2, iso=100, seed=97)
+    cams = [2.0, 2.0, 0.0, 4.0, 1.0, 2.0]
+    isos = [100.0, 800.0, 400.0, 100.0, 3200.0, 1600.0]
+    nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    tr = DeviceTrainer(nf, max_batch=8)
+    tr.loss_and_grad(x, y, iso=isos, cam=cams, is_training=True)
+    nf2 = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    loss_h, _, grads_h = loss_and_grad(nf2, x, y, iso=isos, cam=cams, is_training=True)
+    assert abs(tr.loss()[0] - loss_h) / 4096 < 2e-6
+    grads = tr.gradients()
+    # biases in front of a batch-statistics BatchNorm have an exactly-zero gradient; what both paths return there is
+    # fp32 summation noise of their own (|g| ~ 1e-3 next to gradients of 1..1000), so compare those absolutely
+    zero_g = [k for k in grads_h if k.endswith("/l_1/b") or k.endswith("/l_2/b")]
+    for k in zero_g:
+        assert np.abs(grads[k]).max() < 2e-2 and np.abs(grads_h[k]).max() < 2e-2, k
+    _check({k: g for k, g in grads.items() if k not in zero_g}, {k: g for k, g in grads_h.items() if k not in zero_g}, rel=2e-3)
+
+
+@pytest.mark.parametrize("cuda_graph", [True, False])
+def test_device_graph_replay_equals_plain_launches(shipped, cuda_graph):
+    """The CUDA-graph replay (staged inputs, re-capture on a new batch size) gives the plain-launch results."""
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import DeviceTrainer
+    hps, ck = shipped
+    nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    tr = DeviceTrainer(nf, max_batch=8, cuda_graph=cuda_graph)
+    ref = DeviceTrainer(nf, max_batch=8, cuda_graph=False)
+    for n, seed in ((6, 1), (6, 2), (4, 3), (6, 4)):          # same size replays, new size re-captures
+        x, y = synth_batch(n, seed=400 + seed)
+        tr.loss_and_grad(x, y, iso=[100.0], cam=[2.0])
+        ref.loss_and_grad(x, y, iso=[100.0], cam=[2.0])
+        a, b = tr.red.cpu().numpy(), ref.red.cpu().numpy()
+        # fp32 shared-memory / fp64 global atomics accumulate in launch-dependent order: equal up to summation noise
+        assert np.allclose(a, b, rtol=1e-4, atol=2e-5 * np.abs(b).max()), (n, seed, np.abs(a - b).max())
+        assert abs(tr.loss()[0] - ref.loss()[0]) < 1e-3
+
+
+def test_device_adam_steps_match_host_train_step(shipped):
+    """Three Adam steps on the device == three ``train_step`` calls (host chain rules, numpy Adam): variables,
+    BatchNorm moving statistics and losses."""
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import AdamOptimizer, DeviceTrainer, train_step
+    hps, ck = shipped
+    nf_d = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    nf_h = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    tr = DeviceTrainer(nf_d, learning_rate=1e-4, max_batch=8)
+    opt = AdamOptimizer(learning_rate=1e-4)
+    for s in range(3):
+        x, y = synth_batch(8, seed=200 + s)
+        ld, sd = tr.step(x, y, iso=[100.0], cam=[2.0])
+        lh, sh = train_step(nf_h, opt, x, y, iso=[100.0], cam=[2.0])
+        assert abs(ld - lh) / 4096 < 5e-6, (s, ld, lh)
+        assert abs(sd - sh) < 1e-4
+    got = tr.variables()
+    lr = 1e-4
+    for k, vh in nf_h.variables.items():
+        d = np.abs(got[k].astype(np.float64) - vh.astype(np.float64)).max()
+        if "bn_nvp_conv" in k:
+            assert d < 1e-5 * max(1.0, np.abs(vh).max()), (k, d)
+        else:
+            # Adam's normalised step is +-lr wherever a gradient is ~0 up to fp32 noise (biases in front of a
+            # batch-statistics BatchNorm), so two correct implementations may differ there by a few lr
+            assert d < 3.5 * 3 * lr, (k, d)
+    close = [np.abs(got[k].astype(np.float64) - nf_h.variables[k]).max() < 2e-6 for k in got
+             if k.endswith("/W") or "matpar" in k or "sdn_gain" in k]
+    assert np.mean(close) > 0.9
+    # sync_to_model: the inference engine now evaluates the trained variables
+    tr.sync_to_model()
+    x, y = synth_batch(4, seed=300)
+    nll_d, _ = nf_d._loss(x, y, iso=[100.0], cam=[2.0], is_training=False)
+    nll_h, _ = nf_h._loss(x, y, iso=[100.0], cam=[2.0], is_training=False)
+    assert float((nll_d - nll_h).abs().max()) / 4096 < 1e-4
+
+
+def test_device_trainer_rejects_unsupported():
+    from noise_flow_b200 import NoiseFlow, make_hps
+    from noise_flow_b200.train import DeviceTrainer
+    nf = NoiseFlow([32, 32, 4], True, make_hps(arch="sdn2|unc|gain2"), device="cuda:0", first_call="inverse")
+    with pytest.raises(NotImplementedError):
+        DeviceTrainer(nf)
+    nf = NoiseFlow([32, 32, 4], True, make_hps(arch="sdn5|unc|gain4"), device="cuda:0", first_call="inverse")
+    tr = DeviceTrainer(nf, max_batch=4)
+    x, y = synth_batch(5)
+    with pytest.raises(ValueError):
+        tr.step(x, y, iso=[100.0], cam=[2.0])
+    with pytest.raises(NotImplementedError):
+        tr.step(x[:2], y[:2], iso=[250.0], cam=[2.0])
