@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--tc", type=int, default=0, help="1: tensor-core (tcgen05) coupling convolutions")
     ap.add_argument("--trainer", default="device", choices=["device", "host"],
                     help="train mode: device-resident step (nf_trainer_*) or the host-synchronous path (train_step)")
+    ap.add_argument("--width", type=int, default=4,
+                    help="coupling-net width (reference --width): 4 = shipped weights; 8 / 16 / 32 = CTA-per-patch kernel on a "
+                         "randomly initialised net of the shipped arch")
     ap.add_argument("--arch", default=None, help="override hps.arch, e.g. \"sdn5|gain4\" (HBM-bound streaming kernel)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -188,6 +191,21 @@ def main():
     hps, ck = load_model_files()
     if args.arch:
         hps.arch = args.arch
+    if args.width != 4:     # no shipped checkpoint at other widths: reference initialisers, then non-trivial net weights
+        import numpy as _np
+        hps.width = args.width
+        nf0 = NoiseFlow([32, 32, 4], False, hps, variables={k: v for k, v in ck.items() if "real_nvp_conv_template" not in k},
+                        first_call="inverse", device=dev, seed=0)
+        rng = _np.random.RandomState(0)
+        ck = {k: v.copy() for k, v in nf0.variables.items()}
+        for k in ck:
+            if k.endswith("/l_1/W"):
+                ck[k] = (rng.randn(*ck[k].shape) * 0.5).astype(_np.float32)
+            elif k.endswith("/l_2/W"):
+                ck[k] = (rng.randn(*ck[k].shape) / _np.sqrt(args.width)).astype(_np.float32)
+            elif k.endswith("/l_last/W"):
+                ck[k] = (rng.randn(*ck[k].shape) * 0.05 / _np.sqrt(args.width)).astype(_np.float32)
+        del nf0
     nf = NoiseFlow([32, 32, 4], False, hps, variables=ck, first_call="inverse", device=dev)
     if args.warps:
         nf.set_launch(args.warps, 0)
@@ -354,6 +372,9 @@ def main():
             traffic = None
     n_couplings = hps.arch.split("|").count("unc")
     conv_flop = CONV_FLOP_PER_PATCH * n_couplings / 8.0
+    if args.width != 4:     # 18 W + W^2 + 36 W + 16 MAC per pixel and coupling
+        wd = args.width
+        conv_flop = 2.0 * 1024 * n_couplings * (18 * wd + wd * wd + 36 * wd + 16)
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     out = {"metric": {"log_prob": "patches_per_sec_nll", "sample": "patches_per_sec_sample",
@@ -364,10 +385,11 @@ def main():
            "config": {"workload": "%s Noise Flow (shipped weights, arch %s), batch %d 32x32x4 patches per GPU, "
                                   "cam S6 / ISO 100" % (args.mode, hps.arch, B),
                       "per_gpu_batch": B, "global_batch": world * B, "parallelism": "dp%d" % world,
+                      "width": args.width,
                       "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (2 * B * 16384 / 2 ** 30),
                       "mean_nll_per_dim": mean_nll},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else "nf_chain_kernel",
+                        "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else ("nf_chain_kernel" if args.width == 4 else "nf_wide_chain_kernel"),
                         "kernel_ms": kms, "alg_bytes_per_patch": alg,
                         "note": ("binding roof is the FP32 FMA pipe (see roofline_fp32), not HBM" if n_couplings else
                                  "scale-layer-only chain: streaming kernel, HBM-bound")},

@@ -24,6 +24,7 @@ UNITS = [
     ("nf_kernels.cu", ["-use_fast_math"]),
     ("nf_stream.cu", ["-use_fast_math"]),
     ("nf_tc.cu", ["-use_fast_math"]),
+    ("nf_wide.cu", ["-use_fast_math"]),
     ("nf_train.cu", []),
     ("nf_trainer.cu", []),
     ("nf_api.cu", []),

@@ -17,6 +17,7 @@
 #include "nf_kernels.h"
 #include "nf_params.h"
 #include "nf_train.h"
+#include "nf_wide.h"
 
 namespace {
 
@@ -50,9 +51,22 @@ struct Layer {
         float l1_w[72], l1_b[4], bn1_mean[4], bn1_var[4], l2_w[16], l2_b[4], bn2_mean[4], bn2_var[4];
         float last_w[180], last_b[4], last_logs[4], rescaling_scale, bn_eps;
     } raw = {};
+    // coupling of a wide net (width != 4): reference-shaped copy, [l1_w 18W][l1_b W][bn1_mean W][bn1_var W][l2_w W*W]
+    // [l2_b W][bn2_mean W][bn2_var W][last_w 36(W+1)][last_b 4][last_logs 4]; rescaling_scale / bn_eps in `raw`
+    std::vector<float> wraw;
     // scale
     int scale_kind = 0, full_sum = 1, n_rows = 0;
     float table[NF_MAX_ROWS][4] = {};
+};
+
+struct WideRawView {   // sub-arrays of Layer::wraw
+    const float *l1_w, *l1_b, *bn1_mean, *bn1_var, *l2_w, *l2_b, *bn2_mean, *bn2_var, *last_w, *last_b, *last_logs;
+    WideRawView(const float* p, int W) {
+        l1_w = p; p += 18 * W; l1_b = p; p += W; bn1_mean = p; p += W; bn1_var = p; p += W;
+        l2_w = p; p += W * W; l2_b = p; p += W; bn2_mean = p; p += W; bn2_var = p; p += W;
+        last_w = p; p += 36 * (W + 1); last_b = p; p += 4; last_logs = p;
+    }
+    static size_t floats(int W) { return (size_t)18 * W + 3 * W + (size_t)W * W + 3 * W + 36 * (size_t)(W + 1) + 8; }
 };
 
 }  // namespace
@@ -76,6 +90,12 @@ struct nf_model {
     } st[2];
     double* d_sums = nullptr;
     int64_t chunk = 0;
+    // wide coupling nets (width 8 / 16 / 32, nf_wide.cu): the folded program of the whole chain lives in a device
+    // blob owned by the handle (re-uploaded by nf_model_finalize / nf_model_set_*)
+    int width = 4;
+    NfWideProgram wide_full = {};
+    float* d_wide_full = nullptr;
+    size_t wide_full_floats = 0;
 };
 
 namespace {
@@ -236,6 +256,93 @@ bool range_has_sdn(const nf_model* m, int first, int last) {
     return false;
 }
 
+// ---- wide nets: fold one coupling into its blob block (NfWideLayout), double precision --------------------------
+// bn: explicit BatchNorm statistics [mean1 W][var1 W][mean2 W][var2 W] or null -> the stored moving statistics
+int fold_wide(const Layer& L, int W, const float* bn, const Layer* mixl, float* out) {
+    const WideRawView r(L.wraw.data(), W);
+    const float *m1 = bn ? bn : r.bn1_mean, *v1 = bn ? bn + W : r.bn1_var, *m2 = bn ? bn + 2 * W : r.bn2_mean,
+                *v2 = bn ? bn + 3 * W : r.bn2_var;
+    const double eps = L.raw.bn_eps;
+    const int oA = 0, oAINV = 16, oMETA = 32, oB3 = 36, oB1 = 72, oB2 = oB1 + W, oW1 = oB2 + W, oW2 = oW1 + 18 * W, oW3 = oW2 + W * W;
+    std::vector<double> s1(W), s2(W);
+    for (int o = 0; o < W; ++o) {
+        if (!((double)v1[o] + eps > 0.0) || !((double)v2[o] + eps > 0.0)) return fail(NF_ERR_INVALID, "batch-norm variance + eps must be positive");
+        s1[o] = 1.0 / sqrt((double)v1[o] + eps);
+        s2[o] = 1.0 / sqrt((double)v2[o] + eps);
+    }
+    double e[4];
+    for (int o = 0; o < 4; ++o) e[o] = exp(3.0 * (double)r.last_logs[o]);
+    for (int o = 0; o < 4; ++o)
+        for (int i = 0; i < 4; ++i) {
+            out[oA + o * 4 + i] = mixl ? mixl->a[o][i] : (o == i ? 1.f : 0.f);
+            out[oAINV + o * 4 + i] = mixl ? mixl->ainv[o][i] : (o == i ? 1.f : 0.f);
+        }
+    out[oMETA] = mixl ? 1.f : 0.f;
+    out[oMETA + 1] = L.raw.rescaling_scale;
+    out[oMETA + 2] = out[oMETA + 3] = 0.f;
+    for (int t = 0; t < 9; ++t)
+        for (int o = 0; o < W; ++o)
+            for (int i = 0; i < 2; ++i) out[oW1 + (t * W + o) * 2 + i] = (float)((double)r.l1_w[(t * 2 + i) * W + o] * s1[o]);
+    for (int o = 0; o < W; ++o) {
+        out[oB1 + o] = (float)(((double)r.l1_b[o] - (double)m1[o]) * s1[o]);
+        out[oB2 + o] = (float)(((double)r.l2_b[o] - (double)m2[o]) * s2[o]);
+        for (int i = 0; i < W; ++i) out[oW2 + o * W + i] = (float)((double)r.l2_w[i * W + o] * s2[o]);
+    }
+    for (int t = 0; t < 9; ++t)
+        for (int i = 0; i < W; ++i)
+            for (int o = 0; o < 4; ++o) out[oW3 + (t * W + i) * 4 + o] = (float)((double)r.last_w[(t * (W + 1) + i) * 4 + o] * e[o]);
+    for (int rc = 0; rc < 3; ++rc)        // edge indicator -> bias table by (row class, column class), as fold_coupling
+        for (int cc = 0; cc < 3; ++cc)
+            for (int o = 0; o < 4; ++o) {
+                double acc = r.last_b[o];
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const bool ring = (rc == 0 && dy == 0) || (rc == 2 && dy == 2) || (cc == 0 && dx == 0) || (cc == 2 && dx == 2);
+                        if (ring) acc += (double)r.last_w[((dy * 3 + dx) * (W + 1) + W) * 4 + o];
+                    }
+                out[oB3 + (rc * 3 + cc) * 4 + o] = (float)(acc * e[o]);
+            }
+    return NF_OK;
+}
+
+// kernel program + parameter blob of the bijectors [first, last) of a wide model (same fusion rule as build_program)
+int build_wide_program(const nf_model* m, int first, int last, NfWideProgram* wp, std::vector<float>* blob, float* ldj_const,
+                       int bn_layer = -1, const float* bn_stats = nullptr) {
+    const int W = m->width;
+    memset(wp, 0, sizeof(*wp));
+    wp->width = W;
+    blob->clear();
+    double ldj = 0.0;
+    int n_ops = 0;
+    for (int l = first; l < last; ++l) {
+        const Layer& L = m->layers[l];
+        if (n_ops >= NF_MAX_LAYERS) return fail(NF_ERR_UNSUPPORTED, "more than %d kernel ops", NF_MAX_LAYERS);
+        const size_t off = blob->size();
+        if (L.kind == L_CONV1X1 || L.kind == L_PERMUTE) {
+            ldj += L.log_abs_det * (double)NF_PIXELS;
+            if ((l + 1 < last) && m->layers[l + 1].kind == L_COUPLING) continue;
+            blob->resize(off + NF_WIDE_MIX_FLOATS);
+            memcpy(blob->data() + off, L.a, sizeof(L.a));
+            memcpy(blob->data() + off + 16, L.ainv, sizeof(L.ainv));
+            wp->op[n_ops] = NF_KOP_MIX;
+        } else if (L.kind == L_COUPLING) {
+            blob->resize(off + (size_t)nf_wide_coupling_floats(W));
+            const bool fused = l > first && (m->layers[l - 1].kind == L_CONV1X1 || m->layers[l - 1].kind == L_PERMUTE);
+            int rc = fold_wide(L, W, l == bn_layer ? bn_stats : nullptr, fused ? &m->layers[l - 1] : nullptr, blob->data() + off);
+            if (rc) return rc;
+            wp->op[n_ops] = NF_KOP_COUPLING;
+        } else if (L.kind == L_SCALE) {
+            blob->resize(off + NF_WIDE_SCALE_FLOATS);
+            memcpy(blob->data() + off, L.table, sizeof(L.table));
+            wp->op[n_ops] = L.scale_kind == NF_SCALE_SDN ? NF_KOP_SDN : NF_KOP_GAIN;
+        } else continue;
+        wp->off[n_ops++] = (int32_t)off;
+    }
+    wp->n_layers = n_ops;
+    *ldj_const = (float)ldj;
+    return NF_OK;
+}
+
 int check_ready(const nf_model* m) {
     if (!m) return fail(NF_ERR_INVALID, "null model");
     if (!m->finalized) return fail(NF_ERR_STATE, "model not finalized (call nf_model_finalize)");
@@ -244,12 +351,51 @@ int check_ready(const nf_model* m) {
 
 int num_ctas_for(const nf_model* m) { return m->num_ctas > 0 ? m->num_ctas : m->sm_count; }
 
+// Wide model: launch the bijectors [first, last).  The full chain with the stored statistics uses the handle's resident
+// blob; partial ranges and batch-statistics re-folds upload their own blob, stream-ordered (cudaMallocAsync).
+int launch_wide_range(const nf_model* m, int first, int last, bool inverse, NfChainArgs& a, int bn_layer, const float* bn,
+                      cudaStream_t stream) {
+    cudaError_t e;
+    if (first == 0 && last == (int)m->layers.size() && bn_layer < 0) {
+        NfWideProgram wp;
+        {
+            std::lock_guard<std::mutex> lock(m->prog_mu);
+            wp = m->wide_full;
+            a.ldj_const = m->full_ldj_const;
+        }
+        a.first_layer = 0;
+        a.last_layer = wp.n_layers;
+        e = nf::launch_chain_wide(wp, m->d_wide_full, a, inverse, num_ctas_for(m), stream);
+    } else {
+        NfWideProgram wp;
+        std::vector<float> blob;
+        float ldj = 0.f;
+        int rc;
+        {
+            std::lock_guard<std::mutex> lock(m->prog_mu);
+            rc = build_wide_program(m, first, last, &wp, &blob, &ldj, bn_layer, bn);
+        }
+        if (rc) return rc;
+        a.first_layer = 0;
+        a.last_layer = wp.n_layers;
+        a.ldj_const = ldj;
+        float* d = nullptr;
+        NF_CUDA(cudaMallocAsync((void**)&d, blob.size() * sizeof(float), stream));
+        NF_CUDA(cudaMemcpyAsync(d, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice, stream));   // pageable: staged before return
+        e = nf::launch_chain_wide(wp, d, a, inverse, num_ctas_for(m), stream);
+        NF_CUDA(cudaFreeAsync(d, stream));
+    }
+    if (e != cudaSuccess) return fail(NF_ERR_CUDA, "wide chain kernel launch: %s", cudaGetErrorString(e));
+    return NF_OK;
+}
+
 int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainArgs& a, cudaStream_t stream) {
     if (a.n < 0) return fail(NF_ERR_INVALID, "negative patch count");
     if (a.n == 0) return NF_OK;
     if (!a.y && range_has_sdn(m, first, last)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
     if (a.default_row < 0 || a.default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
     cudaError_t e;
+    if (m->width != 4) return launch_wide_range(m, first, last, inverse, a, -1, nullptr, stream);
     if (first == 0 && last == (int)m->layers.size()) {
         NfModelParams mp;   // snapshot under the lock: parameters travel by value with the launch
         {
@@ -288,6 +434,25 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
     return NF_OK;
 }
 
+// bijectors [lo, hi) with the BatchNorm of coupling `bn_layer` re-folded on explicit statistics (batch-statistics mode)
+int launch_custom(const nf_model* m, int lo, int hi, bool inverse, NfChainArgs& a, int bn_layer, const float* bn, cudaStream_t stream) {
+    if (m->width != 4) return launch_wide_range(m, lo, hi, inverse, a, bn_layer, bn, stream);
+    NfModelParams mp;
+    float ldjc = 0.f;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(m->prog_mu);
+        rc = build_program(m, lo, hi, &mp, &ldjc, bn_layer, bn);
+    }
+    if (rc) return rc;
+    a.first_layer = 0;
+    a.last_layer = mp.n_layers;
+    a.ldj_const = ldjc;
+    cudaError_t e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
+    if (e != cudaSuccess) return fail(NF_ERR_CUDA, "chain launch: %s", cudaGetErrorString(e));
+    return NF_OK;
+}
+
 }  // namespace
 
 int nf::set_error(int code, const char* what, const char* msg) { return fail(code, "%s: %s", what, msg); }
@@ -319,9 +484,12 @@ int nf_model_create(int height, int width, int channels, int net_width, nf_model
     if (height != NF_PATCH_H || width != NF_PATCH_W || channels != NF_PATCH_C)
         return fail(NF_ERR_UNSUPPORTED, "kernels are built for %dx%dx%d patches, got %dx%dx%d", NF_PATCH_H, NF_PATCH_W,
                     NF_PATCH_C, height, width, channels);
-    if (net_width != 4) return fail(NF_ERR_UNSUPPORTED, "kernels are built for coupling-net width 4, got %d", net_width);
+    if (net_width != 4 && !nf::wide_width_supported(net_width))
+        return fail(NF_ERR_UNSUPPORTED, "kernels are built for coupling-net width 4 (fused warp-per-patch kernel) and 8 / 16 / 32 "
+                                        "(CTA-per-patch kernel), got %d", net_width);
     nf_model* m = new (std::nothrow) nf_model();
     if (!m) return fail(NF_ERR_INVALID, "out of host memory");
+    m->width = net_width;
     *out = m;
     return NF_OK;
 }
@@ -339,6 +507,7 @@ int nf_model_destroy(nf_model* m) {
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (m->d_sums) cudaFree(m->d_sums);
+    if (m->d_wide_full) cudaFree(m->d_wide_full);
     delete m;
     return NF_OK;
 }
@@ -387,12 +556,34 @@ int nf_model_add_permute(nf_model* m, const int32_t* perm) {
     return NF_OK;
 }
 
+static int keep_wide_raw(Layer& L, int W, const nf_coupling_weights* w) {
+    if (!w || !w->l1_w || !w->l1_b || !w->bn1_mean || !w->bn1_var || !w->l2_w || !w->l2_b || !w->bn2_mean ||
+        !w->bn2_var || !w->last_w || !w->last_b || !w->last_logs)
+        return fail(NF_ERR_INVALID, "nf_coupling_weights: null pointer");
+    for (int o = 0; o < W; ++o)
+        if (!(w->bn1_var[o] + w->bn_eps > 0.f) || !(w->bn2_var[o] + w->bn_eps > 0.f))
+            return fail(NF_ERR_INVALID, "batch-norm variance + eps must be positive");
+    L.wraw.resize(WideRawView::floats(W));
+    float* p = L.wraw.data();
+    auto put = [&](const float* src, size_t n) { memcpy(p, src, n * sizeof(float)); p += n; };
+    put(w->l1_w, 18 * (size_t)W); put(w->l1_b, W); put(w->bn1_mean, W); put(w->bn1_var, W);
+    put(w->l2_w, (size_t)W * W); put(w->l2_b, W); put(w->bn2_mean, W); put(w->bn2_var, W);
+    put(w->last_w, 36 * (size_t)(W + 1)); put(w->last_b, 4); put(w->last_logs, 4);
+    L.raw.rescaling_scale = w->rescaling_scale;
+    L.raw.bn_eps = w->bn_eps;
+    return NF_OK;
+}
+
 int nf_model_add_affine_coupling(nf_model* m, const nf_coupling_weights* w) {
     if (!m) return fail(NF_ERR_INVALID, "null model");
     Layer L;
     L.kind = L_COUPLING;
-    int rc = fold_coupling(w, &L.cp);
-    if (!rc) keep_raw(L, w);
+    int rc;
+    if (m->width != 4) rc = keep_wide_raw(L, m->width, w);
+    else {
+        rc = fold_coupling(w, &L.cp);
+        if (!rc) keep_raw(L, w);
+    }
     if (rc) return rc;
     m->layers.push_back(L);
     m->finalized = false;
@@ -417,7 +608,20 @@ int nf_model_finalize(nf_model* m) {
     if (!m) return fail(NF_ERR_INVALID, "null model");
     if (m->layers.empty()) return fail(NF_ERR_STATE, "model has no layers");
     int rc;
-    {
+    if (m->width != 4) {   // wide net: fold the whole chain and (re-)upload it to the handle's device blob
+        std::vector<float> blob;
+        std::lock_guard<std::mutex> lock(m->prog_mu);
+        rc = build_wide_program(m, 0, (int)m->layers.size(), &m->wide_full, &blob, &m->full_ldj_const);
+        if (rc) return rc;
+        if (blob.size() > m->wide_full_floats) {
+            if (m->d_wide_full) cudaFree(m->d_wide_full);
+            m->d_wide_full = nullptr;
+            m->wide_full_floats = 0;
+            NF_CUDA(cudaMalloc((void**)&m->d_wide_full, blob.size() * sizeof(float)));
+            m->wide_full_floats = blob.size();
+        }
+        NF_CUDA(cudaMemcpy(m->d_wide_full, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
         std::lock_guard<std::mutex> lock(m->prog_mu);
         rc = build_program(m, 0, (int)m->layers.size(), &m->full, &m->full_ldj_const);
     }
@@ -453,8 +657,11 @@ int nf_model_set_affine_coupling(nf_model* m, int layer, const nf_coupling_weigh
     int rc;
     {
         std::lock_guard<std::mutex> lock(m->prog_mu);
-        rc = fold_coupling(w, &m->layers[layer].cp);
-        if (!rc) keep_raw(m->layers[layer], w);
+        if (m->width != 4) rc = keep_wide_raw(m->layers[layer], m->width, w);
+        else {
+            rc = fold_coupling(w, &m->layers[layer].cp);
+            if (!rc) keep_raw(m->layers[layer], w);
+        }
     }
     return rc ? rc : refinalize(m);
 }
@@ -705,9 +912,10 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
     if (n == 0) return NF_OK;
     if (n < 0 || !out || !stats_ws) return fail(NF_ERR_INVALID, "out and stats_ws are required");
     if (direction == 0 && !in) return fail(NF_ERR_INVALID, "in is required for the inverse direction");
+    if (default_row < 0 || default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool inverse = direction == 0;
-    const int L = (int)m->layers.size();
+    const int L = (int)m->layers.size(), W = m->width;
     // groups of bijectors that form one kernel op: [mix, coupling] pairs, or single layers
     std::vector<std::pair<int, int>> groups;
     for (int l = 0; l < L;) {
@@ -719,73 +927,52 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
     float* run_ld = logdet ? logdet : nll;   // running log-det (nll doubles as scratch until the last launch)
     const bool want_ld = run_ld != nullptr;
     const double cnt = (double)n * NF_PIXELS;
-    int n_cp = 0;
-    for (int l = 0; l < L; ++l) n_cp += m->layers[l].kind == L_COUPLING;
+    std::vector<float> bn((size_t)4 * W);          // [mean1 W][var1 W][mean2 W][var2 W]
+    std::vector<double> h((size_t)2 * W);
     bool first = true;
     for (size_t g = 0; g < groups.size(); ++g) {
         const int lo = groups[g].first, hi = groups[g].second;
         const int cl = m->layers[hi - 1].kind == L_COUPLING ? hi - 1 : -1;
-        float bn[16];
+        if (!y && range_has_sdn(m, lo, hi)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
         if (cl >= 0) {
-            for (int k = 0; k < 4; ++k) { bn[k] = 0.f; bn[8 + k] = 0.f; }
             const float ident = 1.0f - m->layers[cl].raw.bn_eps;   // identity fold: 1/sqrt(var + eps) == 1
-            for (int k = 0; k < 4; ++k) { bn[4 + k] = ident; bn[12 + k] = ident; }
+            for (int k = 0; k < W; ++k) { bn[k] = 0.f; bn[2 * W + k] = 0.f; bn[W + k] = ident; bn[3 * W + k] = ident; }
             for (int stage = 1; stage <= 2; ++stage) {
-                NfModelParams mp;
-                float ldjc = 0.f;
-                {
-                    std::lock_guard<std::mutex> lock(m->prog_mu);
-                    rc = build_program(m, lo, hi, &mp, &ldjc, cl, bn);
-                }
-                if (rc) return rc;
-                NF_CUDA(cudaMemsetAsync(stats_ws, 0, 8 * sizeof(double), stream));
+                NF_CUDA(cudaMemsetAsync(stats_ws, 0, 2 * (size_t)W * sizeof(double), stream));
                 NfChainArgs a = {};
                 a.in = first ? in : out; a.y = y; a.rows = rows; a.n = n; a.default_row = default_row;
                 a.temp = first ? temp : 1.f; a.seed = seed; a.offset = offset; a.patch_base = patch_base;
-                a.first_layer = 0; a.last_layer = mp.n_layers; a.bn_stats = stats_ws; a.bn_stage = stage;
-                if (!a.y && range_has_sdn(m, lo, hi)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
-                cudaError_t e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
-                if (e != cudaSuccess) return fail(NF_ERR_CUDA, "probe launch: %s", cudaGetErrorString(e));
-                double h[8];
-                NF_CUDA(cudaMemcpyAsync(h, stats_ws, sizeof(h), cudaMemcpyDeviceToHost, stream));
+                a.bn_stats = stats_ws; a.bn_stage = stage;
+                rc = launch_custom(m, lo, hi, inverse, a, cl, bn.data(), stream);
+                if (rc) return rc;
+                NF_CUDA(cudaMemcpyAsync(h.data(), stats_ws, 2 * (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, stream));
                 NF_CUDA(cudaStreamSynchronize(stream));
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < W; ++k) {
                     const double mean = h[k] / cnt;
-                    double var = h[4 + k] / cnt - mean * mean;   // population variance (tf.nn.moments)
+                    double var = h[W + k] / cnt - mean * mean;   // population variance (tf.nn.moments)
                     if (var < 0.0) var = 0.0;
-                    bn[(stage - 1) * 8 + k] = (float)mean;
-                    bn[(stage - 1) * 8 + 4 + k] = (float)var;
+                    bn[(stage - 1) * 2 * W + k] = (float)mean;
+                    bn[(stage - 1) * 2 * W + W + k] = (float)var;
                 }
             }
             if (batch_stats_host) {
                 int idx = 0;
                 for (int l = 0; l < cl; ++l) idx += m->layers[l].kind == L_COUPLING;
-                memcpy(batch_stats_host + 16 * idx, bn, sizeof(bn));
+                memcpy(batch_stats_host + (size_t)4 * W * idx, bn.data(), (size_t)4 * W * sizeof(float));
             }
         }
-        NfModelParams mp;
-        float ldjc = 0.f;
-        {
-            std::lock_guard<std::mutex> lock(m->prog_mu);
-            rc = build_program(m, lo, hi, &mp, &ldjc, cl, cl >= 0 ? bn : nullptr);
-        }
-        if (rc) return rc;
         const bool last = g + 1 == groups.size();
         NfChainArgs a = {};
         a.in = first ? in : out; a.y = y; a.rows = rows; a.out = out; a.n = n; a.default_row = default_row;
         a.temp = first ? temp : 1.f; a.seed = seed; a.offset = offset; a.patch_base = patch_base;
-        a.first_layer = 0; a.last_layer = mp.n_layers; a.ldj_const = ldjc;
         a.logdet_in = (want_ld && !first) ? run_ld : nullptr;
         if (last) { a.logdet = logdet; a.nll = inverse ? nll : nullptr; a.sdz = inverse ? sdz : nullptr; }
         else a.logdet = want_ld ? run_ld : nullptr;
-        if (!a.y && range_has_sdn(m, lo, hi)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
-        if (a.default_row < 0 || a.default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
-        cudaError_t e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
-        if (e != cudaSuccess) return fail(NF_ERR_CUDA, "chain launch: %s", cudaGetErrorString(e));
+        rc = launch_custom(m, lo, hi, inverse, a, cl, cl >= 0 ? bn.data() : nullptr, stream);
+        if (rc) return rc;
         first = false;
     }
     NF_CUDA(cudaStreamSynchronize(stream));
-    (void)n_cp;
     return NF_OK;
 }
 
@@ -852,6 +1039,7 @@ int nf_loss_and_grad(const nf_model* m, const float* x, const float* y, const in
                      double* sums_host, void* stream_) {
     int rc = check_ready(m);
     if (rc) return rc;
+    if (m->width != 4) return fail(NF_ERR_UNSUPPORTED, "the train-step kernels are built for coupling-net width 4, got %d", m->width);
     if (n <= 0 || !x || !workspace || !dscratch || !grads_host) return fail(NF_ERR_INVALID, "x, workspace, dscratch, grads_host are required and n > 0");
     if (default_row < 0 || default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
     cudaStream_t stream = (cudaStream_t)stream_;

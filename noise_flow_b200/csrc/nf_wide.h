@@ -1,0 +1,38 @@
+// Wide coupling nets (width 8 / 16 / 32): parameter blob layout and launcher shared by nf_api.cu (host folding)
+// and nf_wide.cu (device code).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nf_params.h"
+
+// One folded coupling inside the model's device blob (floats; every offset is a multiple of 4 -> float4 loads):
+//   A     [4][4]      mix, inverse direction, [o][i]            (identity when has_mix == 0)
+//   AINV  [4][4]      mix, forward direction, [o][i]
+//   META  has_mix, rescaling_scale, 0, 0
+//   B3    [3][3][4]   (b3 + edge-indicator taps) * exp(3 logs) by (row class, column class)
+//   B1    [W]         (b1 - mean1) / sqrt(var1 + eps)
+//   B2    [W]
+//   W1    [9][W][2]   conv 3x3 2 -> W, BN-1 folded, [tap][o][i]
+//   W2    [W][W]      conv 1x1 W -> W, BN-2 folded, [o][i]
+//   W3    [9][W][4]   conv 3x3 W -> 4 (zero-padded h2), * exp(3 logs), [tap][i][o]
+template <int W>
+struct NfWideLayout {
+    static constexpr int A = 0, AINV = 16, META = 32, B3 = 36, B1 = 72, B2 = B1 + W, W1 = B2 + W, W2 = W1 + 18 * W,
+                         W3 = W2 + W * W, SIZE = W3 + 36 * W;
+};
+inline int nf_wide_coupling_floats(int W) { return 72 + 2 * W + 18 * W + W * W + 36 * W; }
+#define NF_WIDE_SCALE_FLOATS (NF_MAX_ROWS * 4)   // scale op: NfScaleP::t
+#define NF_WIDE_MIX_FLOATS 32                    // stand-alone mix op: a[4][4], ainv[4][4], [o][i]
+
+struct NfWideProgram {           // by-value kernel argument; the parameters themselves live in the device blob
+    int32_t width;
+    int32_t n_layers;
+    int32_t op[NF_MAX_LAYERS];   // NfKernelOp, data -> latent order
+    int32_t off[NF_MAX_LAYERS];  // float offset of the op's block in the blob
+};
+
+namespace nf {
+bool wide_width_supported(int width);
+cudaError_t launch_chain_wide(const NfWideProgram& prog, const float* blob, const NfChainArgs& args, bool inverse, int num_sms,
+                              cudaStream_t stream);
+}  // namespace nf

@@ -184,6 +184,8 @@ class NoiseFlow(object):
 
     def set_tensor_cores(self, enable: bool = True):
         """Run the coupling-net 3x3 convolutions on the tensor cores (tcgen05, bf16 hi/lo split operands)."""
+        if int(self.spec.width) != 4:
+            raise NotImplementedError("the tensor-core formulation is built for width 4")
         self.build()
         _lib.check(self._engine.lib.nf_model_set_tensor_cores(self._engine.handle, 1 if enable else 0),
                    "nf_model_set_tensor_cores")
@@ -204,12 +206,13 @@ class NoiseFlow(object):
         The chain runs layer by layer (two probe launches + one apply launch per coupling)."""
         e = self._engine
         out = torch.empty((n, 32, 32, 4), device=self.device, dtype=torch.float32)
-        ws = torch.zeros(8, device=self.device, dtype=torch.float64)
+        w = int(self.spec.width)
+        ws = torch.zeros(2 * w, device=self.device, dtype=torch.float64)
         nll = torch.empty(n, device=self.device, dtype=torch.float32) if want_nll else None
         sdz = torch.empty(n, device=self.device, dtype=torch.float32) if want_nll else None
         ld = torch.empty(n, device=self.device, dtype=torch.float32) if want_logdet else None
         cps = [l for l in self.spec.layers if l.kind == "coupling"]
-        bstats = np.zeros((max(len(cps), 1), 16), dtype=np.float32)
+        bstats = np.zeros((max(len(cps), 1), 4 * w), dtype=np.float32)      # per coupling: mean1, var1, mean2, var2
         p = lambda t: t.data_ptr() if t is not None else None
         with torch.cuda.device(self.device):
             _lib.check(e.lib.nf_chain_batch_stats(
@@ -223,6 +226,7 @@ class NoiseFlow(object):
     def _apply_bn_moving_update(self, bstats, refold=True):
         """``train_m -= 0.1 * (train_m - m)`` (layers.py:394-395) for every coupling, then re-fold the engine."""
         cps = [l for l in self.spec.layers if l.kind == "coupling"]
+        w = int(self.spec.width)
         with self._lock:
             v = self.spec.store.vars
             for k, l in enumerate(cps):
@@ -230,7 +234,7 @@ class NoiseFlow(object):
                 for j, name in enumerate(("bn_nvp_conv_1/mean", "bn_nvp_conv_1/var", "bn_nvp_conv_2/mean",
                                           "bn_nvp_conv_2/var")):
                     cur = v["%s/%s" % (s, name)]
-                    cur -= np.float32(0.1) * (cur - bstats[k, 4 * j:4 * j + 4])
+                    cur -= np.float32(0.1) * (cur - bstats[k, w * j:w * j + w])
             if refold:
                 self._engine.refresh_parameters(self._extra_rows)
         self.last_batch_stats = bstats

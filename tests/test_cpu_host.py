@@ -164,6 +164,9 @@ def test_c_abi_argument_validation_without_gpu():
     h = C.c_void_p()
     assert lib.nf_model_create(16, 16, 16, 4, C.byref(h)) == -2 and b"32x32x4" in lib.nf_last_error()
     assert lib.nf_model_create(32, 32, 4, 512, C.byref(h)) == -2
+    assert lib.nf_model_create(32, 32, 4, 12, C.byref(h)) == -2              # wide kernel: widths 8 / 16 / 32
+    hw = C.c_void_p()
+    assert lib.nf_model_create(32, 32, 4, 32, C.byref(hw)) == 0 and hw.value and lib.nf_model_destroy(hw) == 0
     assert lib.nf_model_create(32, 32, 4, 4, C.byref(h)) == 0 and h.value
     perm = (C.c_int32 * 4)(0, 0, 1, 2)
     assert lib.nf_model_add_permute(h, perm) == -1

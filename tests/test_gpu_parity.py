@@ -287,7 +287,7 @@ def test_error_paths_fail_loudly(shipped):
     with pytest.raises(NotImplementedError):
         NoiseFlow([16, 16, 16], False, hps)
     with pytest.raises(RuntimeError):
-        NoiseFlow([32, 32, 4], False, make_hps(width=8), device="cuda:0").build()
+        NoiseFlow([32, 32, 4], False, make_hps(width=12), device="cuda:0").build()     # widths: 4, 8, 16, 32
     nf = _nf(hps, ck)
     with pytest.raises(ValueError):
         nf._loss(np.zeros((2, 16, 16, 4), np.float32), np.zeros((2, 16, 16, 4), np.float32))

@@ -68,27 +68,52 @@ def test_device_gradients_other_archs(arch, perm, cam, iso):
     _check(tr.gradients(), grads_o, rel=5e-3)
 
 
+def _split_zero_grad(grads):
+    """Biases in front of a batch-statistics BatchNorm have an exactly-zero gradient; what every path returns there is
+    fp32 summation noise of its own (|g| ~ 1e-3 next to gradients of 1..1000): compare those absolutely."""
+    zero_g = [k for k in grads if k.endswith("/l_1/b") or k.endswith("/l_2/b")]
+    return zero_g, {k: g for k, g in grads.items() if k not in zero_g}
+
+
 def test_device_gradients_per_patch_rows(shipped):
-    """Per-patch (camera, ISO): the table-row gradients of several rows chain into the shared sdn5 variables."""
+    """Per-patch (camera, ISO): the table-row gradients of several rows chain into the shared sdn5 variables.  Three
+    independent launch paths must agree: device trainer as a CUDA graph, as plain launches, and the host path."""
     from noise_flow_b200 import NoiseFlow
     from noise_flow_b200.train import DeviceTrainer, loss_and_grad
     hps, ck = shipped
-    x, y = synth_batch(6, cam=2, iso=100, seed=97)
+    # every patch is drawn with the camera NLF of ITS (camera, ISO).  (Feeding S6/ISO-100 noise through other rows
+    # starves some hidden channels: a channel that is constant over the batch has batch variance 0, its normalised
+    # value is 0 or +-1 ulp * 100 depending on summation order, and the ReLU mask of the WHOLE channel flips with it --
+    # two valid, reproducible gradients that differ by per cent.  Observed on the host path; not a kernel bug.)
     cams = [2.0, 2.0, 0.0, 4.0, 1.0, 2.0]
-    isos = [100.0, 800.0, 400.0, 100.0, 3200.0, 1600.0]
-    nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
-    tr = DeviceTrainer(nf, max_batch=8)
-    tr.loss_and_grad(x, y, iso=isos, cam=cams, is_training=True)
+    isos = [100.0, 800.0, 400.0, 100.0, 800.0, 1600.0]
+    parts = [synth_batch(1, cam=int(c), iso=int(i), seed=97 + k) for k, (c, i) in enumerate(zip(cams, isos))]
+    x, y = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    res = {}
+    for name, graph in (("graph", True), ("plain", False)):
+        nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+        tr = DeviceTrainer(nf, max_batch=8, cuda_graph=graph)
+        tr.loss_and_grad(x, y, iso=isos, cam=cams, is_training=True)
+        res[name] = (tr.loss()[0], tr.gradients())
     nf2 = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
     loss_h, _, grads_h = loss_and_grad(nf2, x, y, iso=isos, cam=cams, is_training=True)
-    assert abs(tr.loss()[0] - loss_h) / 4096 < 2e-6
-    grads = tr.gradients()
-    # biases in front of a batch-statistics BatchNorm have an exactly-zero gradient; what both paths return there is
-    # fp32 summation noise of their own (|g| ~ 1e-3 next to gradients of 1..1000), so compare those absolutely
-    zero_g = [k for k in grads_h if k.endswith("/l_1/b") or k.endswith("/l_2/b")]
-    for k in zero_g:
-        assert np.abs(grads[k]).max() < 2e-2 and np.abs(grads_h[k]).max() < 2e-2, k
-    _check({k: g for k, g in grads.items() if k not in zero_g}, {k: g for k, g in grads_h.items() if k not in zero_g}, rel=2e-3)
+    res["host"] = (loss_h, grads_h)
+    report = []
+    for a, b in (("graph", "plain"), ("graph", "host"), ("plain", "host")):
+        zero_g, ga = _split_zero_grad(res[a][1])
+        _, gb = _split_zero_grad(res[b][1])
+        worst = max(np.abs(ga[k] - gb[k]).max() / max(np.abs(gb[k]).max(), 0.5) for k in gb)
+        report.append("%s vs %s: loss diff %.2e, worst relative gradient diff %.2e" % (a, b, abs(res[a][0] - res[b][0]) / 4096, worst))
+    print("\n".join(report))
+    for name in res:
+        assert abs(res[name][0] - loss_h) / 4096 < 2e-6, report
+        zero_g, g = _split_zero_grad(res[name][1])
+        for k in zero_g:
+            assert np.abs(res[name][1][k]).max() < 2e-2, (name, k)
+        try:
+            _check(g, _split_zero_grad(grads_h)[1], rel=2e-3)
+        except AssertionError as e:
+            raise AssertionError("\n".join(report) + "\n" + str(e)[:600])
 
 
 @pytest.mark.parametrize("cuda_graph", [True, False])

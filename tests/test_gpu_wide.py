@@ -1,0 +1,131 @@
+"""Coupling nets wider than the shipped width 4 (``--width`` 8 / 16 / 32, sidd/ArgParser.py:43, job_noise_flow.sh:19):
+the CTA-per-patch kernel (csrc/nf_wide.cu) against the CPU oracle in both directions and both BatchNorm modes."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from common import make_oracle, synth_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _perturbed_model(width, arch="sdn5|unc|unc|gain4|unc", perm=1, seed=11):
+    """Fresh model with non-trivial weights (the reference initialises l_last to zero = identity coupling)."""
+    from noise_flow_b200 import NoiseFlow, make_hps
+    hps = make_hps(arch=arch, width=width, flow_permutation=perm)
+    nf0 = NoiseFlow([32, 32, 4], False, copy.copy(hps), device="cuda:0", seed=seed, first_call="inverse")
+    rng = np.random.RandomState(seed)
+    vs = {k: v.copy() for k, v in nf0.variables.items()}
+    for k in vs:
+        if k.endswith("/l_1/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.5).astype(np.float32)
+        elif k.endswith("/l_2/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * (1.0 / np.sqrt(width))).astype(np.float32)
+        elif k.endswith("/l_last/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * (0.2 / np.sqrt(width))).astype(np.float32)
+        elif k.endswith("/b") or k.endswith("/logs"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.2).astype(np.float32)
+        elif k.endswith("/mean"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.1).astype(np.float32)
+        elif k.endswith("/var"):
+            vs[k] = (0.5 + rng.rand(*vs[k].shape)).astype(np.float32)
+        elif "rescaling_scale" in k:
+            vs[k] = np.float32(0.5)
+    return hps, vs
+
+
+@pytest.mark.parametrize("width", [8, 16, 32])
+def test_wide_log_prob_and_sample_match_oracle(width):
+    from noise_flow_b200 import NoiseFlow
+    hps, vs = _perturbed_model(width)
+    nf = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+    orc = make_oracle(hps, vs)
+    x, y = synth_batch(5, cam=2, iso=100, seed=31)
+    x = (x * 20).astype(np.float32)                 # O(1) inputs so that the coupling nets are exercised
+    nll, sd_z, z = nf._loss(x, y, iso=[100.0], cam=[2.0], return_z=True)
+    nll_o, sd_o = orc._loss(x, y, iso=[100.0], cam=[2.0])
+    assert np.abs(nll.cpu().numpy() - nll_o.numpy()).max() / 4096 < 1e-4          # tolerance: 1e-4 nats / dim
+    assert abs(float(sd_z) - float(sd_o)) < 1e-4
+    z_o, _ = orc.inverse(x, torch.zeros(5, dtype=torch.float64), y, iso=[100.0], cam=[2.0])
+    assert np.abs(z.cpu().numpy() - z_o.numpy()).max() < 2e-4 * max(1.0, float(z_o.abs().max()))
+    # sampling direction with injected eps, and the round trip
+    eps = np.random.RandomState(5).randn(5, 32, 32, 4).astype(np.float32)
+    xs = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], eps=eps).cpu().numpy()
+    xo = orc.sample(eps, 0.6, y, iso=[100.0], cam=[2.0]).numpy()
+    assert np.abs(xs - xo).max() < 2e-4 * max(1.0, np.abs(xo).max())
+    back = nf.forward(z, None, y, iso=[100.0], cam=[2.0]).cpu().numpy()
+    assert np.abs(back - x).max() < 1e-4 * max(1.0, np.abs(x).max())
+
+
+def test_wide_per_bijector_and_permutation():
+    """run_layers over single bijectors (partial programs upload their own blob), channel permutation, per-patch rows."""
+    from noise_flow_b200 import NoiseFlow
+    hps, vs = _perturbed_model(16, arch="unc|sdn4|unc|gain4", perm=0, seed=13)
+    nf = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+    orc = make_oracle(hps, vs)
+    x, y = synth_batch(4, cam=2, iso=100, seed=33)
+    x = (x * 20).astype(np.float32)
+    cams, isos = [2.0, 0.0, 1.0, 4.0], [100.0, 800.0, 400.0, 3200.0]
+    nll = nf._loss(x, y, iso=isos, cam=cams)[0].cpu().numpy()
+    for k in range(4):
+        nll_o, _ = orc._loss(x[k:k + 1], y[k:k + 1], iso=[isos[k]], cam=[cams[k]])
+        assert abs(nll[k] - float(nll_o[0])) / 4096 < 1e-4
+    n_layers = len(nf.get_layer_names())
+    cur = torch.as_tensor(x).cuda()
+    total = torch.zeros(4, device="cuda")
+    for l in range(n_layers):
+        cur, ld = nf.run_layers(l, l + 1, "inverse", cur, y, iso=[100.0], cam=[2.0])
+        total += ld
+    z, ld_all = nf.inverse(x, None, y, iso=[100.0], cam=[2.0])
+    assert float((cur - z).abs().max()) < 1e-4 * max(1.0, float(z.abs().max()))
+    assert float((total - ld_all).abs().max()) / 4096 < 1e-5
+
+
+@pytest.mark.parametrize("width", [8, 32])
+def test_wide_batch_statistics_mode_matches_oracle(width):
+    """is_training=True: BatchNorm on the statistics of the batch, moving statistics updated (layers.py:388-398)."""
+    from noise_flow_b200 import NoiseFlow
+    hps, vs = _perturbed_model(width, arch="sdn5|unc|gain4|unc")
+    nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables={k: v.copy() for k, v in vs.items()}, device="cuda:0",
+                   first_call="inverse")
+    orc = make_oracle(hps, vs)
+    x, y = synth_batch(6, cam=2, iso=100, seed=35)
+    x = (x * 20).astype(np.float32)
+    nll, sd_z = nf._loss(x, y, iso=[100.0], cam=[2.0], is_training=True)
+    nll_o, sd_o = orc._loss(x, y, iso=[100.0], cam=[2.0], is_training=True)
+    assert np.abs(nll.cpu().numpy() - nll_o.numpy()).max() / 4096 < 1e-4
+    for k, v in orc.store.vars.items():
+        if k.endswith("/mean") or k.endswith("/var"):
+            assert np.allclose(nf.variables[k], v.detach().numpy(), rtol=1e-4, atol=1e-5), k
+    eps = np.random.RandomState(6).randn(6, 32, 32, 4).astype(np.float32)
+    xs = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], eps=eps, is_training=True).cpu().numpy()
+    xo = orc.sample(eps, 0.6, y, iso=[100.0], cam=[2.0], is_training=True).numpy()
+    assert np.abs(xs - xo).max() < 5e-4 * max(1.0, np.abs(xo).max())
+
+
+def test_wide_philox_sampling_statistics_and_large_batch():
+    """In-kernel Philox sampling on more patches than CTAs; mean NLL of the sampled noise is finite and stable."""
+    from noise_flow_b200 import NoiseFlow
+    hps, vs = _perturbed_model(8)
+    nf = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+    n = 700
+    y = torch.rand((n, 32, 32, 4), device="cuda")
+    xs = nf.sample(y, 1.0, y, iso=[100.0], cam=[2.0], seed=3, offset=0)
+    xs2 = nf.sample(y, 1.0, y, iso=[100.0], cam=[2.0], seed=3, offset=0)
+    assert torch.equal(xs, xs2)                                  # counter-based RNG: same (seed, offset) -> same draw
+    nll, sd_z, z = nf._loss(xs, y, iso=[100.0], cam=[2.0], return_z=True)
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3 and abs(float(sd_z) - 1.0) < 2e-2
+
+
+def test_wide_training_is_refused_loudly():
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import DeviceTrainer, loss_and_grad
+    hps, vs = _perturbed_model(8)
+    nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+    x, y = synth_batch(2)
+    with pytest.raises(NotImplementedError):
+        DeviceTrainer(nf)
+    with pytest.raises(RuntimeError):
+        loss_and_grad(nf, x, y, iso=[100.0], cam=[2.0])
