@@ -78,72 +78,91 @@ __device__ __forceinline__ void wide_coupling(const float* __restrict__ gblob, W
         for (int r = warp; r < 32; r += WIDE_WARPS) S.z[r * 32 + lane] = w_mix(S.z[r * 32 + lane], w + L::A);
         __syncthreads();
     }
+    // Each thread owns TWO pixels (rows `warp` and `warp + 16`, column `lane`) and walks them together: every weight
+    // fetched from shared memory (broadcast LDS.128) feeds both, which halves the shared-memory instructions per FMA
+    // (with one pixel the LDS pipe, 1 per clock and SM, saturates together with the FMA pipe).
+    static_assert(WIDE_WARPS == 16, "two rows per warp");
+    const int rows2[2] = {warp, warp + 16};
     // ---- P1: conv 3x3 SAME (2 -> W) + folded BN + ReLU ; conv 1x1 (W -> W) + folded BN + ReLU
-    for (int r = warp; r < 32; r += WIDE_WARPS) {
-        float h1[W];
+    {
+        float h1[2][W];
 #pragma unroll
-        for (int o = 0; o < W; ++o) h1[o] = w[L::B1 + o];
+        for (int o = 0; o < W; ++o) h1[0][o] = h1[1][o] = w[L::B1 + o];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-            const int rr = r + dy - 1;
-            if (rr < 0 || rr > 31) continue;
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
                 const int cc = lane + dx - 1;
-                float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cc >= 0 && cc <= 31) x0 = S.z[rr * 32 + cc];
+                float2 x0[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int rr = rows2[q] + dy - 1;
+                    x0[q] = make_float2(0.f, 0.f);
+                    if (rr >= 0 && rr <= 31 && cc >= 0 && cc <= 31) { const float4 v = S.z[rr * 32 + cc]; x0[q] = make_float2(v.x, v.y); }
+                }
                 const float* wt = w + L::W1 + (dy * 3 + dx) * W * 2;
 #pragma unroll
                 for (int o = 0; o < W; o += 2) {
                     const float4 wv = *reinterpret_cast<const float4*>(wt + o * 2);   // (o,i0) (o,i1) (o+1,i0) (o+1,i1)
-                    h1[o] = fmaf(x0.x, wv.x, fmaf(x0.y, wv.y, h1[o]));
-                    h1[o + 1] = fmaf(x0.x, wv.z, fmaf(x0.y, wv.w, h1[o + 1]));
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        h1[q][o] = fmaf(x0[q].x, wv.x, fmaf(x0[q].y, wv.y, h1[q][o]));
+                        h1[q][o + 1] = fmaf(x0[q].x, wv.z, fmaf(x0[q].y, wv.w, h1[q][o + 1]));
+                    }
                 }
             }
         }
-        if (STAGE == 1) {   // probes reduce row by row (no per-thread accumulator arrays: registers)
+        if (STAGE == 1) {   // probes reduce right away (no per-thread accumulator arrays: registers)
 #pragma unroll
             for (int o = 0; o < W; ++o) {
-                const float a = w_warp_sum(h1[o]), q = w_warp_sum(h1[o] * h1[o]);
+                const float a = w_warp_sum(h1[0][o] + h1[1][o]), q = w_warp_sum(fmaf(h1[0][o], h1[0][o], h1[1][o] * h1[1][o]));
                 if (lane == 0) { atomicAdd(&S.sacc[o], a); atomicAdd(&S.sacc[W + o], q); }
             }
-            continue;
+            return;
         }
 #pragma unroll
-        for (int o = 0; o < W; ++o) h1[o] = fmaxf(h1[o], 0.f);
+        for (int o = 0; o < W; ++o) { h1[0][o] = fmaxf(h1[0][o], 0.f); h1[1][o] = fmaxf(h1[1][o], 0.f); }
 #pragma unroll
         for (int o = 0; o < W; o += 4) {
-            float acc[4];
+            float acc[2][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = w[L::B2 + o + j];
+            for (int j = 0; j < 4; ++j) acc[0][j] = acc[1][j] = w[L::B2 + o + j];
 #pragma unroll
             for (int i = 0; i < W; i += 4) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 wv = *reinterpret_cast<const float4*>(w + L::W2 + (o + j) * W + i);
-                    acc[j] = fmaf(h1[i], wv.x, fmaf(h1[i + 1], wv.y, fmaf(h1[i + 2], wv.z, fmaf(h1[i + 3], wv.w, acc[j]))));
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        acc[q][j] = fmaf(h1[q][i], wv.x, fmaf(h1[q][i + 1], wv.y, fmaf(h1[q][i + 2], wv.z, fmaf(h1[q][i + 3], wv.w, acc[q][j]))));
                 }
             }
             if (STAGE == 2) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float a = w_warp_sum(acc[j]), q = w_warp_sum(acc[j] * acc[j]);
+                    const float a = w_warp_sum(acc[0][j] + acc[1][j]), q = w_warp_sum(fmaf(acc[0][j], acc[0][j], acc[1][j] * acc[1][j]));
                     if (lane == 0) { atomicAdd(&S.sacc[o + j], a); atomicAdd(&S.sacc[W + o + j], q); }
                 }
             } else {
-                S.h2[((r + 1) * G + (o >> 2)) * 34 + lane + 1] =
-                    make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    S.h2[((rows2[q] + 1) * G + (o >> 2)) * 34 + lane + 1] =
+                        make_float4(fmaxf(acc[q][0], 0.f), fmaxf(acc[q][1], 0.f), fmaxf(acc[q][2], 0.f), fmaxf(acc[q][3], 0.f));
             }
         }
     }
     if (STAGE) return;
     __syncthreads();
     // ---- P2: conv 3x3 over the zero-padded h2 (+ folded edge-indicator bias) -> shift, log-scale ; affine update
-    for (int r = warp; r < 32; r += WIDE_WARPS) {
-        const int rc = r == 0 ? 0 : (r == 31 ? 2 : 1), cc = lane == 0 ? 0 : (lane == 31 ? 2 : 1);
-        float pre[4];
+    {
+        const int cc = lane == 0 ? 0 : (lane == 31 ? 2 : 1);
+        float pre[2][4];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) pre[o] = w[L::B3 + (rc * 3 + cc) * 4 + o];
+        for (int q = 0; q < 2; ++q) {
+            const int rc = rows2[q] == 0 ? 0 : (rows2[q] == 31 ? 2 : 1);
+#pragma unroll
+            for (int o = 0; o < 4; ++o) pre[q][o] = w[L::B3 + (rc * 3 + cc) * 4 + o];
+        }
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -151,31 +170,37 @@ __device__ __forceinline__ void wide_coupling(const float* __restrict__ gblob, W
                 const float* wt = w + L::W3 + (dy * 3 + dx) * W * 4;
 #pragma unroll 4
                 for (int g = 0; g < G; ++g) {
-                    const float4 h = S.h2[((r + dy) * G + g) * 34 + lane + dx];
                     const float4 w0 = *reinterpret_cast<const float4*>(wt + (g * 4 + 0) * 4);
                     const float4 w1 = *reinterpret_cast<const float4*>(wt + (g * 4 + 1) * 4);
                     const float4 w2 = *reinterpret_cast<const float4*>(wt + (g * 4 + 2) * 4);
                     const float4 w3 = *reinterpret_cast<const float4*>(wt + (g * 4 + 3) * 4);
-                    pre[0] = fmaf(h.x, w0.x, fmaf(h.y, w1.x, fmaf(h.z, w2.x, fmaf(h.w, w3.x, pre[0]))));
-                    pre[1] = fmaf(h.x, w0.y, fmaf(h.y, w1.y, fmaf(h.z, w2.y, fmaf(h.w, w3.y, pre[1]))));
-                    pre[2] = fmaf(h.x, w0.z, fmaf(h.y, w1.z, fmaf(h.z, w2.z, fmaf(h.w, w3.z, pre[2]))));
-                    pre[3] = fmaf(h.x, w0.w, fmaf(h.y, w1.w, fmaf(h.z, w2.w, fmaf(h.w, w3.w, pre[3]))));
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float4 h = S.h2[((rows2[q] + dy) * G + g) * 34 + lane + dx];
+                        pre[q][0] = fmaf(h.x, w0.x, fmaf(h.y, w1.x, fmaf(h.z, w2.x, fmaf(h.w, w3.x, pre[q][0]))));
+                        pre[q][1] = fmaf(h.x, w0.y, fmaf(h.y, w1.y, fmaf(h.z, w2.y, fmaf(h.w, w3.y, pre[q][1]))));
+                        pre[q][2] = fmaf(h.x, w0.z, fmaf(h.y, w1.z, fmaf(h.z, w2.z, fmaf(h.w, w3.z, pre[q][2]))));
+                        pre[q][3] = fmaf(h.x, w0.w, fmaf(h.y, w1.w, fmaf(h.z, w2.w, fmaf(h.w, w3.w, pre[q][3]))));
+                    }
                 }
             }
         const float scale = w[L::META + 1];
-        const float ls0 = scale * w_tanh(pre[2]), ls1 = scale * w_tanh(pre[3]);          // layers.py:362-365
-        float4 z = S.z[r * 32 + lane];
-        if (INV) {                                                                        // layers.py:355-375
-            z.z = fmaf(z.z, w_exp(ls0), pre[0]);
-            z.w = fmaf(z.w, w_exp(ls1), pre[1]);
-            ldj += ls0 + ls1;
-        } else {                                                                          // layers.py:333-353
-            z.z = (z.z - pre[0]) * w_exp(-ls0);
-            z.w = (z.w - pre[1]) * w_exp(-ls1);
-            ldj -= ls0 + ls1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float ls0 = scale * w_tanh(pre[q][2]), ls1 = scale * w_tanh(pre[q][3]);      // layers.py:362-365
+            float4 z = S.z[rows2[q] * 32 + lane];
+            if (INV) {                                                                          // layers.py:355-375
+                z.z = fmaf(z.z, w_exp(ls0), pre[q][0]);
+                z.w = fmaf(z.w, w_exp(ls1), pre[q][1]);
+                ldj += ls0 + ls1;
+            } else {                                                                            // layers.py:333-353
+                z.z = (z.z - pre[q][0]) * w_exp(-ls0);
+                z.w = (z.w - pre[q][1]) * w_exp(-ls1);
+                ldj -= ls0 + ls1;
+            }
+            if (!INV && has_mix) z = w_mix(z, w + L::AINV);
+            S.z[rows2[q] * 32 + lane] = z;
         }
-        if (!INV && has_mix) z = w_mix(z, w + L::AINV);
-        S.z[r * 32 + lane] = z;
     }
 }
 

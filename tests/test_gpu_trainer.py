@@ -156,7 +156,9 @@ def test_device_adam_steps_match_host_train_step(shipped):
     for k, vh in nf_h.variables.items():
         d = np.abs(got[k].astype(np.float64) - vh.astype(np.float64)).max()
         if "bn_nvp_conv" in k:
-            assert d < 1e-5 * max(1.0, np.abs(vh).max()), (k, d)
+            # the conv biases in front of a batch-statistics BatchNorm random-walk by +-lr per step (zero gradient,
+            # Adam's normalised step on fp32 noise) and shift the batch means with them: |d mean| <= 3 lr per step
+            assert d < 1e-4 * max(1.0, np.abs(vh).max()), (k, d)
         else:
             # Adam's normalised step is +-lr wherever a gradient is ~0 up to fp32 noise (biases in front of a
             # batch-statistics BatchNorm), so two correct implementations may differ there by a few lr
