@@ -90,6 +90,8 @@ struct nf_model {
     } st[2];
     double* d_sums = nullptr;
     int64_t chunk = 0;
+    float* h_tmp = nullptr;      // pinned scratch for per-patch results the caller did not ask for (sums only)
+    size_t h_tmp_floats = 0;
     // wide coupling nets (width 8 / 16 / 32, nf_wide.cu): the folded program of the whole chain lives in a device
     // blob owned by the handle (re-uploaded by nf_model_finalize / nf_model_set_*)
     int width = 4;
@@ -507,6 +509,7 @@ int nf_model_destroy(nf_model* m) {
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (m->d_sums) cudaFree(m->d_sums);
+    if (m->h_tmp) cudaFreeHost(m->h_tmp);
     if (m->d_wide_full) cudaFree(m->d_wide_full);
     delete m;
     return NF_OK;
@@ -837,11 +840,20 @@ int nf_log_prob_host(const nf_model* cm, const float* x_host, const float* y_hos
     if (rc) return rc;
     const size_t pb = (size_t)NF_DIMS * sizeof(float);
     double tot[3] = {0.0, 0.0, 0.0};
-    std::vector<float> tmp_nll, tmp_sdz;
-    if (sums_host && !nll_host) tmp_nll.resize((size_t)n);
-    if (sums_host && !sdz_host) tmp_sdz.resize((size_t)n);
-    float* nll_dst = nll_host ? nll_host : tmp_nll.data();
-    float* sdz_dst = sdz_host ? sdz_host : (sums_host ? tmp_sdz.data() : nullptr);
+    // Results the caller did not ask for but the sums need go to PINNED scratch: a device->host copy into pageable
+    // memory blocks the host until the chunk's kernel has finished, which would serialise copies and compute.
+    const size_t need = ((sums_host && !nll_host) ? (size_t)n : 0) + ((sums_host && !sdz_host) ? (size_t)n : 0);
+    if (need > m->h_tmp_floats) {
+        if (m->h_tmp) cudaFreeHost(m->h_tmp);
+        m->h_tmp = nullptr;
+        m->h_tmp_floats = 0;
+        NF_CUDA(cudaHostAlloc((void**)&m->h_tmp, need * sizeof(float), cudaHostAllocDefault));
+        m->h_tmp_floats = need;
+    }
+    float* tmp_nll = (sums_host && !nll_host) ? m->h_tmp : nullptr;
+    float* tmp_sdz = (sums_host && !sdz_host) ? m->h_tmp + (tmp_nll ? (size_t)n : 0) : nullptr;
+    float* nll_dst = nll_host ? nll_host : tmp_nll;
+    float* sdz_dst = sdz_host ? sdz_host : tmp_sdz;
     int64_t k = 0;
     for (int64_t off = 0; off < n; off += m->chunk, ++k) {
         nf_model::Staging& s = m->st[k & 1];

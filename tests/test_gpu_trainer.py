@@ -166,12 +166,16 @@ def test_device_adam_steps_match_host_train_step(shipped):
     close = [np.abs(got[k].astype(np.float64) - nf_h.variables[k]).max() < 2e-6 for k in got
              if k.endswith("/W") or "matpar" in k or "sdn_gain" in k]
     assert np.mean(close) > 0.9
-    # sync_to_model: the inference engine now evaluates the trained variables
+    # sync_to_model: the inference engine now evaluates exactly the trained variables (compared with a fresh model
+    # built from them; the host-trained twin differs by the bias random walk above, ~3e-4 nats/dim in eval mode)
     tr.sync_to_model()
     x, y = synth_batch(4, seed=300)
     nll_d, _ = nf_d._loss(x, y, iso=[100.0], cam=[2.0], is_training=False)
+    nf_f = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=got, device="cuda:0", first_call="inverse")
+    nll_f, _ = nf_f._loss(x, y, iso=[100.0], cam=[2.0], is_training=False)
+    assert torch.equal(nll_d, nll_f)
     nll_h, _ = nf_h._loss(x, y, iso=[100.0], cam=[2.0], is_training=False)
-    assert float((nll_d - nll_h).abs().max()) / 4096 < 1e-4
+    assert float((nll_d - nll_h).abs().max()) / 4096 < 2e-3
 
 
 def test_device_trainer_rejects_unsupported():
@@ -187,3 +191,25 @@ def test_device_trainer_rejects_unsupported():
         tr.step(x, y, iso=[100.0], cam=[2.0])
     with pytest.raises(NotImplementedError):
         tr.step(x[:2], y[:2], iso=[250.0], cam=[2.0])
+
+
+def test_device_gradients_per_patch_rows_match_oracle(shipped):
+    """Moving-statistics mode makes patches independent, so the gradient of the batch-mean NLL with per-patch
+    (camera, ISO) is the mean of per-patch oracle gradients: pins the row -> sdn5-variable chain rule on the device."""
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import DeviceTrainer
+    hps, ck = shipped
+    cams, isos = [2.0, 0.0, 4.0, 1.0], [100.0, 400.0, 100.0, 800.0]
+    parts = [synth_batch(1, cam=int(c), iso=int(i), seed=61 + k) for k, (c, i) in enumerate(zip(cams, isos))]
+    x, y = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    nf = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    tr = DeviceTrainer(nf, max_batch=4)
+    tr.loss_and_grad(x, y, iso=isos, cam=cams, is_training=False)
+    grads = tr.gradients()
+    acc, loss_acc = None, 0.0
+    for k in range(4):
+        l, _, g, _ = _oracle_loss_and_grads(hps, ck, x[k:k + 1], y[k:k + 1], isos[k], cams[k], False)
+        loss_acc += l / 4
+        acc = {n: v / 4 for n, v in g.items()} if acc is None else {n: acc[n] + g[n] / 4 for n in g}
+    assert abs(tr.loss()[0] - loss_acc) / 4096 < 1e-4
+    _check(grads, acc, rel=1e-3)

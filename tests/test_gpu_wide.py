@@ -129,3 +129,29 @@ def test_wide_training_is_refused_loudly():
         DeviceTrainer(nf)
     with pytest.raises(RuntimeError):
         loss_and_grad(nf, x, y, iso=[100.0], cam=[2.0])
+
+
+def test_wide_model_through_saved_artefacts_and_wrapper(tmp_path):
+    """Write hps.txt + a TF-V2 checkpoint of a width-16 model, reload it through ``NoiseFlowWrapper`` (the reference's
+    public sampling API) and compare the fused (moving-statistics) sampler with the oracle on injected noise."""
+    from noise_flow_b200 import NoiseFlow, hps_logger, save_checkpoint
+    from noise_flow_b200.NoiseFlowWrapper import NoiseFlowWrapper
+    hps, vs = _perturbed_model(16, arch="sdn5|unc|unc|gain4|unc|unc")
+    d = tmp_path / "WideFlow"
+    (d / "ckpt").mkdir(parents=True)
+    nf = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+    hps_logger(str(d / "hps.txt"), hps, nf.get_layer_names(), nf.num_trainable_params())      # borealisflows/utils.py:110-119
+    save_checkpoint(str(d / "ckpt" / "model.ckpt.best"), nf.variables)
+    w = NoiseFlowWrapper(str(d), sampling_temperature=0.6, template_order="training", bn_mode="moving", seed=5)
+    assert int(w.hps.width) == 16 and w.nf_model.get_layer_names() == nf.get_layer_names()
+    y = np.random.RandomState(8).rand(7, 32, 32, 4).astype(np.float32)
+    out = w.sample_noise_nf(y, 0.0, 0.0, 800, 2)
+    assert out.shape == (7, 32, 32, 4) and out.dtype == np.float32 and np.isfinite(out).all()
+    eps = np.random.RandomState(9).randn(7, 32, 32, 4).astype(np.float32)
+    xs = w.nf_model.sample(y, 0.6, y, iso=[800.0], cam=[2.0], eps=eps).cpu().numpy()
+    xo = make_oracle(hps, vs).sample(eps, 0.6, y, iso=[800.0], cam=[2.0]).numpy()
+    assert np.abs(xs - xo).max() < 2e-4 * max(1.0, np.abs(xo).max())
+    # the wrapper's default (batch statistics, is_training=True as the reference feeds) runs on wide nets too
+    w2 = NoiseFlowWrapper(str(d), sampling_temperature=0.6)
+    out2 = w2.sample_noise_nf(y, 0.0, 0.0, 800, 2)
+    assert out2.shape == (7, 32, 32, 4) and np.isfinite(out2).all()
