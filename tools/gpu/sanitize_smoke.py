@@ -30,6 +30,32 @@ if os.environ.get("NF_SANITIZE_TRAIN", "1") == "1":
     nf3 = NoiseFlow([32, 32, 4], True, hps, variables=dict(ck), device="cuda:0", first_call="inverse")
     loss, sd = train_step(nf3, AdamOptimizer(1e-4), x, y, iso=[100.0], cam=[2.0])
     print("train loss", float(loss))
+if os.environ.get("NF_SANITIZE_TRAINER", "1") == "1":     # device-resident train step: plain launches and CUDA-graph replay
+    from noise_flow_b200.train import DeviceTrainer
+    nt = min(n, 11)
+    for graph in (False, True):
+        nf4 = NoiseFlow([32, 32, 4], True, hps, variables=dict(ck), device="cuda:0", first_call="inverse")
+        tr = DeviceTrainer(nf4, learning_rate=1e-4, max_batch=16, cuda_graph=graph)
+        for _ in range(2):
+            l4, s4 = tr.step(x[:nt], y[:nt], iso=[100.0], cam=[2.0])
+        tr.loss_and_grad(x[:nt], y[:nt], iso=[100.0] * nt, cam=[2.0] * (nt - 1) + [0.0], is_training=False)   # per-patch rows
+        tr.sync_to_model()
+        print("device trainer graph=%s loss %.4f" % (graph, l4 / 4096))
+if os.environ.get("NF_SANITIZE_WIDE", "1") == "1":        # CTA-per-patch kernel for wide coupling nets
+    nw = min(n, 7)
+    for wd in (8, 32):
+        nfw = NoiseFlow([32, 32, 4], False, make_hps(arch="sdn5|unc|gain4|unc", width=wd), device="cuda:0", first_call="inverse", seed=1)
+        for k, v in nfw.variables.items():
+            if k.endswith("/l_last/W"):
+                v[...] = (np.random.RandomState(2).randn(*v.shape) * 0.05).astype(np.float32)
+        nfw.refresh_parameters()
+        nl, _, zw = nfw._loss(x[:nw], y[:nw], iso=[100.0], cam=[2.0], return_z=True)
+        xw = nfw.forward(zw, None, yy=y[:nw], iso=[100.0], cam=[2.0])
+        sw = nfw.sample(y[:nw], 0.6, y[:nw], iso=[100.0], cam=[2.0], seed=3, offset=0)
+        nb, _ = nfw._loss(x[:nw], y[:nw], iso=[100.0], cam=[2.0], is_training=True)
+        zl, _ = nfw.run_layers(1, 3, "inverse", x[:nw], yy=y[:nw], iso=[100.0], cam=[2.0])
+        print("wide %d: nll/dim %.4f round trip %.2e batch-stat nll/dim %.4f" % (wd, float(nl.mean()) / 4096,
+              float(np.abs(xw.cpu().numpy() - x[:nw]).max()), float(nb.mean()) / 4096))
 if os.environ.get("NF_SANITIZE_TC", "0") == "1":
     nf.set_tensor_cores(True)
     nll_t, _ = nf._loss(x, y, iso=[100.0], cam=[2.0])
