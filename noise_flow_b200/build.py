@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
         deps_newer = (not os.path.exists(obj)) or force or any(
-            os.path.getmtime(s) > os.path.getmtime(obj) for s in _sources() if s.endswith(".h") or s == path)
+            os.path.getmtime(s) > os.path.getmtime(obj) for s in _sources() if s.endswith((".h", ".cuh")) or s == path)
         if not deps_newer:
             continue
         cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]

@@ -34,6 +34,29 @@ __device__ __forceinline__ B3 load_b3(const CP& P, int lane) {
     return b;
 }
 
+// the 4x4 mix matrix as OPAQUE per-thread registers: ptxas otherwise hoists these 16 uniform loads out of the row loop,
+// runs out of uniform registers, parks them in vector registers and pays an R2UR per value and row
+template <bool INV, class CP>
+__device__ __forceinline__ void load_mix_regs(const CP& P, float2 (&am)[4][2]) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        am[o][0] = INV ? ld2(&P.a[o][0]) : ld2(&P.ainv[o][0]);
+        am[o][1] = INV ? ld2(&P.a[o][2]) : ld2(&P.ainv[o][2]);
+        asm volatile("" : "+f"(am[o][0].x), "+f"(am[o][0].y), "+f"(am[o][1].x), "+f"(am[o][1].y));
+    }
+}
+__device__ __forceinline__ float4 mix4r(float4 v, const float2 (&m)[4][2]) {
+    const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+    float r[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        float2 t = ffma2(lo, m[o][0], make_float2(0.f, 0.f));
+        t = ffma2(hi, m[o][1], t);
+        r[o] = t.x + t.y;
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+
 // STATS: 0 = normal step.  1 / 2 = batch-statistics probe (reference batch_norm(training=True),
 // layers.py:388-398): accumulate sum and sum-of-squares of the conv-1 (1) or conv-2 (2) output BEFORE its
 // BatchNorm into stats[0..3] / stats[4..7]; nothing is published and stage C does not run.  The caller folds
@@ -41,7 +64,7 @@ __device__ __forceinline__ B3 load_b3(const CP& P, int lane) {
 template <bool INV, bool GUARDED, int STATS = 0, class CP>
 __device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const ZStore& zs, const int lane, const int t,
                                               const bool has_mix, Acc4& b_old, Acc4& b_mid, Acc4& c_old, Acc4& c_mid,
-                                              const B3& b3, float& ldj, float* stats = nullptr) {
+                                              const B3& b3, float& ldj, const float2 (&am)[4][2], float* stats = nullptr) {
     const float2 zero2 = make_float2(0.f, 0.f);
     const bool do_a = !GUARDED || t < 32;
     const bool b_fma = !GUARDED || (t >= 1 && t <= 32);
@@ -60,7 +83,7 @@ __device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const ZS
     if (do_a) {
         float4 z = za;
         if (INV && has_mix) {
-            z = mix4(z, P.a);                                   // Conv2d1x1._inverse, layers.py:117-119
+            z = mix4r(z, am);                                   // Conv2d1x1._inverse, layers.py:117-119
             zs.store(t, z);
         }
         s.xr[t & 1][lane + 1] = make_float2(z.x, z.y);
@@ -160,7 +183,7 @@ __device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const ZS
             z.z = (z.z - h3[0]) * fast_exp(-ls0);                                // layers.py:343-347
             z.w = (z.w - h3[1]) * fast_exp(-ls1);
             ldj -= ls0 + ls1;                                                    // layers.py:352
-            if (has_mix) z = mix4(z, P.ainv);                                    // Conv2d1x1._forward, layers.py:113-114
+            if (has_mix) z = mix4r(z, am);                                       // Conv2d1x1._forward, layers.py:113-114
         }
         zs.store(q, z);
     }
@@ -171,13 +194,15 @@ template <bool INV, class CP>
 __device__ __forceinline__ void coupling_pass(const CP& P, WarpSmem& s, const ZStore& zs, const int lane, float& ldj) {
     const bool has_mix = P.has_mix != 0;
     const B3 b3 = load_b3(P, lane);
+    float2 am[4][2];
+    load_mix_regs<INV>(P, am);
     Acc4 b_old, b_mid, c_old, c_mid;
 #pragma unroll
     for (int o = 0; o < 4; ++o) b_old.v[o] = b_mid.v[o] = c_old.v[o] = c_mid.v[o] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int t = 0; t < 36; ++t) {
-        if (t >= 5 && t < 32) coupling_step<INV, false>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj);
-        else                  coupling_step<INV, true>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj);
+        if (t >= 5 && t < 32) coupling_step<INV, false>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am);
+        else                  coupling_step<INV, true>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am);
     }
 }
 
@@ -190,9 +215,11 @@ __device__ __forceinline__ void coupling_stats_pass(const CP& P, WarpSmem& s, co
 #pragma unroll
     for (int o = 0; o < 4; ++o) b_old.v[o] = b_mid.v[o] = c_old.v[o] = c_mid.v[o] = make_float2(0.f, 0.f);
     float ldj = 0.f;
+    float2 am[4][2];
+    load_mix_regs<INV>(P, am);
 #pragma unroll 1
     for (int t = 0; t < 34; ++t)
-        coupling_step<INV, true, STAGE>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, stats);
+        coupling_step<INV, true, STAGE>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am, stats);
 }
 
 }  // namespace nf
