@@ -34,15 +34,20 @@ __device__ __forceinline__ B3 load_b3(const CP& P, int lane) {
     return b;
 }
 
-// the 4x4 mix matrix as OPAQUE per-thread registers: ptxas otherwise hoists these 16 uniform loads out of the row loop,
-// runs out of uniform registers, parks them in vector registers and pays an R2UR per value and row
+// The 4x4 mix matrix as PER-THREAD registers.  Left to itself ptxas hoists these 16 uniform loads (and a dozen conv-1
+// weights) out of the row loop, runs out of uniform registers, parks the values in vector registers and pays an R2UR per
+// value and row step (31 of 293 instructions).  Adding a 0.0f that is only known at run time (the zero halo of the row
+// ring, read from shared memory) makes the values genuinely per-thread for ptxas -- it sees through empty inline asm and
+// even through shuffles of warp-uniform values -- so the mix runs as FFMA2 with vector-register operands: 261
+// instructions per step, no R2UR (data -> latent kernel; the latent -> data kernel keeps its 34 R2UR either way).
 template <bool INV, class CP>
-__device__ __forceinline__ void load_mix_regs(const CP& P, float2 (&am)[4][2]) {
+__device__ __forceinline__ void load_mix_regs(const CP& P, float2 (&am)[4][2], const float rt_zero) {
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
         am[o][0] = INV ? ld2(&P.a[o][0]) : ld2(&P.ainv[o][0]);
         am[o][1] = INV ? ld2(&P.a[o][2]) : ld2(&P.ainv[o][2]);
-        asm volatile("" : "+f"(am[o][0].x), "+f"(am[o][0].y), "+f"(am[o][1].x), "+f"(am[o][1].y));
+        am[o][0] = make_float2(am[o][0].x + rt_zero, am[o][0].y + rt_zero);
+        am[o][1] = make_float2(am[o][1].x + rt_zero, am[o][1].y + rt_zero);
     }
 }
 __device__ __forceinline__ float4 mix4r(float4 v, const float2 (&m)[4][2]) {
@@ -195,7 +200,7 @@ __device__ __forceinline__ void coupling_pass(const CP& P, WarpSmem& s, const ZS
     const bool has_mix = P.has_mix != 0;
     const B3 b3 = load_b3(P, lane);
     float2 am[4][2];
-    load_mix_regs<INV>(P, am);
+    load_mix_regs<INV>(P, am, s.xr[0][0].x);
     Acc4 b_old, b_mid, c_old, c_mid;
 #pragma unroll
     for (int o = 0; o < 4; ++o) b_old.v[o] = b_mid.v[o] = c_old.v[o] = c_mid.v[o] = make_float2(0.f, 0.f);
@@ -216,7 +221,7 @@ __device__ __forceinline__ void coupling_stats_pass(const CP& P, WarpSmem& s, co
     for (int o = 0; o < 4; ++o) b_old.v[o] = b_mid.v[o] = c_old.v[o] = c_mid.v[o] = make_float2(0.f, 0.f);
     float ldj = 0.f;
     float2 am[4][2];
-    load_mix_regs<INV>(P, am);
+    load_mix_regs<INV>(P, am, s.xr[0][0].x);
 #pragma unroll 1
     for (int t = 0; t < 34; ++t)
         coupling_step<INV, true, STAGE>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am, stats);
