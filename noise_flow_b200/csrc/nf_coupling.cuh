@@ -69,8 +69,9 @@ __device__ __forceinline__ float4 mix4r(float4 v, const float2 (&m)[4][2]) {
 template <bool INV, bool GUARDED, int STATS = 0, class CP>
 __device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const ZStore& zs, const int lane, const int t,
                                               const bool has_mix, Acc4& b_old, Acc4& b_mid, Acc4& c_old, Acc4& c_mid,
-                                              const B3& b3, float& ldj, const float2 (&am)[4][2], float* stats = nullptr) {
+                                              const B3& b3, float& ldj, const float2 (&am)[4][2], const float2 (&w2c)[4][2], float* stats = nullptr) {
     const float2 zero2 = make_float2(0.f, 0.f);
+    constexpr bool W2R = !INV && STATS == 0;
     const bool do_a = !GUARDED || t < 32;
     const bool b_fma = !GUARDED || (t >= 1 && t <= 32);
     const bool b_emit = !GUARDED || (t >= 2 && t <= 33);
@@ -134,8 +135,8 @@ __device__ __forceinline__ void coupling_step(const CP& P, WarpSmem& s, const ZS
         float h2[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-            float2 u = ffma2(h01, ld2(&P.w2[o][0]), zero2);
-            u = ffma2(h23, ld2(&P.w2[o][2]), u);
+            float2 u = ffma2(h01, W2R ? w2c[o][0] : ld2(&P.w2[o][0]), zero2);
+            u = ffma2(h23, W2R ? w2c[o][1] : ld2(&P.w2[o][2]), u);
             const float c2 = u.x + u.y + P.b2[o];
             if (STATS == 2) { stats[o] += c2; stats[4 + o] = fmaf(c2, c2, stats[4 + o]); }
             h2[o] = fmaxf(c2, 0.f);
@@ -201,13 +202,22 @@ __device__ __forceinline__ void coupling_pass(const CP& P, WarpSmem& s, const ZS
     const B3 b3 = load_b3(P, lane);
     float2 am[4][2];
     load_mix_regs<INV>(P, am, s.xr[0][0].x);
+    float2 w2c[4][2];
+    if (!INV) {
+        const float rz = s.xr[0][0].x;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            w2c[o][0] = make_float2(P.w2[o][0] + rz, P.w2[o][1] + rz);
+            w2c[o][1] = make_float2(P.w2[o][2] + rz, P.w2[o][3] + rz);
+        }
+    }
     Acc4 b_old, b_mid, c_old, c_mid;
 #pragma unroll
     for (int o = 0; o < 4; ++o) b_old.v[o] = b_mid.v[o] = c_old.v[o] = c_mid.v[o] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int t = 0; t < 36; ++t) {
-        if (t >= 5 && t < 32) coupling_step<INV, false>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am);
-        else                  coupling_step<INV, true>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am);
+        if (t >= 5 && t < 32) coupling_step<INV, false>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am, w2c);
+        else                  coupling_step<INV, true>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am, w2c);
     }
 }
 
@@ -222,9 +232,10 @@ __device__ __forceinline__ void coupling_stats_pass(const CP& P, WarpSmem& s, co
     float ldj = 0.f;
     float2 am[4][2];
     load_mix_regs<INV>(P, am, s.xr[0][0].x);
+    float2 w2c[4][2] = {};
 #pragma unroll 1
     for (int t = 0; t < 34; ++t)
-        coupling_step<INV, true, STAGE>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am, stats);
+        coupling_step<INV, true, STAGE>(P, s, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, b3, ldj, am, w2c, stats);
 }
 
 }  // namespace nf
