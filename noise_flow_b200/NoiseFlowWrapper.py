@@ -69,7 +69,7 @@ class NoiseFlowWrapper:
     def sample_noise_nf(self, batch_x, b1, b2, iso, cam):
         """NoiseFlowWrapper.py:81-87.  ``b1``/``b2`` are fed as nlf0/nlf1 (ignored by the shipped arch)."""
         x = self.sample_sidd_tf(batch_x, b1, b2, iso, cam)
-        return x.detach().cpu().numpy()
+        return self.nf_model.to_numpy(x)
 
     def sample_sidd_tf(self, batch_x, b1=0.0, b2=0.0, iso=100, cam=0):
         """NoiseFlowWrapper.py:89-94: returns the device tensor (the reference returns the TF op)."""

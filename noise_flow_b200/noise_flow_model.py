@@ -145,6 +145,8 @@ class NoiseFlow(object):
         self.device = torch.device(device)
         self._engine: Optional[_Engine] = None
         self._lock = threading.Lock()
+        self._tls = threading.local()
+        self._stale = False
         self._extra_rows: List[tuple] = []
         self._seed = seed
         self._sample_calls = 0
@@ -177,6 +179,14 @@ class NoiseFlow(object):
         if self._engine is not None:
             with self._lock:
                 self._engine.refresh_parameters(self._extra_rows)
+                self._stale = False
+
+    def _fresh(self):
+        """Re-fold the engine if the BatchNorm moving statistics were moved since the last fold.  A batch-statistics
+        call (is_training=True) only WRITES the moving statistics; folding them into the fused moving-statistics
+        program is deferred to the first call that reads them."""
+        if self._stale:
+            self.refresh_parameters()
 
     def set_launch(self, warps_per_cta: int = 12, num_ctas: int = 0):
         self.build()
@@ -236,18 +246,62 @@ class NoiseFlow(object):
                     cur = v["%s/%s" % (s, name)]
                     cur -= np.float32(0.1) * (cur - bstats[k, w * j:w * j + w])
             if refold:
-                self._engine.refresh_parameters(self._extra_rows)
+                self._stale = True            # lazily re-folded by the next moving-statistics call (_fresh)
         self.last_batch_stats = bstats
+
+    # ---- host <-> device staging for the numpy-in / numpy-out calls of the reference API --------------------------
+    # A pageable cudaMemcpy runs at a few GB/s; large numpy batches therefore go through per-thread PINNED staging
+    # buffers (multi-threaded host copy into / out of them, DMA at PCIe speed).  One set per calling thread: the
+    # reference drives one model from 16-32 Python threads (train_noise_flow.py:38-47).
+    _PIN_MIN_BYTES = 1 << 20
+
+    def _pinned(self, role, shape):
+        tl = self._tls
+        pool = getattr(tl, "pool", None)
+        if pool is None:
+            pool = tl.pool = {}
+        n = int(np.prod(shape))
+        buf = pool.get(role)
+        if buf is None or buf.numel() < n:
+            buf = pool[role] = torch.empty(max(n, 2 * (buf.numel() if buf is not None else 0)), dtype=torch.float32, pin_memory=True)
+        return buf[:n].view(shape)
 
     def _dev(self, a, name):
         if a is None:
             return None
         if not isinstance(a, torch.Tensor):
-            a = torch.as_tensor(np.asarray(a))
+            arr = np.asarray(a)
+            if arr.ndim != 4 or tuple(arr.shape[1:]) != (32, 32, 4):
+                raise ValueError("%s must have shape [N, 32, 32, 4], got %s" % (name, tuple(arr.shape)))
+            if arr.size * 4 >= self._PIN_MIN_BYTES and self.device.type == "cuda":
+                ev = getattr(self._tls, "h2d_done_" + name, None)
+                if ev is not None:
+                    ev.synchronize()                       # the previous upload from this staging buffer has finished
+                pin = self._pinned("in_" + name, arr.shape)
+                pin.copy_(torch.from_numpy(np.ascontiguousarray(arr)))        # dtype conversion + parallel host copy
+                out = pin.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                setattr(self._tls, "h2d_done_" + name, ev)
+                return out
+            a = torch.as_tensor(arr)
         a = a.to(device=self.device, dtype=torch.float32).contiguous()
         if a.dim() != 4 or tuple(a.shape[1:]) != (32, 32, 4):
             raise ValueError("%s must have shape [N, 32, 32, 4], got %s" % (name, tuple(a.shape)))
         return a
+
+    def to_numpy(self, t: torch.Tensor) -> np.ndarray:
+        """Device tensor -> fresh float32 numpy array (what ``sess.run`` returned); large results travel through the
+        calling thread's pinned staging buffer."""
+        t = t.detach()
+        if not t.is_cuda or t.numel() * 4 < self._PIN_MIN_BYTES:
+            return t.cpu().numpy()
+        pin = self._pinned("out", tuple(t.shape))
+        pin.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        out = torch.empty(tuple(t.shape), dtype=torch.float32)
+        out.copy_(pin)                                     # parallel host copy out of the reusable pinned buffer
+        return out.numpy()
 
     def _rows(self, n, nlf0, nlf1, iso, cam):
         """(rows tensor or None, default_row).  The reference feeds length-1 ``iso``/``cam`` lists per
@@ -300,6 +354,7 @@ class NoiseFlow(object):
                 return z, ld
             obj = objective if isinstance(objective, torch.Tensor) else torch.as_tensor(np.asarray(objective))
             return z, obj.to(self.device, torch.float32) + ld
+        self._fresh()
         z = torch.empty_like(x)
         ld = torch.empty(n, device=self.device, dtype=torch.float32)
         e = self._engine
@@ -321,6 +376,7 @@ class NoiseFlow(object):
         rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
         if training:
             return self._batch_stats_chain(1, z, yy, rows, drow, n)[0]
+        self._fresh()
         x = torch.empty_like(z)
         e = self._engine
         with torch.cuda.device(self.device):
@@ -338,8 +394,9 @@ class NoiseFlow(object):
         call counter, so successive calls give fresh noise like ``tf.random_normal``)."""
         training = self._check_training(is_training)
         self.build()
+        same = yy is y
         y = self._dev(y, "y")
-        yy = self._dev(yy, "yy") if yy is not None else None
+        yy = y if same else (self._dev(yy, "yy") if yy is not None else None)   # sidd_utils.py:1165-1170 passes y twice
         n = y.shape[0]
         rows, drow = self._rows(n, nlf0, nlf1, iso, cam)
         temp = 1.0 if eps_std is None else float(np.asarray(eps_std).reshape(-1)[0])
@@ -351,6 +408,7 @@ class NoiseFlow(object):
         if training:
             return self._batch_stats_chain(1, eps, yy, rows, drow, n, temp, self._seed if seed is None else seed,
                                            offset, patch_base)[0]
+        self._fresh()
         x = torch.empty_like(y)
         e = self._engine
         with torch.cuda.device(self.device):
@@ -380,6 +438,7 @@ class NoiseFlow(object):
             self.last_sums = sums
             sd_z = (sums[1] / max(n, 1)).to(torch.float32)
             return (nll, sd_z, z) if return_z else (nll, sd_z)
+        self._fresh()
         nll = torch.empty(n, device=self.device, dtype=torch.float32)
         sdz = torch.empty(n, device=self.device, dtype=torch.float32)
         z = torch.empty_like(x) if return_z else None
@@ -422,6 +481,7 @@ class NoiseFlow(object):
     def run_layers(self, first: int, last: int, direction: str, x, yy=None, nlf0=None, nlf1=None, iso=None, cam=None):
         """``_inverse_and_log_det_jacobian`` / ``_forward_and_log_det_jacobian`` of bijectors first..last-1."""
         self.build("inverse")
+        self._fresh()
         x, yy = self._dev(x, "x"), self._dev(yy, "yy")
         n = x.shape[0]
         rows, drow = self._rows(n, nlf0, nlf1, iso, cam)

@@ -158,6 +158,7 @@ def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_trainin
     numpy, same shapes as the variables) for every trainable variable.  With ``is_training`` (the reference's train
     thread, ``train_noise_flow.py:64-71``) BatchNorm runs on batch statistics and the moving statistics are updated."""
     nf.build("inverse")
+    nf._fresh()          # the engine's moving statistics feed the is_training=False gradient
     _tick(None)
     eng, spec = nf._engine, nf.spec
     lib = eng.lib
