@@ -3,12 +3,20 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
 legs may import this module.  The product (``noise_flow_b200``) never does.
 
-PARITY UNPINNED: the reference (BorealisAI/noise_flow, TF 1.12 / TFP 0.5) ships no tests and
-TensorFlow cannot run in this environment, so this restatement is pinned only by (a) the shipped
-checkpoint artefacts (tensor names / shapes / ``num_params`` / layer names) and the initial-value
-constants of the shipped ``.meta`` graph (LU assembly and 6-vector ordering, initialisers), (b) closed-form
-known answers derived from the reference's own formulas and (c) self-consistency
-(round trips, brute-force Jacobians).  See DESIGN.md "Oracle".
+PARITY PINNED against the reference's own Python: TensorFlow 1.12 / TFP 0.5 cannot be installed here (Python
+3.12, no network) and the reference ships no tests, but its unmodified source files (``borealisflows/*.py`` including
+the ``NoiseFlowWrapper`` class) are executed in the build container over a stand-in for the TF-1.12 API surface they
+touch (``oracle/tf1_shim.py``: the TF primitives restated over torch fp64, a deferred graph with placeholders /
+Session / Saver) by ``oracle/make_reference_goldens.py``, and the outputs are committed as ``tests/golden/ref_*.npz``.
+This restatement reproduces them to fp64 round-off (tests/test_cpu_reference_goldens.py): NLL, z, log-det, samples,
+both BatchNorm modes and their moving-average side effects, tf.gradients of all 2433 parameters, two Adam steps,
+the wrapper's sampling-only graph, every ``sdn*`` / ``gain*`` token, squeeze / unsqueeze.  What remains restated on
+BOTH sides -- and is therefore pinned only by TensorFlow's documented semantics -- is the handful of TF primitives
+themselves (conv2d SAME/VALID, moments, make_template scope naming, fill_triangular, where / one_hot).
+Additional pins: (a) the shipped checkpoint artefacts (tensor names / shapes / ``num_params`` / layer names) and the
+initial-value constants of the shipped ``.meta`` graph (LU assembly and 6-vector ordering, initialisers),
+(b) closed-form known answers derived from the reference's own formulas and (c) self-consistency (round trips,
+brute-force Jacobians).  See DESIGN.md "Oracle".
 
 It is a line-by-line restatement in torch-CPU (float64 by default, float32 on request) of
 
