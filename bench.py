@@ -117,31 +117,46 @@ def cpu_oracle_rate(hps, ck, seconds_target=12.0, threads=None):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path = oracle port (TF 1.12 cannot run), all host threads."""
+    """--impl reference: the reference's own CPU path on the box's host cores, all threads.  TF 1.12 cannot run and
+    /root/reference does not exist on the GPU box, so the timed code is the oracle port (torch-CPU fp32) -- the same
+    restatement that reproduces the reference's own Python to fp64 round-off (tests/test_cpu_reference_goldens.py).
+    Same config / metric / unit as our arm; every step is a bounded sample (--ref-patches) of that workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from common import make_oracle, synth_batch
     hps, ck = load_model_files()
+    if args.arch:
+        hps.arch = args.arch
     threads = os.cpu_count()
     torch.set_num_threads(threads)
     orc = make_oracle(hps, ck, dtype=torch.float32)
     per_step = args.ref_patches
     x, y = synth_batch(per_step, seed=5)
+    eps = np.random.RandomState(6).randn(per_step, 32, 32, 4).astype(np.float32)
+    if args.mode == "sample":
+        step = lambda: orc.sample(eps, 0.6, y, iso=[100.0], cam=[2.0])     # noqa: E731
+    else:
+        step = lambda: orc.loss(x, y, iso=[100.0], cam=[2.0])             # noqa: E731
     for _ in range(max(args.warmup, 1)):
-        orc._loss(x, y, iso=[100.0], cam=[2.0])
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.loss(x, y, iso=[100.0], cam=[2.0])
+        step()
     dt = time.perf_counter() - t0
     val = per_step * args.steps / dt
-    out = {"impl": "reference", "metric": "patches_per_sec_nll", "value": val, "unit": "patches/s",
+    mode = "sample" if args.mode == "sample" else "log_prob"
+    sample = "%d steps x %d patches of the workload on %d host threads" % (args.steps, per_step, threads)
+    out = {"impl": "reference", "metric": {"log_prob": "patches_per_sec_nll", "sample": "patches_per_sec_sample"}[mode],
+           "value": val, "unit": "patches/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "log_prob S-Ax4-G-Ax4 (shipped weights), %d patches/step on host cores" % per_step,
+           "config": {"workload": "%s Noise Flow (shipped weights, arch %s), batch %d 32x32x4 patches per GPU, "
+                                  "cam S6 / ISO 100" % (mode, hps.arch, args.batch),
+                      "per_gpu_batch": args.batch, "global_batch": args.gpus * args.batch, "parallelism": "dp%d" % args.gpus,
+                      "width": 4, "reference_sample": sample,
                       "note": "TF 1.12/TFP 0.5 reference cannot run here; timed arm = oracle port (torch-CPU fp32)"},
-           "cpu_baseline": {"value": val, "unit": "patches/s", "cores": threads, "kind": "port",
-                            "sample": "%d steps x %d patches" % (args.steps, per_step)},
+           "cpu_baseline": {"value": val, "unit": "patches/s", "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
