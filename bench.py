@@ -367,7 +367,7 @@ def main():
         d2h = B * 4 if args.mode == "log_prob" else nb
         e2e = {"value": world * B * e_steps / edt, "unit": "patches/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e_steps,
-               "path": "nf_%s_host: pinned host buffers, 4096-patch chunks double-buffered on 2 streams" % args.mode}
+               "path": "nf_%s_host: pinned host buffers, 4096-patch chunks in flight on 4 streams" % args.mode}
         del hx_t, hy_t, hn_t
 
     if rank != 0:

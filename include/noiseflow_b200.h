@@ -244,7 +244,7 @@ int nf_histogram(const float* data, int64_t count, const double* edges, int n_bi
                  void* stream);
 
 /* ---- host-buffer entry points (what NoiseFlowWrapper.sample_noise_nf / sess.run replace) -------- */
-/* Host pointers; copies are chunked and double-buffered on two internal streams.  Buffers from
+/* Host pointers; copies are chunked (4096 patches) and pipelined over four internal streams.  Buffers from
  * nf_host_alloc (pinned) overlap copies with compute; pageable memory works but serialises.
  * sums (host double[3], optional) as nf_reduce_sums. rows_host may be NULL. */
 int nf_log_prob_host(const nf_model* m, const float* x_host, const float* y_host, const int32_t* rows_host,

@@ -87,7 +87,8 @@ struct nf_model {
         int32_t* rows = nullptr;
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-    } st[2];
+    } st[4];                     // staging slots of the _host pipeline (kSlots)
+    static constexpr int kSlots = 4;
     double* d_sums = nullptr;
     int64_t chunk = 0;
     float* h_tmp = nullptr;      // pinned scratch for per-patch results the caller did not ask for (sums only)
@@ -856,7 +857,7 @@ int nf_log_prob_host(const nf_model* cm, const float* x_host, const float* y_hos
     float* sdz_dst = sdz_host ? sdz_host : tmp_sdz;
     int64_t k = 0;
     for (int64_t off = 0; off < n; off += m->chunk, ++k) {
-        nf_model::Staging& s = m->st[k & 1];
+        nf_model::Staging& s = m->st[k % nf_model::kSlots];
         const int64_t c = (n - off < m->chunk) ? n - off : m->chunk;
         NF_CUDA(cudaEventSynchronize(s.done));   // previous use of this slot has drained
         NF_CUDA(cudaMemcpyAsync(s.x, x_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));
@@ -894,7 +895,7 @@ int nf_sample_host(const nf_model* cm, const float* y_host, const int32_t* rows_
     const size_t pb = (size_t)NF_DIMS * sizeof(float);
     int64_t k = 0;
     for (int64_t off = 0; off < n; off += m->chunk, ++k) {
-        nf_model::Staging& s = m->st[k & 1];
+        nf_model::Staging& s = m->st[k % nf_model::kSlots];
         const int64_t c = (n - off < m->chunk) ? n - off : m->chunk;
         NF_CUDA(cudaEventSynchronize(s.done));
         if (y_host) NF_CUDA(cudaMemcpyAsync(s.y, y_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));

@@ -58,9 +58,39 @@ struct __align__(16) TdSmem {
     float4 g[34 * 34];                     // padded gradient image
 };
 
-__device__ __forceinline__ void cta_acc(float* acc, int slot, float v, int lane) {
-    v = tw_sum(v);
-    if (lane == 0 && v != 0.f) atomicAdd(acc + slot, v);
+// K partial sums per lane -> lane l (l < K) ends up with the warp-wide total of v[l].  Transposed butterfly: at offset
+// `half` a lane keeps the half of its values whose index has that bit equal to its own lane bit and trades the other
+// half, so the value count halves with every step: P - 1 shuffles for P = 2^ceil(log2 K) values (offsets >= P are plain
+// butterflies over the K values) instead of 5 K -- the parameter-gradient reductions were ~1000 SHFL per warp and patch
+// in pass B1, half of its stall samples (profiles/r02_td_b1_train_207_ncu_full.txt).
+template <int K>
+__device__ __forceinline__ float warp_reduce_to_lanes(const float (&v)[K], int lane) {
+    constexpr int P = K <= 1 ? 1 : K <= 2 ? 2 : K <= 4 ? 4 : K <= 8 ? 8 : K <= 16 ? 16 : 32;
+    static_assert(K >= 1 && K <= 32, "one value per lane at most");
+    float x[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) x[i] = i < K ? v[i] : 0.f;
+#pragma unroll
+    for (int half = 16; half >= P; half >>= 1)
+#pragma unroll
+        for (int i = 0; i < K; ++i) x[i] += __shfl_xor_sync(0xffffffffu, x[i], half);
+#pragma unroll
+    for (int half = P / 2; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = up ? x[i + half] : x[i];
+            const float send = up ? x[i] : x[i + half];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return x[0];      // lane l: total of v[l % P]
+}
+// CTA-level accumulation of K consecutive slots: one shared-memory atomic instruction per warp (lane l -> slot l)
+template <int K>
+__device__ __forceinline__ void cta_acc_vec(float* acc, const float (&v)[K], int lane) {
+    const float tot = warp_reduce_to_lanes<K>(v, lane);
+    if (lane < K && tot != 0.f) atomicAdd(acc + lane, tot);
 }
 __device__ __forceinline__ bool on_ring(int k) {
     const int R = k / 34, C = k - R * 34;
@@ -153,8 +183,7 @@ td_fwd_kernel(const TdCoupling d, const float* __restrict__ vars, const float* _
 #pragma unroll
                 for (int o = 0; o < 4; ++o) { s[o] += c1[o]; q[o] = fmaf(c1[o], c1[o], q[o]); }
             }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) { cta_acc(S.acc, o, s[o], lane); cta_acc(S.acc, 4 + o, q[o], lane); }
+            { const float v8[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]}; cta_acc_vec<8>(S.acc, v8, lane); }
         } else if (STAGE == 2) {
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
             for (int r = warp; r < 32; r += TD_WARPS) {
@@ -171,8 +200,7 @@ td_fwd_kernel(const TdCoupling d, const float* __restrict__ vars, const float* _
                     q[o] = fmaf(c2, c2, q[o]);
                 }
             }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) { cta_acc(S.acc, 8 + o, s[o], lane); cta_acc(S.acc, 12 + o, q[o], lane); }
+            { const float v8[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]}; cta_acc_vec<8>(S.acc + 8, v8, lane); }
         } else {
             for (int r = warp; r < 32; r += TD_WARPS) {
                 float c1hat[4], h1[4], c2hat[4];
@@ -278,17 +306,17 @@ td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
             gzp[p * NF_PIXELS + r * 32 + lane] = make_float4(go.x, go.y, go.z * el0, go.w * el1);   // x0 part completed in B3
         }
         __syncthreads();
-        cta_acc(S.acc, NF_G_SCALE, g_scale, lane);
-#pragma unroll
-        for (int o = 0; o < 4; ++o) { cta_acc(S.acc, NF_G_LOGS + o, g_logs[o], lane); cta_acc(S.acc, NF_G_B3 + o, g_b3[o], lane); }
+        {   // slots NF_G_B3 .. NF_G_SCALE are consecutive: b3[4], logs[4], scale
+            static_assert(NF_G_LOGS == NF_G_B3 + 4 && NF_G_SCALE == NF_G_B3 + 8, "gradient block layout");
+            const float v9[9] = {g_b3[0], g_b3[1], g_b3[2], g_b3[3], g_logs[0], g_logs[1], g_logs[2], g_logs[3], g_scale};
+            cta_acc_vec<9>(S.acc + NF_G_B3, v9, lane);
+        }
         // grad W3[dy][dx][ci][o] = sum_pixels in(r+dy, c+dx)[ci] * g_pre3(r, c)[o]   (ci = 4: ring indicator)
         for (int dy = 0; dy < 3; ++dy)
             for (int dx = 0; dx < 3; ++dx) {
-                float a[5][4];
+                float a[20];            // [ci][o], the 20 consecutive slots of this tap
 #pragma unroll
-                for (int ci = 0; ci < 5; ++ci)
-#pragma unroll
-                    for (int o = 0; o < 4; ++o) a[ci][o] = 0.f;
+                for (int k = 0; k < 20; ++k) a[k] = 0.f;
                 for (int r = warp; r < 32; r += TD_WARPS) {
                     const int R = r + dy, C = lane + dx;
                     const float4 h = S.h2[R * 34 + C];
@@ -298,12 +326,9 @@ td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
 #pragma unroll
                     for (int ci = 0; ci < 5; ++ci)
 #pragma unroll
-                        for (int o = 0; o < 4; ++o) a[ci][o] = fmaf(hv[ci], gv[o], a[ci][o]);
+                        for (int o = 0; o < 4; ++o) a[ci * 4 + o] = fmaf(hv[ci], gv[o], a[ci * 4 + o]);
                 }
-#pragma unroll
-                for (int ci = 0; ci < 5; ++ci)
-#pragma unroll
-                    for (int o = 0; o < 4; ++o) cta_acc(S.acc, NF_G_W3 + ((dy * 3 + dx) * 5 + ci) * 4 + o, a[ci][o], lane);
+                cta_acc_vec<20>(S.acc + NF_G_W3 + (dy * 3 + dx) * 20, a, lane);
             }
         // g_h2(r, c)[ci] = sum_{dy,dx,o} W3[dy][dx][ci][o] * g_pre3(r-dy+1, c-dx+1)[o] ; ReLU mask ; BatchNorm-2 sums
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -330,8 +355,7 @@ td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
             }
             scratch[p * NF_PIXELS + r * 32 + lane] = make_float4(gc[0], gc[1], gc[2], gc[3]);
         }
-#pragma unroll
-        for (int o = 0; o < 4; ++o) { cta_acc(S.acc, NF_G_BN2 + o, s1[o], lane); cta_acc(S.acc, NF_G_BN2 + 4 + o, s2[o], lane); }
+        { const float v8[8] = {s1[0], s1[1], s1[2], s1[3], s2[0], s2[1], s2[2], s2[3]}; cta_acc_vec<8>(S.acc + NF_G_BN2, v8, lane); }
         __syncthreads();
     }
     td_flush(S, grads, 0, NF_G_COUPLING_DOUBLES);
@@ -381,13 +405,18 @@ td_b2_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
             }
             scratch[p * NF_PIXELS + r * 32 + lane] = make_float4(gc1[0], gc1[1], gc1[2], gc1[3]);
         }
+        {   // W2[4][4] and b2[4] are 20 consecutive slots; the BatchNorm-1 sums 8 more
+            static_assert(NF_G_B2 == NF_G_W2 + 16, "gradient block layout");
+            float v20[20];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            cta_acc(S.acc, NF_G_B2 + i, gb2[i], lane);
-            cta_acc(S.acc, NF_G_BN1 + i, t1[i], lane);
-            cta_acc(S.acc, NF_G_BN1 + 4 + i, t2[i], lane);
+            for (int i = 0; i < 4; ++i) {
 #pragma unroll
-            for (int o = 0; o < 4; ++o) cta_acc(S.acc, NF_G_W2 + i * 4 + o, gw2[i][o], lane);
+                for (int o = 0; o < 4; ++o) v20[i * 4 + o] = gw2[i][o];
+                v20[16 + i] = gb2[i];
+            }
+            cta_acc_vec<20>(S.acc + NF_G_W2, v20, lane);
+            const float v8[8] = {t1[0], t1[1], t1[2], t1[3], t2[0], t2[1], t2[2], t2[3]};
+            cta_acc_vec<8>(S.acc + NF_G_BN1, v8, lane);
         }
         __syncthreads();
     }
@@ -428,25 +457,30 @@ td_b3_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
             S.g[(r + 1) * 34 + lane + 1] = make_float4(gc1[0], gc1[1], gc1[2], gc1[3]);
         }
         __syncthreads();
-#pragma unroll
-        for (int o = 0; o < 4; ++o) cta_acc(S.acc, NF_G_B1 + o, gb1[o], lane);
+        cta_acc_vec<4>(S.acc + NF_G_B1, gb1, lane);
         // grad W1[dy][dx][ci][o] = sum_pixels x0(r+dy-1, c+dx-1)[ci] * g_c1(r, c)[o]
-        for (int dy = 0; dy < 3; ++dy)
-            for (int dx = 0; dx < 3; ++dx) {
-                float a[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                for (int r = warp; r < 32; r += TD_WARPS) {
-                    const int rr = r + dy - 1, cc = lane + dx - 1;
-                    if (rr < 0 || rr > 31 || cc < 0 || cc > 31) continue;
+        for (int dy = 0; dy < 3; ++dy) {
+            float a[24];                // [dx][ci][o]: the 24 consecutive slots of filter row dy
+#pragma unroll
+            for (int k = 0; k < 24; ++k) a[k] = 0.f;
+            for (int r = warp; r < 32; r += TD_WARPS) {
+                const int rr = r + dy - 1;
+                if (rr < 0 || rr > 31) continue;
+                const float4 g = S.g[(r + 1) * 34 + lane + 1];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int cc = lane + dx - 1;
+                    if (cc < 0 || cc > 31) continue;
                     const float4 z = S.zp[rr * 32 + cc];
-                    const float4 g = S.g[(r + 1) * 34 + lane + 1];
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) { a[0][o] = fmaf(z.x, comp(g, o), a[0][o]); a[1][o] = fmaf(z.y, comp(g, o), a[1][o]); }
+                    for (int o = 0; o < 4; ++o) {
+                        a[dx * 8 + o] = fmaf(z.x, comp(g, o), a[dx * 8 + o]);
+                        a[dx * 8 + 4 + o] = fmaf(z.y, comp(g, o), a[dx * 8 + 4 + o]);
+                    }
                 }
-#pragma unroll
-                for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-                    for (int o = 0; o < 4; ++o) cta_acc(S.acc, NF_G_W1 + ((dy * 3 + dx) * 2 + ci) * 4 + o, a[ci][o], lane);
             }
+            cta_acc_vec<24>(S.acc + NF_G_W1 + dy * 24, a, lane);
+        }
         // g_x0 (transposed conv), complete g_z', grad A, G_in
         float gA[4][4];
 #pragma unroll
@@ -482,10 +516,12 @@ td_b3_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
             gin[p * NF_PIXELS + r * 32 + lane] = out;
         }
         if (S.P.has_mix) {
+            float v16[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int o = 0; o < 4; ++o) cta_acc(S.acc, NF_G_A + i * 4 + o, gA[i][o], lane);
+                for (int o = 0; o < 4; ++o) v16[i * 4 + o] = gA[i][o];
+            cta_acc_vec<16>(S.acc + NF_G_A, v16, lane);
         }
         __syncthreads();
     }
