@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tc", type=int, default=0, help="1: tensor-core (tcgen05) coupling convolutions")
+    ap.add_argument("--cta-warps", type=int, default=0, help="train mode: warps per patch-CTA (0 = automatic, 8, 16)")
+    ap.add_argument("--fused", type=int, default=1, help="train mode: 1 = one cooperative kernel per loss+gradient, 0 = one launch per pass")
     ap.add_argument("--trainer", default="device", choices=["device", "host"],
                     help="train mode: device-resident step (nf_trainer_*) or the host-synchronous path (train_step)")
     ap.add_argument("--width", type=int, default=4,
@@ -254,7 +256,7 @@ def main():
         from noise_flow_b200 import train as nf_train
         from noise_flow_b200.train import AdamOptimizer, DeviceTrainer, train_step
         if args.trainer == "device":
-            trainer = DeviceTrainer(nf, learning_rate=1e-4, max_batch=B)
+            trainer = DeviceTrainer(nf, learning_rate=1e-4, max_batch=B, cta_warps=args.cta_warps, fused=bool(args.fused))
         else:
             train_opt = AdamOptimizer(learning_rate=1e-4)
 
@@ -418,6 +420,8 @@ def main():
         out["roofline"] = None
         out["roofline_fp32"] = None
         out["config"]["trainer"] = args.trainer
+        out["config"]["cta_warps"] = args.cta_warps
+        out["config"]["fused"] = args.fused
         out["config"]["loss_per_dim_last_step"] = None if last_loss[0] is None else float(last_loss[0][0]) / 4096
         if trainer is not None:
             out["gpu_launches"] = world * args.steps * trainer.launches_per_step(True)

@@ -81,6 +81,8 @@ SIGNATURES = {
     "nf_trainer_set_vars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nf_trainer_launches_per_step": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "nf_trainer_set_graph": (C.c_int, [C.c_void_p, C.c_int]),
+    "nf_trainer_set_cta_warps": (C.c_int, [C.c_void_p, C.c_int]),
+    "nf_trainer_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "nf_reduce_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nf_baseline_nll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),

@@ -7,7 +7,8 @@
 // the chain rules back to the LU / scale variables, Adam, the BatchNorm moving averages -- are small kernels
 // between the heavy passes, so a step is one stream of ~60 launches with no cudaStreamSynchronize in it.
 //
-// Mapping: ONE CTA OWNS ONE PATCH (8 warps; warp w owns image rows w, w+8, ...; lane = column).  A train batch
+// Mapping: ONE CTA OWNS ONE PATCH (8 warps -- 16 when the batch has no more patches than the GPU has SMs, e.g. the
+// reference's 138 --; warp w owns image rows w, w+NW, ...; lane = column).  A train batch
 // is 138-207 patches per GPU (job_noise_flow.sh:37), far fewer than the 148 x 16 resident warps of the
 // inference kernel, so the patch is split over a whole CTA to cut the latency of every pass by ~8x; images live
 // in that CTA's shared memory; parameter-gradient partial sums go warp shuffle -> shared fp32 -> one fp64
@@ -20,6 +21,7 @@
 //     h3 = (conv3x3_VALID(pad(h2) (+) ring; W3) + b3) * exp(3 logs) ; shift = h3[:2], raw = h3[2:]
 //     ls = scale * tanh(raw) ; out = [x0, x1*exp(ls) + shift] ; ldj = sum ls
 //   forward passes F1 (sums of c1), F2 (sums of c2), F3 (apply) ; backward passes B1, B2, B3 as in nf_train.cu.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -99,29 +101,35 @@ __device__ __forceinline__ bool on_ring(int k) {
 
 // stats: double[16] of this coupling = sum c1[4], sum c1^2[4], sum c2[4], sum c2^2[4] over the batch.
 // need_bn: how many of the two BatchNorms must be valid (0, 1, 2).
-__device__ void td_load_params(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* __restrict__ A,
-                               const double* __restrict__ stats, double inv_cnt, int need_bn) {
+// reuse: the weights of this coupling are already in S.P (previous pass of the fused kernel): only the BatchNorm statistics in
+// force and the accumulators are refreshed.
+__device__ void td_load_params(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A,
+                               const double* stats, double inv_cnt, int need_bn, bool reuse = false) {
     const int t = threadIdx.x;
     float* w1 = &S.P.w1[0][0][0][0];
     float* w2 = &S.P.w2[0][0];
     float* w3 = &S.P.w3[0][0][0][0];
-    for (int k = t; k < 72; k += blockDim.x) w1[k] = vars[d.off_w1 + k];
-    for (int k = t; k < 16; k += blockDim.x) w2[k] = vars[d.off_w2 + k];
-    for (int k = t; k < 180; k += blockDim.x) w3[k] = vars[d.off_w3 + k];
+    if (!reuse) {
+        for (int k = t; k < 72; k += blockDim.x) w1[k] = vars[d.off_w1 + k];
+        for (int k = t; k < 16; k += blockDim.x) w2[k] = vars[d.off_w2 + k];
+        for (int k = t; k < 180; k += blockDim.x) w3[k] = vars[d.off_w3 + k];
+        if (t < 16) (&S.P.A[0][0])[t] = d.has_mix ? __ldcg(A + t) : ((t >> 2) == (t & 3) ? 1.f : 0.f);
+    }
     for (int k = t; k < NF_G_COUPLING_DOUBLES; k += blockDim.x) S.acc[k] = 0.f;
-    if (t < 16) (&S.P.A[0][0])[t] = d.has_mix ? A[t] : ((t >> 2) == (t & 3) ? 1.f : 0.f);
     if (t < 4) {
-        S.P.b1[t] = vars[d.off_b1 + t];
-        S.P.b2[t] = vars[d.off_b2 + t];
-        S.P.b3[t] = vars[d.off_b3 + t];
-        S.P.logs[t] = vars[d.off_logs + t];
+        if (!reuse) {
+            S.P.b1[t] = vars[d.off_b1 + t];
+            S.P.b2[t] = vars[d.off_b2 + t];
+            S.P.b3[t] = vars[d.off_b3 + t];
+            S.P.logs[t] = vars[d.off_logs + t];
+        }
         float m[2] = {0.f, 0.f}, is[2] = {1.f, 1.f};
         for (int j = 0; j < 2; ++j) {
             if (j >= need_bn) break;
             float mean, var;
             if (d.batch_stats) {
-                const double mu = stats[8 * j + t] * inv_cnt;
-                double v = stats[8 * j + 4 + t] * inv_cnt - mu * mu;      // population variance (tf.nn.moments)
+                const double mu = __ldcg(stats + 8 * j + t) * inv_cnt;       // written by other CTAs (atomics at L2)
+                double v = __ldcg(stats + 8 * j + 4 + t) * inv_cnt - mu * mu;      // population variance (tf.nn.moments)
                 if (v < 0.0) v = 0.0;
                 mean = (float)mu;
                 var = (float)v;
@@ -138,8 +146,9 @@ __device__ void td_load_params(TdSmem& S, const TdCoupling& d, const float* __re
     if (t == 0) { S.P.scale = vars[d.off_scale]; S.P.has_mix = d.has_mix; }
 }
 
-__device__ __forceinline__ void td_load_mixed(TdSmem& S, const float4* __restrict__ zin, int warp, int lane) {
-    for (int r = warp; r < 32; r += TD_WARPS) {
+template <int NW>
+__device__ __forceinline__ void td_load_mixed(TdSmem& S, const float4* zin, int warp, int lane) {
+    for (int r = warp; r < 32; r += NW) {
         float4 z = zin[r * 32 + lane];
         if (S.P.has_mix) z = mix_fwd(z, &S.P.A[0][0]);
         S.zp[r * 32 + lane] = z;
@@ -147,7 +156,7 @@ __device__ __forceinline__ void td_load_mixed(TdSmem& S, const float4* __restric
 }
 
 // flush the CTA partial sums [lo, hi) with one fp64 atomic each
-__device__ __forceinline__ void td_flush(TdSmem& S, double* __restrict__ dst, int lo, int hi) {
+__device__ __forceinline__ void td_flush(TdSmem& S, double* dst, int lo, int hi) {
     __syncthreads();
     for (int k = lo + (int)threadIdx.x; k < hi; k += blockDim.x) {
         const float v = S.acc[k];
@@ -157,27 +166,28 @@ __device__ __forceinline__ void td_flush(TdSmem& S, double* __restrict__ dst, in
 
 // ---------------------------------------------------------------------------------------------- forward
 // STAGE 1: batch sums of c1 ; STAGE 2: batch sums of c2 ; STAGE 3: apply the coupling, accumulate the log-det.
-template <int STAGE>
-__global__ void __launch_bounds__(TD_THREADS, 2)
-td_fwd_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __restrict__ A, double* __restrict__ stats,
-              const float4* __restrict__ zin, float4* __restrict__ zout, float* __restrict__ ld, long long n, double inv_cnt) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TdSmem& S = *reinterpret_cast<TdSmem*>(smem_raw);
+// (The bodies are device functions shared by the per-pass kernels and the fused cooperative kernel td_step_kernel; buffers
+// that the fused kernel rewrites while it runs are therefore NOT declared __restrict__ / read-only.)
+template <int STAGE, int NW>
+__device__ __forceinline__ void
+td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, double* stats,
+            const float4* zin, float4* zout, float* ld, long long n, double inv_cnt, bool reuse = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    td_load_params(S, d, vars, A, stats, inv_cnt, STAGE - 1);
+    // reuse (fused kernel, one patch per CTA): weights and the mixed patch z' are still in shared memory from the previous stage
+    td_load_params(S, d, vars, A, stats, inv_cnt, STAGE - 1, reuse);
     __syncthreads();
     float e3[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) e3[o] = expf(3.f * S.P.logs[o]);
     for (long long p = blockIdx.x; p < n; p += gridDim.x) {
-        td_load_mixed(S, zin + p * NF_PIXELS, warp, lane);
+        if (!reuse) td_load_mixed<NW>(S, zin + p * NF_PIXELS, warp, lane);
         if (STAGE == 3)
             for (int k = threadIdx.x; k < 34 * 34; k += blockDim.x)
                 if (on_ring(k)) S.h2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
         if (STAGE == 1) {
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int r = warp; r < 32; r += TD_WARPS) {
+            for (int r = warp; r < 32; r += NW) {
                 float c1[4];
                 conv1_at(S.P, S, r, lane, c1);
 #pragma unroll
@@ -186,7 +196,7 @@ td_fwd_kernel(const TdCoupling d, const float* __restrict__ vars, const float* _
             { const float v8[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]}; cta_acc_vec<8>(S.acc, v8, lane); }
         } else if (STAGE == 2) {
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int r = warp; r < 32; r += TD_WARPS) {
+            for (int r = warp; r < 32; r += NW) {
                 float c1[4], h1[4];
                 conv1_at(S.P, S, r, lane, c1);
 #pragma unroll
@@ -202,14 +212,14 @@ td_fwd_kernel(const TdCoupling d, const float* __restrict__ vars, const float* _
             }
             { const float v8[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]}; cta_acc_vec<8>(S.acc + 8, v8, lane); }
         } else {
-            for (int r = warp; r < 32; r += TD_WARPS) {
+            for (int r = warp; r < 32; r += NW) {
                 float c1hat[4], h1[4], c2hat[4];
                 net_to_c2hat(S.P, S, r, lane, c1hat, h1, c2hat);
                 S.h2[(r + 1) * 34 + lane + 1] = make_float4(fmaxf(c2hat[0], 0.f), fmaxf(c2hat[1], 0.f), fmaxf(c2hat[2], 0.f), fmaxf(c2hat[3], 0.f));
             }
             __syncthreads();
             float lsum = 0.f;
-            for (int r = warp; r < 32; r += TD_WARPS) {
+            for (int r = warp; r < 32; r += NW) {
                 float pre[4];
 #pragma unroll
                 for (int o = 0; o < 4; ++o) pre[o] = S.P.b3[o];
@@ -236,7 +246,7 @@ td_fwd_kernel(const TdCoupling d, const float* __restrict__ vars, const float* _
             __syncthreads();
             if (threadIdx.x == 0) {
                 float tot = 0.f;
-                for (int w = 0; w < TD_WARPS; ++w) tot += S.acc[16 + w];
+                for (int w = 0; w < NW; ++w) tot += S.acc[16 + w];
                 ld[p] += tot;
             }
         }
@@ -245,15 +255,21 @@ td_fwd_kernel(const TdCoupling d, const float* __restrict__ vars, const float* _
     if (STAGE == 1) td_flush(S, stats, 0, 8);
     if (STAGE == 2) td_flush(S, stats, 8, 16);
 }
+template <int STAGE, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
+td_fwd_kernel(const TdCoupling d, const float* __restrict__ vars, const float* A, double* stats,
+              const float4* zin, float4* zout, float* ld, long long n, double inv_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    td_fwd_body<STAGE, NW>(*reinterpret_cast<TdSmem*>(smem_raw), d, vars, A, stats, zin, zout, ld, n, inv_cnt);
+}
 
 // ---------------------------------------------------------------------------------------------- pass B1
 // G_out -> g_shift, g_ls, g_x1 ; grads of scale, logs, b3, W3 ; g_h2 (transposed conv) ; BatchNorm-2 sums
-__global__ void __launch_bounds__(TD_THREADS, 2)
-td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __restrict__ A, const double* __restrict__ stats,
-             const float4* __restrict__ zin, const float4* __restrict__ gout, float4* __restrict__ gzp,
-             float4* __restrict__ scratch, long long n, float inv_n, double inv_cnt, double* __restrict__ grads) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TdSmem& S = *reinterpret_cast<TdSmem*>(smem_raw);
+template <int NW>
+__device__ __forceinline__ void
+td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, const double* stats,
+           const float4* zin, const float4* gout, float4* gzp, float4* scratch, long long n, float inv_n, double inv_cnt,
+           double* grads) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     td_load_params(S, d, vars, A, stats, inv_cnt, 2);
     __syncthreads();
@@ -261,11 +277,11 @@ td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
 #pragma unroll
     for (int o = 0; o < 4; ++o) e3[o] = expf(3.f * S.P.logs[o]);
     for (long long p = blockIdx.x; p < n; p += gridDim.x) {
-        td_load_mixed(S, zin + p * NF_PIXELS, warp, lane);
+        td_load_mixed<NW>(S, zin + p * NF_PIXELS, warp, lane);
         for (int k = threadIdx.x; k < 34 * 34; k += blockDim.x)
             if (on_ring(k)) { S.h2[k] = make_float4(0.f, 0.f, 0.f, 0.f); S.g[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
         __syncthreads();
-        for (int r = warp; r < 32; r += TD_WARPS) {
+        for (int r = warp; r < 32; r += NW) {
             float c1hat[4], h1[4], c2hat[4];
             net_to_c2hat(S.P, S, r, lane, c1hat, h1, c2hat);
             S.h2[(r + 1) * 34 + lane + 1] = make_float4(fmaxf(c2hat[0], 0.f), fmaxf(c2hat[1], 0.f), fmaxf(c2hat[2], 0.f), fmaxf(c2hat[3], 0.f));
@@ -273,7 +289,7 @@ td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
         __syncthreads();
         // conv-3 forward + coupling backward -> g_pre3 image, partial G_z'
         float g_scale = 0.f, g_logs[4] = {0.f, 0.f, 0.f, 0.f}, g_b3[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = warp; r < 32; r += TD_WARPS) {
+        for (int r = warp; r < 32; r += NW) {
             float pre[4];
 #pragma unroll
             for (int o = 0; o < 4; ++o) pre[o] = S.P.b3[o];
@@ -317,7 +333,7 @@ td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
                 float a[20];            // [ci][o], the 20 consecutive slots of this tap
 #pragma unroll
                 for (int k = 0; k < 20; ++k) a[k] = 0.f;
-                for (int r = warp; r < 32; r += TD_WARPS) {
+                for (int r = warp; r < 32; r += NW) {
                     const int R = r + dy, C = lane + dx;
                     const float4 h = S.h2[R * 34 + C];
                     const float ring = (R == 0 || R == 33 || C == 0 || C == 33) ? 1.f : 0.f;
@@ -332,7 +348,7 @@ td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
             }
         // g_h2(r, c)[ci] = sum_{dy,dx,o} W3[dy][dx][ci][o] * g_pre3(r-dy+1, c-dx+1)[o] ; ReLU mask ; BatchNorm-2 sums
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = warp; r < 32; r += TD_WARPS) {
+        for (int r = warp; r < 32; r += NW) {
             float gh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
@@ -361,28 +377,35 @@ td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
     td_flush(S, grads, 0, NF_G_COUPLING_DOUBLES);
 }
 
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
+td_b1_kernel(const TdCoupling d, const float* __restrict__ vars, const float* A, const double* stats, const float4* zin,
+             const float4* gout, float4* gzp, float4* scratch, long long n, float inv_n, double inv_cnt, double* grads) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    td_b1_body<NW>(*reinterpret_cast<TdSmem*>(smem_raw), d, vars, A, stats, zin, gout, gzp, scratch, n, inv_n, inv_cnt, grads);
+}
+
 // ---------------------------------------------------------------------------------------------- pass B2
 // BatchNorm-2 backward ; grads of W2, b2 ; g_h1 ; BatchNorm-1 sums
-__global__ void __launch_bounds__(TD_THREADS, 2)
-td_b2_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __restrict__ A, const double* __restrict__ stats,
-             const float4* __restrict__ zin, float4* __restrict__ scratch, long long n, double inv_cnt, double* __restrict__ grads) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TdSmem& S = *reinterpret_cast<TdSmem*>(smem_raw);
+template <int NW>
+__device__ __forceinline__ void
+td_b2_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, const double* stats,
+           const float4* zin, float4* scratch, long long n, double inv_cnt, double* grads, bool reuse = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float bn2[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) bn2[k] = d.batch_stats ? (float)(grads[NF_G_BN2 + k] * inv_cnt) : 0.f;
-    td_load_params(S, d, vars, A, stats, inv_cnt, 2);
+    for (int k = 0; k < 8; ++k) bn2[k] = d.batch_stats ? (float)(__ldcg(grads + NF_G_BN2 + k) * inv_cnt) : 0.f;   // other CTAs' atomics
+    td_load_params(S, d, vars, A, stats, inv_cnt, 2, reuse);
     __syncthreads();
     for (long long p = blockIdx.x; p < n; p += gridDim.x) {
-        td_load_mixed(S, zin + p * NF_PIXELS, warp, lane);
+        if (!reuse) td_load_mixed<NW>(S, zin + p * NF_PIXELS, warp, lane);
         __syncthreads();
         float gw2[4][4], gb2[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int o = 0; o < 4; ++o) gw2[i][o] = 0.f;
-        for (int r = warp; r < 32; r += TD_WARPS) {
+        for (int r = warp; r < 32; r += NW) {
             float c1hat[4], h1[4], c2hat[4];
             net_to_c2hat(S.P, S, r, lane, c1hat, h1, c2hat);
             const float4 gc4 = scratch[p * NF_PIXELS + r * 32 + lane];
@@ -423,27 +446,34 @@ td_b2_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
     td_flush(S, grads, 0, NF_G_COUPLING_DOUBLES);
 }
 
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
+td_b2_kernel(const TdCoupling d, const float* __restrict__ vars, const float* A, const double* stats, const float4* zin,
+             float4* scratch, long long n, double inv_cnt, double* grads) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    td_b2_body<NW>(*reinterpret_cast<TdSmem*>(smem_raw), d, vars, A, stats, zin, scratch, n, inv_cnt, grads);
+}
+
 // ---------------------------------------------------------------------------------------------- pass B3
 // BatchNorm-1 backward ; grads of W1, b1 ; g_x0 (transposed conv) ; grad of A ; G_in = g_z' . A^T
-__global__ void __launch_bounds__(TD_THREADS, 2)
-td_b3_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __restrict__ A, const double* __restrict__ stats,
-             const float4* __restrict__ zin, const float4* __restrict__ scratch, const float4* __restrict__ gzp,
-             float4* __restrict__ gin, long long n, double inv_cnt, double* __restrict__ grads) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TdSmem& S = *reinterpret_cast<TdSmem*>(smem_raw);
+template <int NW>
+__device__ __forceinline__ void
+td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, const double* stats,
+           const float4* zin, const float4* scratch, const float4* gzp, float4* gin, long long n, double inv_cnt, double* grads,
+           bool reuse = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float bn1[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) bn1[k] = d.batch_stats ? (float)(grads[NF_G_BN1 + k] * inv_cnt) : 0.f;
-    td_load_params(S, d, vars, A, stats, inv_cnt, 2);
+    for (int k = 0; k < 8; ++k) bn1[k] = d.batch_stats ? (float)(__ldcg(grads + NF_G_BN1 + k) * inv_cnt) : 0.f;
+    td_load_params(S, d, vars, A, stats, inv_cnt, 2, reuse);
     __syncthreads();
     for (long long p = blockIdx.x; p < n; p += gridDim.x) {
-        td_load_mixed(S, zin + p * NF_PIXELS, warp, lane);
+        if (!reuse) td_load_mixed<NW>(S, zin + p * NF_PIXELS, warp, lane);
         for (int k = threadIdx.x; k < 34 * 34; k += blockDim.x)
             if (on_ring(k)) S.g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
         float gb1[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = warp; r < 32; r += TD_WARPS) {
+        for (int r = warp; r < 32; r += NW) {
             float c1[4];
             conv1_at(S.P, S, r, lane, c1);
             const float4 g4 = scratch[p * NF_PIXELS + r * 32 + lane];
@@ -463,7 +493,7 @@ td_b3_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
             float a[24];                // [dx][ci][o]: the 24 consecutive slots of filter row dy
 #pragma unroll
             for (int k = 0; k < 24; ++k) a[k] = 0.f;
-            for (int r = warp; r < 32; r += TD_WARPS) {
+            for (int r = warp; r < 32; r += NW) {
                 const int rr = r + dy - 1;
                 if (rr < 0 || rr > 31) continue;
                 const float4 g = S.g[(r + 1) * 34 + lane + 1];
@@ -487,7 +517,7 @@ td_b3_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int o = 0; o < 4; ++o) gA[i][o] = 0.f;
-        for (int r = warp; r < 32; r += TD_WARPS) {
+        for (int r = warp; r < 32; r += NW) {
             float gx0[2] = {0.f, 0.f};
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
@@ -528,6 +558,14 @@ td_b3_kernel(const TdCoupling d, const float* __restrict__ vars, const float* __
     td_flush(S, grads, 0, NF_G_COUPLING_DOUBLES);
 }
 
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
+td_b3_kernel(const TdCoupling d, const float* __restrict__ vars, const float* A, const double* stats, const float4* zin,
+             const float4* scratch, const float4* gzp, float4* gin, long long n, double inv_cnt, double* grads) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    td_b3_body<NW>(*reinterpret_cast<TdSmem*>(smem_raw), d, vars, A, stats, zin, scratch, gzp, gin, n, inv_cnt, grads);
+}
+
 // ---------------------------------------------------------------------------------------------- scale layers
 // deterministic CTA sum (fixed shuffle tree per warp, warps added in order by thread 0); result valid in thread 0
 __device__ __forceinline__ float cta_sum_det(float v, float* sh, int warp, int lane) {
@@ -537,21 +575,19 @@ __device__ __forceinline__ float cta_sum_det(float v, float* sh, int warp, int l
     __syncthreads();
     float tot = 0.f;
     if (threadIdx.x == 0)
-        for (int w = 0; w < TD_WARPS; ++w) tot += sh[w];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
     return tot;
 }
 
 // table: [NF_MAX_ROWS][2] = (a, b) for sdn (scale^2 = a*y + b), (g, -) for gain.  z_out = z_in / scale.
-__global__ void __launch_bounds__(TD_THREADS)
-td_scale_fwd_kernel(const float* __restrict__ table, int is_sdn, int full_sum, const float4* __restrict__ zin,
-                    const float4* __restrict__ y, float4* __restrict__ zout, float* __restrict__ ld,
-                    const int* __restrict__ rows, int default_row, long long n) {
-    __shared__ float sh[TD_WARPS];
+__device__ __forceinline__ void
+td_scale_fwd_body(float* sh, const float* table, int is_sdn, int full_sum, const float4* zin, const float4* __restrict__ y,
+                  float4* zout, float* ld, const int* __restrict__ rows, int default_row, long long n) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (long long p = blockIdx.x; p < n; p += gridDim.x) {
         int row = rows ? rows[p] : default_row;
         row = min(max(row, 0), NF_MAX_ROWS - 1);
-        const float a = table[row * 2], b = table[row * 2 + 1];
+        const float a = __ldcg(table + row * 2), b = __ldcg(table + row * 2 + 1);
         float lsum = 0.f;
         for (int k = threadIdx.x; k < NF_PIXELS; k += blockDim.x) {
             const long long idx = p * NF_PIXELS + k;
@@ -570,18 +606,23 @@ td_scale_fwd_kernel(const float* __restrict__ table, int is_sdn, int full_sum, c
         if (threadIdx.x == 0) ld[p] += is_sdn ? tot : -(full_sum ? (float)NF_DIMS : 1.f) * logf(a);
     }
 }
+__global__ void __launch_bounds__(TD_THREADS)
+td_scale_fwd_kernel(const float* table, int is_sdn, int full_sum, const float4* zin, const float4* __restrict__ y, float4* zout,
+                    float* ld, const int* __restrict__ rows, int default_row, long long n) {
+    __shared__ float sh[16];
+    td_scale_fwd_body(sh, table, is_sdn, full_sum, zin, y, zout, ld, rows, default_row, n);
+}
 
 // G_in = G_out / scale ; table-row gradients (see nf_train_scale_kernel in nf_train.cu)
-__global__ void __launch_bounds__(TD_THREADS)
-td_scale_bwd_kernel(const float* __restrict__ table, int is_sdn, int full_sum, const float4* __restrict__ zout,
-                    const float4* __restrict__ y, const float4* __restrict__ gout, float4* __restrict__ gin,
-                    const int* __restrict__ rows, int default_row, long long n, float inv_n, double* __restrict__ grads) {
-    __shared__ float sh[TD_WARPS];
+__device__ __forceinline__ void
+td_scale_bwd_body(float* sh, const float* table, int is_sdn, int full_sum, const float4* zout, const float4* __restrict__ y,
+                  const float4* gout, float4* gin, const int* __restrict__ rows, int default_row, long long n, float inv_n,
+                  double* grads) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (long long p = blockIdx.x; p < n; p += gridDim.x) {
         int row = rows ? rows[p] : default_row;
         row = min(max(row, 0), NF_MAX_ROWS - 1);
-        const float a = table[row * 2], b = table[row * 2 + 1];
+        const float a = __ldcg(table + row * 2), b = __ldcg(table + row * 2 + 1);
         float ga = 0.f, gb = 0.f;
         for (int k = threadIdx.x; k < NF_PIXELS; k += blockDim.x) {
             const long long idx = p * NF_PIXELS + k;
@@ -615,13 +656,19 @@ td_scale_bwd_kernel(const float* __restrict__ table, int is_sdn, int full_sum, c
         }
     }
 }
+__global__ void __launch_bounds__(TD_THREADS)
+td_scale_bwd_kernel(const float* table, int is_sdn, int full_sum, const float4* zout, const float4* __restrict__ y,
+                    const float4* gout, float4* gin, const int* __restrict__ rows, int default_row, long long n, float inv_n,
+                    double* grads) {
+    __shared__ float sh[16];
+    td_scale_bwd_body(sh, table, is_sdn, full_sum, zout, y, gout, gin, rows, default_row, n, inv_n, grads);
+}
 
 // prior + loss terms of one patch, and the seed of the backward sweep G = z / N:
 //   nll = -(ldj + ldj_const + sum -0.5 (log 2pi + z^2)) ; sd_z = sqrt(var_hwc(z))   (noise_flow_model.py:458-480)
-__global__ void __launch_bounds__(TD_THREADS)
-td_nll_kernel(const float4* __restrict__ z, const float* __restrict__ ld, const double* __restrict__ consts, float4* __restrict__ g,
-              float* __restrict__ nll, float* __restrict__ sdz, long long n, float inv_n) {
-    __shared__ float sh[TD_WARPS];
+__device__ __forceinline__ void
+td_nll_body(float* sh, const float4* z, const float* ld, const double* consts, float4* g, float* nll, float* sdz, long long n,
+            float inv_n) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (long long p = blockIdx.x; p < n; p += gridDim.x) {
         float s1 = 0.f, s2 = 0.f;
@@ -636,13 +683,18 @@ td_nll_kernel(const float4* __restrict__ z, const float* __restrict__ ld, const 
         if (threadIdx.x == 0) {
             const double S1 = t1, S2 = t2;
             const double logp = -0.5 * ((double)NF_DIMS * 1.8378770664093453 + S2);
-            nll[p] = (float)(-((double)ld[p] + consts[0] + logp));
+            nll[p] = (float)(-((double)ld[p] + __ldcg(consts) + logp));
             const double mean = S1 / NF_DIMS;
             double var = S2 / NF_DIMS - mean * mean;
             if (var < 0.0) var = 0.0;
             sdz[p] = (float)sqrt(var);
         }
     }
+}
+__global__ void __launch_bounds__(TD_THREADS)
+td_nll_kernel(const float4* z, const float* ld, const double* consts, float4* g, float* nll, float* sdz, long long n, float inv_n) {
+    __shared__ float sh[16];
+    td_nll_body(sh, z, ld, consts, g, nll, sdz, n, inv_n);
 }
 
 // ---------------------------------------------------------------------------------------------- small device-side host work
@@ -692,14 +744,16 @@ __device__ void td_scale_row(const nf_train_op& o, const float* vars, int cam, i
     }
 }
 
-// one thread per op: derived 1x1 matrices, scale tables, constant log-det of the chain
-__global__ void td_prep_kernel(const TdProgram* __restrict__ prog, const float* __restrict__ vars, float* __restrict__ Amat,
-                               float* __restrict__ tables, double* __restrict__ consts) {
-    const int i = threadIdx.x;
-    if (i >= prog->n_ops) return;
+// derived 1x1 matrices, scale tables, constant log-det of the chain.  Work items = (op, table row): a coupling's matrix is
+// item (op, 0); the 32 rows of a scale table (six fp64 exp each for sdn5) go to 32 threads instead of one.
+__device__ __forceinline__ void td_prep_body(const TdProgram* __restrict__ prog, const float* __restrict__ vars, float* Amat,
+                                             float* tables, double* consts) {
+  for (int item = threadIdx.x; item < prog->n_ops * NF_MAX_ROWS; item += blockDim.x) {
+    const int i = item / NF_MAX_ROWS, row = item % NF_MAX_ROWS;
     const TdOp& op = prog->ops[i];
     const nf_train_op& o = op.o;
     if (o.kind == NF_TOP_COUPLING) {
+        if (row != 0) continue;
         float* A = Amat + op.cidx * 16;
         if (o.mix_kind == 1) {
             double P[4][4], L[4][4], U[4][4], sd[4], LU[4][4];
@@ -718,13 +772,16 @@ __global__ void td_prep_kernel(const TdProgram* __restrict__ prog, const float* 
         }
     } else if (o.kind == NF_TOP_SCALE) {
         float* T = tables + op.sidx * NF_MAX_ROWS * 2;
-        for (int row = 0; row < NF_MAX_ROWS; ++row) {
-            double a = 1.0, b = 1.0;
-            if (row < 25) td_scale_row(o, vars, row / 5, row % 5, a, b);
-            T[row * 2] = (float)a;
-            T[row * 2 + 1] = (float)b;
-        }
+        double a = 1.0, b = 1.0;
+        if (row < 25) td_scale_row(o, vars, row / 5, row % 5, a, b);
+        T[row * 2] = (float)a;
+        T[row * 2 + 1] = (float)b;
     }
+  }
+}
+__global__ void td_prep_kernel(const TdProgram* __restrict__ prog, const float* __restrict__ vars, float* Amat, float* tables,
+                               double* consts) {
+    td_prep_body(prog, vars, Amat, tables, consts);
 }
 
 // Chain rules from the kernel-level gradients to the TF variables, all into the flat reduce buffer:
@@ -860,6 +917,110 @@ td_apply_kernel(const TdProgram* __restrict__ prog, float* __restrict__ vars, co
     if (threadIdx.x == 0) step[0] = t;
 }
 
+// ---------------------------------------------------------------------------------------------- the fused step
+// Loss + gradient of one batch as ONE cooperative kernel.  At the reference's batch sizes (138-207 patches per GPU) the
+// per-pass kernels above each run a single wave of one-patch CTAs for 9-27 us, and the 57 dependent launches of a step cost
+// ~0.6 ms whatever the batch (0.63 ms at 64 patches, 0.64 ms at 138): the step is bound by launch + prologue latency, not
+// by work.  Here every CTA keeps ITS patch for the whole step and walks the op list itself -- prep, forward (three stages
+// per coupling), prior / NLL, backward (three passes per coupling) -- with a grid-wide barrier only where the math needs
+// the whole batch: after prep (matrices / tables are built by CTA 0) and around the BatchNorm batch sums (2 per coupling and
+// direction).  Activations and gradients still go through the global work space (a CTA re-reads only what it wrote
+// itself: L1/L2 hits), so the pass bodies are shared with the per-pass kernels, which remain the path for batches larger
+// than the number of co-resident CTAs and the cross-check of this kernel (tests/test_gpu_trainer.py).
+struct TdStepArgs {
+    const TdProgram* prog;
+    const float* vars;
+    float *Amat, *tables;
+    double *stats, *cgrads, *sgrads, *consts;
+    float* ws;                  // activation / gradient slots, `stride` floats each: [0, n_ops) op outputs, then gA gB scratch gzp, ld nll sdz
+    long long stride;
+    const float *x, *y;
+    const int* rows;
+    int default_row;
+    long long n;
+    int batch_stats;
+    float bn_eps;
+};
+
+__device__ __forceinline__ TdCoupling td_desc(const nf_train_op& o, int batch_stats, float bn_eps) {
+    TdCoupling d;
+    d.off_w1 = o.off_w1; d.off_b1 = o.off_b1; d.off_w2 = o.off_w2; d.off_b2 = o.off_b2;
+    d.off_w3 = o.off_w3; d.off_b3 = o.off_b3; d.off_logs = o.off_logs; d.off_scale = o.off_scale;
+    d.off_bn[0] = o.off_bn1_mean; d.off_bn[1] = o.off_bn1_var; d.off_bn[2] = o.off_bn2_mean; d.off_bn[3] = o.off_bn2_var;
+    d.has_mix = o.mix_kind != 0;
+    d.batch_stats = batch_stats;
+    d.bn_eps = bn_eps;
+    d.pad_ = 0;
+    return d;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
+td_step_kernel(const TdStepArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TdSmem& S = *reinterpret_cast<TdSmem*>(smem_raw);
+    __shared__ float sh[16];
+    const TdProgram* prog = a.prog;
+    const int G = prog->n_ops;
+    const long long n = a.n;
+    const double inv_cnt = 1.0 / ((double)n * NF_PIXELS);
+    const float inv_n = 1.f / (float)n;
+    auto slot = [&](int k) { return a.ws + (long long)k * a.stride; };
+    float *gA = slot(G), *gB = slot(G + 1), *scratch = slot(G + 2), *gzp = slot(G + 3);
+    float *ld = slot(G + 4), *nll = ld + n, *sdz = nll + n;
+
+    if (blockIdx.x == 0) td_prep_body(prog, a.vars, a.Amat, a.tables, a.consts);
+    grid.sync();
+    // ---- forward, keeping every op's input
+    for (int i = 0; i < G; ++i) {
+        const TdOp& op = prog->ops[i];
+        const float4* in = (const float4*)(i == 0 ? a.x : slot(i - 1));
+        float4* out = (float4*)slot(i);
+        if (op.o.kind == NF_TOP_COUPLING) {
+            const TdCoupling d = td_desc(op.o, a.batch_stats, a.bn_eps);
+            const float* A = a.Amat + op.cidx * 16;
+            double* st = a.stats + op.cidx * 16;
+            if (a.batch_stats) {
+                td_fwd_body<1, NW>(S, d, a.vars, A, st, in, out, ld, n, inv_cnt);
+                grid.sync();
+                td_fwd_body<2, NW>(S, d, a.vars, A, st, in, out, ld, n, inv_cnt, true);
+                grid.sync();
+            }
+            td_fwd_body<3, NW>(S, d, a.vars, A, st, in, out, ld, n, inv_cnt, a.batch_stats != 0);
+        } else {
+            td_scale_fwd_body(sh, a.tables + op.sidx * NF_MAX_ROWS * 2, op.o.token != NF_TOKEN_GAIN4, 1, in, (const float4*)a.y, out, ld,
+                              a.rows, a.default_row, n);
+        }
+        __syncthreads();        // the next op reads what this CTA just wrote
+    }
+    td_nll_body(sh, (const float4*)slot(G - 1), ld, a.consts, (float4*)gA, nll, sdz, n, inv_n);
+    __syncthreads();
+    // ---- backward
+    for (int i = G - 1; i >= 0; --i) {
+        const TdOp& op = prog->ops[i];
+        const float4* zin = (const float4*)(i == 0 ? a.x : slot(i - 1));
+        const float4* zout = (const float4*)slot(i);
+        if (op.o.kind == NF_TOP_COUPLING) {
+            const TdCoupling d = td_desc(op.o, a.batch_stats, a.bn_eps);
+            const float* A = a.Amat + op.cidx * 16;
+            const double* st = a.stats + op.cidx * 16;
+            double* cgr = a.cgrads + (long long)op.cidx * NF_G_COUPLING_DOUBLES;
+            td_b1_body<NW>(S, d, a.vars, A, st, zin, (const float4*)gA, (float4*)gzp, (float4*)scratch, n, inv_n, inv_cnt, cgr);
+            if (a.batch_stats) grid.sync(); else __syncthreads();      // BatchNorm-2 backward sums over the whole batch
+            td_b2_body<NW>(S, d, a.vars, A, st, zin, (float4*)scratch, n, inv_cnt, cgr, true);
+            if (a.batch_stats) grid.sync(); else __syncthreads();      // BatchNorm-1 backward sums
+            td_b3_body<NW>(S, d, a.vars, A, st, zin, (const float4*)scratch, (const float4*)gzp, (float4*)gB, n, inv_cnt, cgr, true);
+        } else {
+            td_scale_bwd_body(sh, a.tables + op.sidx * NF_MAX_ROWS * 2, op.o.token != NF_TOKEN_GAIN4, 1, zout, (const float4*)a.y,
+                              (const float4*)gA, (float4*)gB, a.rows, a.default_row, n, inv_n, a.sgrads + (long long)op.sidx * NF_MAX_ROWS * 2);
+        }
+        __syncthreads();
+        float* tmp = gA; gA = gB; gB = tmp;
+    }
+}
+
 }  // namespace nf
 
 // =====================================================================================================
@@ -884,6 +1045,10 @@ struct nf_trainer {
     int64_t dbl_len = 0;
     // CUDA-graph replay of the loss+gradient launch sequence: inputs are staged into trainer-owned buffers so the
     // captured pointers never change; the graph is re-captured only when (n, row, mode, reduce buffer) change
+    int cta_warps = 0;            // 0 = automatic (16 when n <= #SMs, else 8); 8 / 16 = forced (nf_trainer_set_cta_warps)
+    int fused = 1;                // 1 = one cooperative kernel per loss+gradient when the batch is co-resident (nf_trainer_set_fused)
+    int coop_cap[2] = {-1, -1};   // co-resident CTAs of td_step_kernel<8>, <16> (-1 = not queried yet)
+    int last_launches = 0, last_mode = -1;   // kernels enqueued by the last loss+gradient, and its batch_stats flag
     int use_graph = 1;
     float *d_xs = nullptr, *d_ys = nullptr;
     int32_t* d_rows = nullptr;
@@ -904,12 +1069,13 @@ int td_smem_attr() {
     static bool done = false;
     if (done) return NF_OK;
     const int bytes = (int)sizeof(nf::TdSmem);
-    TD_CUDA(cudaFuncSetAttribute(nf::td_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    TD_CUDA(cudaFuncSetAttribute(nf::td_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    TD_CUDA(cudaFuncSetAttribute(nf::td_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    TD_CUDA(cudaFuncSetAttribute(nf::td_b1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    TD_CUDA(cudaFuncSetAttribute(nf::td_b2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    TD_CUDA(cudaFuncSetAttribute(nf::td_b3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+#define TD_ATTR(K) TD_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+    TD_ATTR((nf::td_fwd_kernel<1, 8>)); TD_ATTR((nf::td_fwd_kernel<2, 8>)); TD_ATTR((nf::td_fwd_kernel<3, 8>));
+    TD_ATTR((nf::td_fwd_kernel<1, 16>)); TD_ATTR((nf::td_fwd_kernel<2, 16>)); TD_ATTR((nf::td_fwd_kernel<3, 16>));
+    TD_ATTR(nf::td_b1_kernel<8>); TD_ATTR(nf::td_b2_kernel<8>); TD_ATTR(nf::td_b3_kernel<8>);
+    TD_ATTR(nf::td_b1_kernel<16>); TD_ATTR(nf::td_b2_kernel<16>); TD_ATTR(nf::td_b3_kernel<16>);
+    TD_ATTR(nf::td_step_kernel<8>); TD_ATTR(nf::td_step_kernel<16>);
+#undef TD_ATTR
     done = true;
     return NF_OK;
 }
@@ -1029,6 +1195,8 @@ int nf_trainer_launches_per_step(const nf_trainer* t, int batch_stats, int* n_la
     if (!t || !n_launches) return nf::set_error(NF_ERR_INVALID, "nf_trainer_launches_per_step", "null argument");
     // prep + per coupling (F1, F2 with batch statistics) F3, B1, B2, B3 + per scale layer fwd, bwd + nll + reduce + chain + apply
     *n_launches = 1 + t->n_cp * ((batch_stats ? 2 : 0) + 4) + t->n_sc * 2 + 4;
+    // what the last evaluation in this mode really enqueued (the fused path: step + reduce + chain), + apply
+    if (t->last_launches > 0 && t->last_mode == (batch_stats ? 1 : 0)) *n_launches = t->last_launches + 1;
     return NF_OK;
 }
 
@@ -1048,6 +1216,8 @@ static int td_enqueue(nf_trainer* t, const float* x, const float* y, const int32
     const float inv_n = 1.f / (float)n;
     const unsigned grid = (unsigned)n;
     const size_t smem = sizeof(nf::TdSmem);
+    // no more patches than SMs (the reference trains on 138 per step): give every patch 16 warps, one CTA per SM
+    const bool wide_cta = t->cta_warps == 16 || (t->cta_warps == 0 && n <= (int64_t)t->sm_count);
     for (int i = 0; i < G; ++i)
         if (t->prog.ops[i].o.kind == NF_TOP_SCALE && t->prog.ops[i].o.token != NF_TOKEN_GAIN4 && !y)
             return nf::set_error(NF_ERR_INVALID, "nf_trainer_loss_and_grad", "clean patch y is required by an sdn layer");
@@ -1055,7 +1225,36 @@ static int td_enqueue(nf_trainer* t, const float* x, const float* y, const int32
     TD_CUDA(cudaMemsetAsync(t->d_dbl, 0, (size_t)t->dbl_len * sizeof(double), s));
     TD_CUDA(cudaMemsetAsync(red, 0, (size_t)(t->n_vars + 3 + 16 * t->n_cp) * sizeof(double), s));
     TD_CUDA(cudaMemsetAsync(d_ld, 0, (size_t)n * sizeof(float), s));
-    nf::td_prep_kernel<<<1, 64, 0, s>>>(t->d_prog, t->d_vars, t->d_A, t->d_tables, d_consts);
+    t->last_mode = batch_stats ? 1 : 0;
+    if (t->fused) {
+        // one cooperative kernel when every patch-CTA can be resident at once (296 at 8 warps, 148 at 16 on a B200)
+        int& cap = t->coop_cap[wide_cta ? 1 : 0];
+        if (cap < 0) {
+            int per_sm = 0;
+            cudaError_t e = wide_cta ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nf::td_step_kernel<16>, 512, smem)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nf::td_step_kernel<8>, 256, smem);
+            if (e != cudaSuccess) return nf::set_error(NF_ERR_CUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", cudaGetErrorString(e));
+            cap = per_sm * t->sm_count;
+        }
+        if (n <= (int64_t)cap) {
+            nf::TdStepArgs a = {};
+            a.prog = t->d_prog; a.vars = t->d_vars; a.Amat = t->d_A; a.tables = t->d_tables;
+            a.stats = d_stats; a.cgrads = d_cg; a.sgrads = d_sg; a.consts = d_consts;
+            a.ws = t->d_ws; a.stride = S; a.x = x; a.y = y; a.rows = rows; a.default_row = default_row;
+            a.n = n; a.batch_stats = batch_stats ? 1 : 0; a.bn_eps = t->bn_eps;
+            void* kargs[] = {&a};
+            TD_CUDA(cudaLaunchCooperativeKernel(wide_cta ? (const void*)nf::td_step_kernel<16> : (const void*)nf::td_step_kernel<8>,
+                                                dim3(grid), dim3(wide_cta ? 512 : 256), kargs, smem, s));
+            cudaError_t e = nf::launch_reduce(d_nll, d_sdz, n, red + t->n_vars, s);
+            if (e != cudaSuccess) return nf::set_error(NF_ERR_CUDA, "reduce launch", cudaGetErrorString(e));
+            nf::td_chain_kernel<<<1, 320, 0, s>>>(t->d_prog, t->d_vars, d_cg, d_sg, d_stats, inv_cnt, batch_stats ? 1 : 0, t->n_vars, red);
+            TD_CUDA(cudaGetLastError());
+            t->last_launches = 3;
+            return NF_OK;
+        }
+    }
+    t->last_launches = 1 + t->n_cp * ((batch_stats ? 2 : 0) + 4) + t->n_sc * 2 + 3;
+    nf::td_prep_kernel<<<1, 256, 0, s>>>(t->d_prog, t->d_vars, t->d_A, t->d_tables, d_consts);
     // ---- forward, keeping every op's input
     for (int i = 0; i < G; ++i) {
         const nf::TdOp& op = t->prog.ops[i];
@@ -1065,11 +1264,19 @@ static int td_enqueue(nf_trainer* t, const float* x, const float* y, const int32
             const nf::TdCoupling d = coupling_desc(t, op.o, batch_stats);
             const float* A = t->d_A + op.cidx * 16;
             double* st = d_stats + op.cidx * 16;
-            if (batch_stats) {
-                nf::td_fwd_kernel<1><<<grid, TD_THREADS, smem, s>>>(d, t->d_vars, A, st, in, out, d_ld, n, inv_cnt);
-                nf::td_fwd_kernel<2><<<grid, TD_THREADS, smem, s>>>(d, t->d_vars, A, st, in, out, d_ld, n, inv_cnt);
+            if (wide_cta) {
+                if (batch_stats) {
+                    nf::td_fwd_kernel<1, 16><<<grid, 512, smem, s>>>(d, t->d_vars, A, st, in, out, d_ld, n, inv_cnt);
+                    nf::td_fwd_kernel<2, 16><<<grid, 512, smem, s>>>(d, t->d_vars, A, st, in, out, d_ld, n, inv_cnt);
+                }
+                nf::td_fwd_kernel<3, 16><<<grid, 512, smem, s>>>(d, t->d_vars, A, st, in, out, d_ld, n, inv_cnt);
+            } else {
+                if (batch_stats) {
+                    nf::td_fwd_kernel<1, 8><<<grid, 256, smem, s>>>(d, t->d_vars, A, st, in, out, d_ld, n, inv_cnt);
+                    nf::td_fwd_kernel<2, 8><<<grid, 256, smem, s>>>(d, t->d_vars, A, st, in, out, d_ld, n, inv_cnt);
+                }
+                nf::td_fwd_kernel<3, 8><<<grid, 256, smem, s>>>(d, t->d_vars, A, st, in, out, d_ld, n, inv_cnt);
             }
-            nf::td_fwd_kernel<3><<<grid, TD_THREADS, smem, s>>>(d, t->d_vars, A, st, in, out, d_ld, n, inv_cnt);
         } else {
             const int is_sdn = op.o.token != NF_TOKEN_GAIN4;
             nf::td_scale_fwd_kernel<<<grid, TD_THREADS, 0, s>>>(t->d_tables + op.sidx * NF_MAX_ROWS * 2, is_sdn, 1, in, (const float4*)y, out,
@@ -1089,9 +1296,15 @@ static int td_enqueue(nf_trainer* t, const float* x, const float* y, const int32
             const float* A = t->d_A + op.cidx * 16;
             const double* st = d_stats + op.cidx * 16;
             double* cg = d_cg + (int64_t)op.cidx * NF_G_COUPLING_DOUBLES;
-            nf::td_b1_kernel<<<grid, TD_THREADS, smem, s>>>(d, t->d_vars, A, st, zin, (const float4*)gA, (float4*)gzp, (float4*)scratch, n, inv_n, inv_cnt, cg);
-            nf::td_b2_kernel<<<grid, TD_THREADS, smem, s>>>(d, t->d_vars, A, st, zin, (float4*)scratch, n, inv_cnt, cg);
-            nf::td_b3_kernel<<<grid, TD_THREADS, smem, s>>>(d, t->d_vars, A, st, zin, (const float4*)scratch, (const float4*)gzp, (float4*)gB, n, inv_cnt, cg);
+            if (wide_cta) {
+                nf::td_b1_kernel<16><<<grid, 512, smem, s>>>(d, t->d_vars, A, st, zin, (const float4*)gA, (float4*)gzp, (float4*)scratch, n, inv_n, inv_cnt, cg);
+                nf::td_b2_kernel<16><<<grid, 512, smem, s>>>(d, t->d_vars, A, st, zin, (float4*)scratch, n, inv_cnt, cg);
+                nf::td_b3_kernel<16><<<grid, 512, smem, s>>>(d, t->d_vars, A, st, zin, (const float4*)scratch, (const float4*)gzp, (float4*)gB, n, inv_cnt, cg);
+            } else {
+                nf::td_b1_kernel<8><<<grid, 256, smem, s>>>(d, t->d_vars, A, st, zin, (const float4*)gA, (float4*)gzp, (float4*)scratch, n, inv_n, inv_cnt, cg);
+                nf::td_b2_kernel<8><<<grid, 256, smem, s>>>(d, t->d_vars, A, st, zin, (float4*)scratch, n, inv_cnt, cg);
+                nf::td_b3_kernel<8><<<grid, 256, smem, s>>>(d, t->d_vars, A, st, zin, (const float4*)scratch, (const float4*)gzp, (float4*)gB, n, inv_cnt, cg);
+            }
         } else {
             const int is_sdn = op.o.token != NF_TOKEN_GAIN4;
             nf::td_scale_bwd_kernel<<<grid, TD_THREADS, 0, s>>>(t->d_tables + op.sidx * NF_MAX_ROWS * 2, is_sdn, 1, zout, (const float4*)y,
@@ -1102,6 +1315,20 @@ static int td_enqueue(nf_trainer* t, const float* x, const float* y, const int32
     }
     nf::td_chain_kernel<<<1, 320, 0, s>>>(t->d_prog, t->d_vars, d_cg, d_sg, d_stats, inv_cnt, batch_stats ? 1 : 0, t->n_vars, red);
     TD_CUDA(cudaGetLastError());
+    return NF_OK;
+}
+
+int nf_trainer_set_cta_warps(nf_trainer* t, int warps) {
+    if (!t || (warps != 0 && warps != 8 && warps != 16)) return nf::set_error(NF_ERR_INVALID, "nf_trainer_set_cta_warps", "warps must be 0 (automatic), 8 or 16");
+    t->cta_warps = warps;
+    if (t->exec) { cudaGraphExecDestroy(t->exec); t->exec = nullptr; }   // the captured launch shapes are stale
+    return NF_OK;
+}
+
+int nf_trainer_set_fused(nf_trainer* t, int enable) {
+    if (!t) return nf::set_error(NF_ERR_INVALID, "nf_trainer_set_fused", "null trainer");
+    t->fused = enable ? 1 : 0;
+    if (t->exec) { cudaGraphExecDestroy(t->exec); t->exec = nullptr; }
     return NF_OK;
 }
 

@@ -379,7 +379,7 @@ class DeviceTrainer:
     """
 
     def __init__(self, nf, learning_rate=1e-4, beta1=0.9, beta2=0.999, epsilon=1e-8, max_batch=256, group=None,
-                 cuda_graph=True):
+                 cuda_graph=True, cta_warps=0, fused=True):
         from .params import BN_EPS
         nf.build("inverse")
         self.nf, self.group = nf, group
@@ -402,6 +402,8 @@ class DeviceTrainer:
         self.red = torch.zeros(n.value, device=nf.device, dtype=torch.float64)
         self.steps = 0
         _lib.check(self.lib.nf_trainer_set_graph(self.handle, 1 if cuda_graph else 0), "nf_trainer_set_graph")
+        _lib.check(self.lib.nf_trainer_set_cta_warps(self.handle, int(cta_warps)), "nf_trainer_set_cta_warps")
+        _lib.check(self.lib.nf_trainer_set_fused(self.handle, 1 if fused else 0), "nf_trainer_set_fused")
 
     def _flatten(self):
         v = self.nf.spec.store.vars

@@ -125,6 +125,58 @@ def test_device_gradients_per_patch_rows(shipped):
             raise AssertionError("\n".join(report) + "\n" + str(e)[:600])
 
 
+@pytest.mark.parametrize("warps,fused", [(8, True), (16, True), (8, False), (16, False)])
+def test_device_cta_shapes_agree(shipped, warps, fused):
+    """8 and 16 warps per patch-CTA (16 is picked automatically when the batch fits one CTA per SM), as ONE cooperative
+    kernel (default when the batch is co-resident) or as one launch per pass: same step."""
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import DeviceTrainer
+    hps, ck = shipped
+    x, y = synth_batch(6, seed=77)
+    nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    tr = DeviceTrainer(nf, max_batch=8, cta_warps=warps, fused=fused)
+    assert tr.launches_per_step(True) == 57      # before any evaluation: the per-pass count
+    tr.loss_and_grad(x, y, iso=[100.0], cam=[2.0])
+    loss_o, sd_o, grads_o, _ = _oracle_loss_and_grads(hps, ck, x, y, 100.0, 2.0, True)
+    assert abs(tr.loss()[0] - loss_o) / 4096 < 1e-4
+    _check(tr.gradients(), grads_o, rel=5e-3)
+    assert tr.launches_per_step(True) == (4 if fused else 57)
+
+
+@pytest.mark.parametrize("is_training", [False, True])
+def test_fused_step_kernel_equals_per_pass_launches(shipped, is_training):
+    """The cooperative whole-step kernel and the per-pass kernels share their bodies: loss, statistics and every gradient
+    agree to summation noise, at a batch that fills the co-resident grid partly (8 warps, 40 patches) and in both
+    BatchNorm modes; a batch beyond the co-resident capacity falls back to per-pass launches by itself."""
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import DeviceTrainer
+    hps, ck = shipped
+    x, y = synth_batch(40, seed=81)
+    res = {}
+    for fused in (True, False):
+        nf = NoiseFlow([32, 32, 4], is_training, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+        tr = DeviceTrainer(nf, max_batch=400, cta_warps=8, fused=fused)
+        tr.loss_and_grad(x, y, iso=[100.0], cam=[2.0], is_training=is_training)
+        res[fused] = (tr.loss(), tr.gradients(), tr.batch_stats().copy(), tr.launches_per_step(is_training))
+    assert res[True][3] == 4 and res[False][3] == (57 if is_training else 41)
+    assert abs(res[True][0][0] - res[False][0][0]) / 4096 < 2e-6 and abs(res[True][0][1] - res[False][0][1]) < 1e-5
+    assert np.allclose(res[True][2], res[False][2], rtol=2e-4, atol=1e-6)
+    # batch statistics: fp32 summation order moves the normalised activations by ulps and a few ReLU masks with them,
+    # so two correct evaluations differ by more than round-off; both must sit within the oracle tolerance
+    _check(_split_zero_grad(res[True][1])[1], _split_zero_grad(res[False][1])[1], rel=1e-2 if is_training else 2e-4)
+    loss_o, _, grads_o, _ = _oracle_loss_and_grads(hps, ck, x, y, 100.0, 2.0, is_training)
+    for fused in (True, False):
+        assert abs(res[fused][0][0] - loss_o) / 4096 < 2e-5
+        _check(res[fused][1], grads_o, rel=5e-3 if is_training else 2e-4)
+    # 400 patches > 296 co-resident CTAs: the fused trainer uses the per-pass kernels
+    x2, y2 = synth_batch(400, seed=82)
+    nf = NoiseFlow([32, 32, 4], is_training, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
+    tr = DeviceTrainer(nf, max_batch=400, fused=True)
+    tr.loss_and_grad(x2, y2, iso=[100.0], cam=[2.0], is_training=is_training)
+    assert tr.launches_per_step(is_training) == (57 if is_training else 41)
+    assert np.isfinite(tr.loss()[0])
+
+
 @pytest.mark.parametrize("cuda_graph", [True, False])
 def test_device_graph_replay_equals_plain_launches(shipped, cuda_graph):
     """The CUDA-graph replay (staged inputs, re-capture on a new batch size) gives the plain-launch results."""
@@ -141,7 +193,7 @@ def test_device_graph_replay_equals_plain_launches(shipped, cuda_graph):
         a, b = tr.red.cpu().numpy(), ref.red.cpu().numpy()
         # fp32 shared-memory / fp64 global atomics accumulate in launch-dependent order: equal up to summation noise
         assert np.allclose(a, b, rtol=1e-4, atol=2e-5 * np.abs(b).max()), (n, seed, np.abs(a - b).max())
-        assert abs(tr.loss()[0] - ref.loss()[0]) < 1e-3
+        assert abs(tr.loss()[0] - ref.loss()[0]) < 5e-3        # fp32 loss of magnitude 1.2e4
 
 
 def test_device_adam_steps_match_host_train_step(shipped):
