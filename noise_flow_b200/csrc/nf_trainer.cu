@@ -56,6 +56,7 @@ struct __align__(16) TdSmem {
     NfTrainCoupling P;                     // raw parameters + BatchNorm statistics in force
     float acc[NF_G_COUPLING_DOUBLES];      // CTA-level partial sums, NF_G_* layout
     float4 zp[NF_PIXELS];                  // z' = z_in . A
+    float4 c1[NF_PIXELS];                  // conv-1 output of the resident patch (kept across the passes of the fused kernel)
     float4 h2[34 * 34];                    // padded h2 image (ring = 0)
     float4 g[34 * 34];                     // padded gradient image
 };
@@ -97,6 +98,33 @@ __device__ __forceinline__ void cta_acc_vec(float* acc, const float (&v)[K], int
 __device__ __forceinline__ bool on_ring(int k) {
     const int R = k / 34, C = k - R * 34;
     return R == 0 || R == 33 || C == 0 || C == 33;
+}
+
+// conv-1 output at pixel (r, lane): computed from z' and parked in S.c1, or -- `cached`: a previous pass of the fused kernel
+// already did that for this patch -- read back (conv-1 was 13 % of the fused kernel's stall samples, recomputed by six passes)
+__device__ __forceinline__ void td_c1(TdSmem& S, int r, int lane, float (&c1)[4], bool cached) {
+    if (cached) {
+        const float4 v = S.c1[r * 32 + lane];
+        c1[0] = v.x; c1[1] = v.y; c1[2] = v.z; c1[3] = v.w;
+    } else {
+        conv1_at(S.P, S, r, lane, c1);
+        S.c1[r * 32 + lane] = make_float4(c1[0], c1[1], c1[2], c1[3]);
+    }
+}
+// h1 (post BatchNorm-1 + ReLU) and the normalised c2hat at pixel (r, lane)   (net_to_c2hat of nf_train_common.cuh)
+__device__ __forceinline__ void td_net_to_c2hat(TdSmem& S, int r, int lane, float (&c1hat)[4], float (&h1)[4], float (&c2hat)[4],
+                                                bool cached) {
+    float c1[4];
+    td_c1(S, r, lane, c1, cached);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { c1hat[o] = (c1[o] - S.P.m1[o]) * S.P.is1[o]; h1[o] = fmaxf(c1hat[o], 0.f); }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        float c2 = S.P.b2[o];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c2 = fmaf(h1[i], S.P.w2[i][o], c2);
+        c2hat[o] = (c2 - S.P.m2[o]) * S.P.is2[o];
+    }
 }
 
 // stats: double[16] of this coupling = sum c1[4], sum c1^2[4], sum c2[4], sum c2^2[4] over the batch.
@@ -189,7 +217,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
             for (int r = warp; r < 32; r += NW) {
                 float c1[4];
-                conv1_at(S.P, S, r, lane, c1);
+                td_c1(S, r, lane, c1, reuse);
 #pragma unroll
                 for (int o = 0; o < 4; ++o) { s[o] += c1[o]; q[o] = fmaf(c1[o], c1[o], q[o]); }
             }
@@ -198,7 +226,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
             for (int r = warp; r < 32; r += NW) {
                 float c1[4], h1[4];
-                conv1_at(S.P, S, r, lane, c1);
+                td_c1(S, r, lane, c1, reuse);
 #pragma unroll
                 for (int o = 0; o < 4; ++o) h1[o] = fmaxf((c1[o] - S.P.m1[o]) * S.P.is1[o], 0.f);
 #pragma unroll
@@ -214,7 +242,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
         } else {
             for (int r = warp; r < 32; r += NW) {
                 float c1hat[4], h1[4], c2hat[4];
-                net_to_c2hat(S.P, S, r, lane, c1hat, h1, c2hat);
+                td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, reuse);
                 S.h2[(r + 1) * 34 + lane + 1] = make_float4(fmaxf(c2hat[0], 0.f), fmaxf(c2hat[1], 0.f), fmaxf(c2hat[2], 0.f), fmaxf(c2hat[3], 0.f));
             }
             __syncthreads();
@@ -283,7 +311,7 @@ td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
         __syncthreads();
         for (int r = warp; r < 32; r += NW) {
             float c1hat[4], h1[4], c2hat[4];
-            net_to_c2hat(S.P, S, r, lane, c1hat, h1, c2hat);
+            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, false);     // first backward pass of the coupling: computes and parks c1
             S.h2[(r + 1) * 34 + lane + 1] = make_float4(fmaxf(c2hat[0], 0.f), fmaxf(c2hat[1], 0.f), fmaxf(c2hat[2], 0.f), fmaxf(c2hat[3], 0.f));
         }
         __syncthreads();
@@ -407,7 +435,7 @@ td_b2_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
             for (int o = 0; o < 4; ++o) gw2[i][o] = 0.f;
         for (int r = warp; r < 32; r += NW) {
             float c1hat[4], h1[4], c2hat[4];
-            net_to_c2hat(S.P, S, r, lane, c1hat, h1, c2hat);
+            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, reuse);
             const float4 gc4 = scratch[p * NF_PIXELS + r * 32 + lane];
             float gc2[4], gh1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -475,7 +503,7 @@ td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
         float gb1[4] = {0.f, 0.f, 0.f, 0.f};
         for (int r = warp; r < 32; r += NW) {
             float c1[4];
-            conv1_at(S.P, S, r, lane, c1);
+            td_c1(S, r, lane, c1, reuse);
             const float4 g4 = scratch[p * NF_PIXELS + r * 32 + lane];
             float gc1[4];
 #pragma unroll
