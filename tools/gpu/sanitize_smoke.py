@@ -17,15 +17,20 @@ hps = hps_loader(os.path.join(g, "hps.txt"))
 ck = load_checkpoint(os.path.join(g, "ckpt", "model.ckpt.best"))
 n = int(os.environ.get("NF_SANITIZE_N", "37"))          # not a multiple of the warps per CTA: exercises the inactive-warp tail
 x, y = synth_batch(n, seed=1)
+# NF_SANITIZE_CHAIN=0 skips the TMEM-resident chain kernel: synccheck (CUDA 12.9) reports "Barrier error detected. Missing
+# init ... shared address 0x0" at its tcgen05.alloc (which has no mbarrier at all) and then kills the launch; the other three
+# tools run it clean.
+CHAIN = os.environ.get("NF_SANITIZE_CHAIN", "1") == "1"
 nf = NoiseFlow([32, 32, 4], False, hps, variables=ck, device="cuda:0", first_call="inverse")
-nll, sdz, z = nf._loss(x, y, iso=[100.0], cam=[2.0], return_z=True)
-xs = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], seed=3, offset=0)
-xr = nf.forward(z, None, yy=y, iso=[100.0], cam=[2.0])
-nll_b, _ = nf._loss(x, y, iso=[100.0], cam=[2.0], is_training=True)            # batch-statistics probes
-zz, ld = nf.run_layers(0, 3, "inverse", x, yy=y, iso=[100.0], cam=[2.0])
+if CHAIN:
+    nll, sdz, z = nf._loss(x, y, iso=[100.0], cam=[2.0], return_z=True)
+    xs = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], seed=3, offset=0)
+    xr = nf.forward(z, None, yy=y, iso=[100.0], cam=[2.0])
+    nll_b, _ = nf._loss(x, y, iso=[100.0], cam=[2.0], is_training=True)            # batch-statistics probes
+    zz, ld = nf.run_layers(0, 3, "inverse", x, yy=y, iso=[100.0], cam=[2.0])
 nf2 = NoiseFlow([32, 32, 4], False, make_hps(arch="sdn5|gain4"), device="cuda:0", first_call="inverse")
 nll_s, _ = nf2._loss(x, y, iso=[100.0], cam=[2.0])                              # streaming kernel
-if os.environ.get("NF_SANITIZE_TRAIN", "1") == "1":
+if CHAIN and os.environ.get("NF_SANITIZE_TRAIN", "1") == "1":
     from noise_flow_b200.train import AdamOptimizer, train_step
     nf3 = NoiseFlow([32, 32, 4], True, hps, variables=dict(ck), device="cuda:0", first_call="inverse")
     loss, sd = train_step(nf3, AdamOptimizer(1e-4), x, y, iso=[100.0], cam=[2.0])
@@ -33,14 +38,14 @@ if os.environ.get("NF_SANITIZE_TRAIN", "1") == "1":
 if os.environ.get("NF_SANITIZE_TRAINER", "1") == "1":     # device-resident train step: plain launches and CUDA-graph replay
     from noise_flow_b200.train import DeviceTrainer
     nt = min(n, 11)
-    for graph in (False, True):
+    for graph, fused, warps in ((False, True, 0), (True, True, 8), (False, False, 8), (True, False, 16)):   # cooperative step kernel / per-pass kernels
         nf4 = NoiseFlow([32, 32, 4], True, hps, variables=dict(ck), device="cuda:0", first_call="inverse")
-        tr = DeviceTrainer(nf4, learning_rate=1e-4, max_batch=16, cuda_graph=graph)
+        tr = DeviceTrainer(nf4, learning_rate=1e-4, max_batch=16, cuda_graph=graph, fused=fused, cta_warps=warps)
         for _ in range(2):
             l4, s4 = tr.step(x[:nt], y[:nt], iso=[100.0], cam=[2.0])
         tr.loss_and_grad(x[:nt], y[:nt], iso=[100.0] * nt, cam=[2.0] * (nt - 1) + [0.0], is_training=False)   # per-patch rows
         tr.sync_to_model()
-        print("device trainer graph=%s loss %.4f" % (graph, l4 / 4096))
+        print("device trainer graph=%s fused=%s warps=%d loss %.4f" % (graph, fused, warps, l4 / 4096))
 if os.environ.get("NF_SANITIZE_WIDE", "1") == "1":        # CTA-per-patch kernel for wide coupling nets
     nw = min(n, 7)
     for wd in (8, 32):
@@ -61,5 +66,8 @@ if os.environ.get("NF_SANITIZE_TC", "0") == "1":
     nll_t, _ = nf._loss(x, y, iso=[100.0], cam=[2.0])
     print("tc max diff", float((nll_t - nll).abs().max()))
 torch.cuda.synchronize()
+if not CHAIN:
+    print("ok (chain kernel skipped)", float(nll_s.mean()) / 4096)
+    sys.exit(0)
 print("ok", float(nll.mean()) / 4096, float(np.abs(xr.cpu().numpy() - x).max()), float(nll_s.mean()) / 4096,
       float(nll_b.mean()) / 4096, tuple(xs.shape), tuple(zz.shape))
