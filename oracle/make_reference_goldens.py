@@ -213,20 +213,26 @@ ARCH_CASES = [
     ("sdn5_unknown_iso", "sdn5|unc|gain4", 1, 2, 250),
     ("sdn2_unknown_iso", "sdn2|gain1", 1, 0, 250),
     ("gain3_unknown_iso", "gain3|unc", 1, 1, 250),
+    # wider coupling nets (`--width`, sidd/ArgParser.py:43): the CTA-per-patch kernels of csrc/nf_wide.cu
+    ("width8", "sdn5|unc|gain4|unc", 1, 2, 400, 8),
+    ("width16", "sdn5|unc|unc|gain4", 0, 0, 800, 16),
+    ("width32", "sdn5|unc|gain4|unc", 1, 4, 100, 32),
 ]
 
 
-def perturb(rng):
-    """Fresh variables make every coupling the identity (W3 = 0): move everything off its initial value."""
+def perturb(rng, width=4):
+    """Fresh variables make every coupling the identity (W3 = 0): move everything off its initial value (activations
+    kept O(1) at any width)."""
+    w_std, last_std = 0.5 / np.sqrt(width / 4.0), (0.1 if width == 4 else 0.02)
     for name, v in tf.get_default_graph().vars.items():
         leaf = name.split("/")[-1]
         a = v.t.detach().numpy()
         if leaf.startswith(("P_matpar", "sign_S")):
             continue
         if name.endswith("/l_1/W") or name.endswith("/l_2/W"):
-            new = rng.randn(*a.shape) * 0.5
+            new = rng.randn(*a.shape) * w_std
         elif name.endswith("/l_last/W"):
-            new = rng.randn(*a.shape) * 0.1
+            new = rng.randn(*a.shape) * last_std
         elif leaf in ("b", "logs"):
             new = rng.randn(*a.shape) * 0.2
         elif leaf == "mean":
@@ -242,11 +248,11 @@ def perturb(rng):
         v.load(new.astype(np.float32))                  # fp32-representable, like a checkpoint
 
 
-def arch_case_goldens(tag, arch, perm, cam, iso):
+def arch_case_goldens(tag, arch, perm, cam, iso, width=4):
     tf.reset_default_graph()
     np.random.seed(5)
     hps = ref_hps()
-    hps.arch, hps.flow_permutation = arch, perm
+    hps.arch, hps.flow_permutation, hps.width = arch, perm, width
     # train_noise_flow.py:200-213 (`init_params`) -- the wrapper's hps_loader leaves npcam unset for other archs
     npcam = 1 if "sdn6" in arch else 3
     cam_i = np.ndarray([npcam, 5])
@@ -265,8 +271,8 @@ def arch_case_goldens(tag, arch, perm, cam, iso):
     with tf.variable_scope("model", reuse=True):
         z_t, obj_t = nf.inverse(c(x), tf.zeros([n]), yy=c(y), **a)
     xs_t = nf.sample(c(y), 0.6, c(y), a["nlf0"], a["nlf1"], a["iso"], a["cam"])
-    perturb(np.random.RandomState(33))
-    out = {"arch": np.array(arch), "flow_permutation": np.int64(perm), "x": x, "y": y, "eps": eps, "iso": np.float32(iso),
+    perturb(np.random.RandomState(33), width)
+    out = {"arch": np.array(arch), "flow_permutation": np.int64(perm), "width": np.int64(width), "x": x, "y": y, "eps": eps, "iso": np.float32(iso),
            "cam": np.float32(cam), "nlf0": np.float64(nlf0), "nlf1": np.float64(nlf1),
            "layer_names": np.array(nf.get_layer_names()),
            "num_params": np.int64(sum(int(np.prod(v.get_shape().as_list())) for v in tf.trainable_variables()))}
@@ -305,8 +311,9 @@ def main():
     save("ref_training_graph.npz", training_graph_goldens())
     save("ref_wrapper_graph.npz", wrapper_goldens())
     cases = {}
-    for tag, arch, perm, cam, iso in ARCH_CASES:
-        for k, v in arch_case_goldens(tag, arch, perm, cam, iso).items():
+    for case in ARCH_CASES:
+        tag = case[0]
+        for k, v in arch_case_goldens(*case).items():
             cases[tag + "::" + k] = v
     save("ref_arch_cases.npz", cases)
     save("ref_squeeze.npz", squeeze_goldens())

@@ -177,7 +177,7 @@ def test_oracle_reproduces_reference_arch_cases(tag):
     from noise_flow_b200 import make_hps
     ac, _ = _arch_cases()
     g = {k.split("::", 1)[1]: ac[k] for k in ac.files if k.startswith(tag + "::")}
-    hps = make_hps(arch=str(g["arch"]), flow_permutation=int(g["flow_permutation"]))
+    hps = make_hps(arch=str(g["arch"]), flow_permutation=int(g["flow_permutation"]), width=int(g["width"]))
     variables = {k[len("var/"):]: v for k, v in g.items() if k.startswith("var/")}
     orc = make_oracle(hps, variables)
     assert orc.get_layer_names() == list(g["layer_names"])
