@@ -102,20 +102,20 @@ __device__ __forceinline__ bool on_ring(int k) {
 
 // conv-1 output at pixel (r, lane): computed from z' and parked in S.c1, or -- `cached`: a previous pass of the fused kernel
 // already did that for this patch -- read back (conv-1 was 13 % of the fused kernel's stall samples, recomputed by six passes)
-__device__ __forceinline__ void td_c1(TdSmem& S, int r, int lane, float (&c1)[4], bool cached) {
+__device__ __forceinline__ void td_c1(TdSmem& S, int r, int lane, float (&c1)[4], bool cached, bool park) {
     if (cached) {
         const float4 v = S.c1[r * 32 + lane];
         c1[0] = v.x; c1[1] = v.y; c1[2] = v.z; c1[3] = v.w;
     } else {
         conv1_at(S.P, S, r, lane, c1);
-        S.c1[r * 32 + lane] = make_float4(c1[0], c1[1], c1[2], c1[3]);
+        if (park) S.c1[r * 32 + lane] = make_float4(c1[0], c1[1], c1[2], c1[3]);     // fused kernel only
     }
 }
 // h1 (post BatchNorm-1 + ReLU) and the normalised c2hat at pixel (r, lane)   (net_to_c2hat of nf_train_common.cuh)
 __device__ __forceinline__ void td_net_to_c2hat(TdSmem& S, int r, int lane, float (&c1hat)[4], float (&h1)[4], float (&c2hat)[4],
-                                                bool cached) {
+                                                bool cached, bool park) {
     float c1[4];
-    td_c1(S, r, lane, c1, cached);
+    td_c1(S, r, lane, c1, cached, park);
 #pragma unroll
     for (int o = 0; o < 4; ++o) { c1hat[o] = (c1[o] - S.P.m1[o]) * S.P.is1[o]; h1[o] = fmaxf(c1hat[o], 0.f); }
 #pragma unroll
@@ -199,7 +199,7 @@ __device__ __forceinline__ void td_flush(TdSmem& S, double* dst, int lo, int hi)
 template <int STAGE, int NW>
 __device__ __forceinline__ void
 td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, double* stats,
-            const float4* zin, float4* zout, float* ld, long long n, double inv_cnt, bool reuse = false) {
+            const float4* zin, float4* zout, float* ld, long long n, double inv_cnt, bool reuse = false, bool park = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // reuse (fused kernel, one patch per CTA): weights and the mixed patch z' are still in shared memory from the previous stage
     td_load_params(S, d, vars, A, stats, inv_cnt, STAGE - 1, reuse);
@@ -217,7 +217,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
             for (int r = warp; r < 32; r += NW) {
                 float c1[4];
-                td_c1(S, r, lane, c1, reuse);
+                td_c1(S, r, lane, c1, reuse, park);
 #pragma unroll
                 for (int o = 0; o < 4; ++o) { s[o] += c1[o]; q[o] = fmaf(c1[o], c1[o], q[o]); }
             }
@@ -226,7 +226,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
             for (int r = warp; r < 32; r += NW) {
                 float c1[4], h1[4];
-                td_c1(S, r, lane, c1, reuse);
+                td_c1(S, r, lane, c1, reuse, park);
 #pragma unroll
                 for (int o = 0; o < 4; ++o) h1[o] = fmaxf((c1[o] - S.P.m1[o]) * S.P.is1[o], 0.f);
 #pragma unroll
@@ -242,7 +242,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
         } else {
             for (int r = warp; r < 32; r += NW) {
                 float c1hat[4], h1[4], c2hat[4];
-                td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, reuse);
+                td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, reuse, park);
                 S.h2[(r + 1) * 34 + lane + 1] = make_float4(fmaxf(c2hat[0], 0.f), fmaxf(c2hat[1], 0.f), fmaxf(c2hat[2], 0.f), fmaxf(c2hat[3], 0.f));
             }
             __syncthreads();
@@ -297,7 +297,7 @@ template <int NW>
 __device__ __forceinline__ void
 td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, const double* stats,
            const float4* zin, const float4* gout, float4* gzp, float4* scratch, long long n, float inv_n, double inv_cnt,
-           double* grads) {
+           double* grads, bool park = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     td_load_params(S, d, vars, A, stats, inv_cnt, 2);
     __syncthreads();
@@ -311,7 +311,7 @@ td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
         __syncthreads();
         for (int r = warp; r < 32; r += NW) {
             float c1hat[4], h1[4], c2hat[4];
-            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, false);     // first backward pass of the coupling: computes and parks c1
+            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, false, park);     // first backward pass of the coupling: parks c1 for B2 / B3
             S.h2[(r + 1) * 34 + lane + 1] = make_float4(fmaxf(c2hat[0], 0.f), fmaxf(c2hat[1], 0.f), fmaxf(c2hat[2], 0.f), fmaxf(c2hat[3], 0.f));
         }
         __syncthreads();
@@ -419,6 +419,7 @@ template <int NW>
 __device__ __forceinline__ void
 td_b2_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, const double* stats,
            const float4* zin, float4* scratch, long long n, double inv_cnt, double* grads, bool reuse = false) {
+    const bool park = false;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float bn2[8];
 #pragma unroll
@@ -435,7 +436,7 @@ td_b2_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
             for (int o = 0; o < 4; ++o) gw2[i][o] = 0.f;
         for (int r = warp; r < 32; r += NW) {
             float c1hat[4], h1[4], c2hat[4];
-            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, reuse);
+            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, reuse, park);
             const float4 gc4 = scratch[p * NF_PIXELS + r * 32 + lane];
             float gc2[4], gh1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -489,6 +490,7 @@ __device__ __forceinline__ void
 td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, const double* stats,
            const float4* zin, const float4* scratch, const float4* gzp, float4* gin, long long n, double inv_cnt, double* grads,
            bool reuse = false) {
+    const bool park = false;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float bn1[8];
 #pragma unroll
@@ -503,7 +505,7 @@ td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
         float gb1[4] = {0.f, 0.f, 0.f, 0.f};
         for (int r = warp; r < 32; r += NW) {
             float c1[4];
-            td_c1(S, r, lane, c1, reuse);
+            td_c1(S, r, lane, c1, reuse, park);
             const float4 g4 = scratch[p * NF_PIXELS + r * 32 + lane];
             float gc1[4];
 #pragma unroll
@@ -1011,7 +1013,7 @@ td_step_kernel(const TdStepArgs a) {
             const float* A = a.Amat + op.cidx * 16;
             double* st = a.stats + op.cidx * 16;
             if (a.batch_stats) {
-                td_fwd_body<1, NW>(S, d, a.vars, A, st, in, out, ld, n, inv_cnt);
+                td_fwd_body<1, NW>(S, d, a.vars, A, st, in, out, ld, n, inv_cnt, false, true);
                 grid.sync();
                 td_fwd_body<2, NW>(S, d, a.vars, A, st, in, out, ld, n, inv_cnt, true);
                 grid.sync();
@@ -1035,7 +1037,7 @@ td_step_kernel(const TdStepArgs a) {
             const float* A = a.Amat + op.cidx * 16;
             const double* st = a.stats + op.cidx * 16;
             double* cgr = a.cgrads + (long long)op.cidx * NF_G_COUPLING_DOUBLES;
-            td_b1_body<NW>(S, d, a.vars, A, st, zin, (const float4*)gA, (float4*)gzp, (float4*)scratch, n, inv_n, inv_cnt, cgr);
+            td_b1_body<NW>(S, d, a.vars, A, st, zin, (const float4*)gA, (float4*)gzp, (float4*)scratch, n, inv_n, inv_cnt, cgr, true);
             if (a.batch_stats) grid.sync(); else __syncthreads();      // BatchNorm-2 backward sums over the whole batch
             td_b2_body<NW>(S, d, a.vars, A, st, zin, (float4*)scratch, n, inv_cnt, cgr, true);
             if (a.batch_stats) grid.sync(); else __syncthreads();      // BatchNorm-1 backward sums
