@@ -224,8 +224,8 @@ int nf_trainer_launches_per_step(const nf_trainer* t, int batch_stats, int* n_la
  * launch sequence as ONE CUDA graph (re-captured when n, default_row, batch_stats or reduce_buf change) on an
  * internal stream fenced against `stream` with events; 0: plain launches on `stream`. */
 int nf_trainer_set_graph(nf_trainer* t, int enable);
-/* Warps per patch-CTA of the coupling passes: 0 (default) = 16 when the batch has no more patches than the GPU has
- * SMs (one CTA per SM, e.g. the reference's 138-patch step), else 8 (two CTAs per SM); 8 / 16 force a shape. */
+/* Warps per patch-CTA of the coupling passes: 0 (default) = 8 (four image rows per warp: every weight read from shared
+ * memory is applied to four rows); 8 / 16 force a shape (16 = two rows per warp, one CTA per SM). */
 int nf_trainer_set_cta_warps(nf_trainer* t, int warps);
 /* 1 (default): when every patch of the batch can own a co-resident CTA (<= 296 patches at 8 warps, <= 148 at 16 on a
  * B200) the whole loss + gradient evaluation is ONE cooperative kernel (grid barriers around the BatchNorm batch sums)

@@ -7,8 +7,7 @@
 // the chain rules back to the LU / scale variables, Adam, the BatchNorm moving averages -- are small kernels
 // between the heavy passes, so a step is one stream of ~60 launches with no cudaStreamSynchronize in it.
 //
-// Mapping: ONE CTA OWNS ONE PATCH (8 warps -- 16 when the batch has no more patches than the GPU has SMs, e.g. the
-// reference's 138 --; warp w owns image rows w, w+NW, ...; lane = column).  A train batch
+// Mapping: ONE CTA OWNS ONE PATCH (8 warps, 16 selectable; warp w owns image rows w, w+NW, ...; lane = column).  A train batch
 // is 138-207 patches per GPU (job_noise_flow.sh:37), far fewer than the 148 x 16 resident warps of the
 // inference kernel, so the patch is split over a whole CTA to cut the latency of every pass by ~8x; images live
 // in that CTA's shared memory; parameter-gradient partial sums go warp shuffle -> shared fp32 -> one fp64
@@ -100,22 +99,50 @@ __device__ __forceinline__ bool on_ring(int k) {
     return R == 0 || R == 33 || C == 0 || C == 33;
 }
 
-// conv-1 output at pixel (r, lane): computed from z' and parked in S.c1, or -- `cached`: a previous pass of the fused kernel
-// already did that for this patch -- read back (conv-1 was 13 % of the fused kernel's stall samples, recomputed by six passes)
-__device__ __forceinline__ void td_c1(TdSmem& S, int r, int lane, float (&c1)[4], bool cached, bool park) {
-    if (cached) {
-        const float4 v = S.c1[r * 32 + lane];
-        c1[0] = v.x; c1[1] = v.y; c1[2] = v.z; c1[3] = v.w;
-    } else {
-        conv1_at(S.P, S, r, lane, c1);
-        if (park) S.c1[r * 32 + lane] = make_float4(c1[0], c1[1], c1[2], c1[3]);     // fused kernel only
-    }
+// conv-1 (3x3 SAME, 2 -> 4 channels) of the rows this warp owns, register-blocked over those rows: the 8 weights of a tap
+// are read from shared memory once and applied to every row (9 x (2 + R) LDS.128 for R rows instead of 27 R), no divergent
+// edge handling (column clamped, contribution masked).  The result is parked in S.c1; every later use in this pass -- and,
+// in the fused kernel, in the following passes of the same coupling -- reads it back (each thread reads only what it wrote).
+// conv-1 recomputed per pixel by all six passes was 13 % of the fused kernel's stall samples.
+template <int NW>
+__device__ __forceinline__ void td_conv1_rows(TdSmem& S, int warp, int lane) {
+    constexpr int R = 32 / NW;
+    float acc[R][4];
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[k][o] = S.P.b1[o];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&S.P.w1[dy][dx][0][0]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&S.P.w1[dy][dx][1][0]);
+            const int cc = lane + dx - 1, ccs = min(max(cc, 0), 31);
+            const float cm = cc == ccs ? 1.f : 0.f;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int rr = warp + k * NW + dy - 1;
+                if (rr < 0 || rr > 31) continue;                      // warp-uniform
+                const float4 z = S.zp[rr * 32 + ccs];
+                const float zx = z.x * cm, zy = z.y * cm;
+                acc[k][0] = fmaf(zx, w0.x, fmaf(zy, w1.x, acc[k][0]));
+                acc[k][1] = fmaf(zx, w0.y, fmaf(zy, w1.y, acc[k][1]));
+                acc[k][2] = fmaf(zx, w0.z, fmaf(zy, w1.z, acc[k][2]));
+                acc[k][3] = fmaf(zx, w0.w, fmaf(zy, w1.w, acc[k][3]));
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < R; ++k) S.c1[(warp + k * NW) * 32 + lane] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
 }
-// h1 (post BatchNorm-1 + ReLU) and the normalised c2hat at pixel (r, lane)   (net_to_c2hat of nf_train_common.cuh)
-__device__ __forceinline__ void td_net_to_c2hat(TdSmem& S, int r, int lane, float (&c1hat)[4], float (&h1)[4], float (&c2hat)[4],
-                                                bool cached, bool park) {
+__device__ __forceinline__ void td_c1(const TdSmem& S, int r, int lane, float (&c1)[4]) {
+    const float4 v = S.c1[r * 32 + lane];
+    c1[0] = v.x; c1[1] = v.y; c1[2] = v.z; c1[3] = v.w;
+}
+// h1 (post BatchNorm-1 + ReLU) and the normalised c2hat at pixel (r, lane) from the parked conv-1 output
+__device__ __forceinline__ void td_net_to_c2hat(const TdSmem& S, int r, int lane, float (&c1hat)[4], float (&h1)[4], float (&c2hat)[4]) {
     float c1[4];
-    td_c1(S, r, lane, c1, cached, park);
+    td_c1(S, r, lane, c1);
 #pragma unroll
     for (int o = 0; o < 4; ++o) { c1hat[o] = (c1[o] - S.P.m1[o]) * S.P.is1[o]; h1[o] = fmaxf(c1hat[o], 0.f); }
 #pragma unroll
@@ -125,6 +152,80 @@ __device__ __forceinline__ void td_net_to_c2hat(TdSmem& S, int r, int lane, floa
         for (int i = 0; i < 4; ++i) c2 = fmaf(h1[i], S.P.w2[i][o], c2);
         c2hat[o] = (c2 - S.P.m2[o]) * S.P.is2[o];
     }
+}
+
+// conv-3 (edge-padded: 3x3 VALID over the zero-padded h2 image + the ring-indicator channel, 5 -> 4, layers.py:555-583,
+// 651-674) of the rows this warp owns, register-blocked like conv-1: 9 x (5 + R) LDS.128 instead of 54 R.
+template <int NW>
+__device__ __forceinline__ void td_conv3_rows(const TdSmem& S, int warp, int lane, float (&pre)[32 / NW][4]) {
+    constexpr int R = 32 / NW;
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) pre[k][o] = S.P.b3[o];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            float4 w[5];
+#pragma unroll
+            for (int ci = 0; ci < 5; ++ci) w[ci] = *reinterpret_cast<const float4*>(&S.P.w3[dy][dx][ci][0]);
+            const int C = lane + dx;
+            const bool cedge = C == 0 || C == 33;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int Rr = warp + k * NW + dy;
+                const float4 h = S.h2[Rr * 34 + C];
+                const float ring = (cedge || Rr == 0 || Rr == 33) ? 1.f : 0.f;
+                pre[k][0] += h.x * w[0].x + h.y * w[1].x + h.z * w[2].x + h.w * w[3].x + ring * w[4].x;
+                pre[k][1] += h.x * w[0].y + h.y * w[1].y + h.z * w[2].y + h.w * w[3].y + ring * w[4].y;
+                pre[k][2] += h.x * w[0].z + h.y * w[1].z + h.z * w[2].z + h.w * w[3].z + ring * w[4].z;
+                pre[k][3] += h.x * w[0].w + h.y * w[1].w + h.z * w[2].w + h.w * w[3].w + ring * w[4].w;
+            }
+        }
+}
+// transposed conv-3: g_h2(r, c)[ci] = sum_{dy,dx,o} W3[dy][dx][ci][o] * g_pre3(r-dy+1, c-dx+1)[o] over the padded gradient image
+template <int NW>
+__device__ __forceinline__ void td_conv3t_rows(const TdSmem& S, int warp, int lane, float (&gh)[32 / NW][4]) {
+    constexpr int R = 32 / NW;
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) gh[k][ci] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            float4 w[4];
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) w[ci] = *reinterpret_cast<const float4*>(&S.P.w3[dy][dx][ci][0]);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const float4 gp = S.g[(warp + k * NW - dy + 2) * 34 + (lane - dx + 2)];   // padded index of pixel (r-dy+1, c-dx+1)
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) gh[k][ci] += gp.x * w[ci].x + gp.y * w[ci].y + gp.z * w[ci].z + gp.w * w[ci].w;
+            }
+        }
+}
+// transposed conv-1: g_x0(r, c)[ci] = sum_{dy,dx,o} W1[dy][dx][ci][o] * g_c1(r-dy+1, c-dx+1)[o]
+template <int NW>
+__device__ __forceinline__ void td_conv1t_rows(const TdSmem& S, int warp, int lane, float (&gx0)[32 / NW][2]) {
+    constexpr int R = 32 / NW;
+#pragma unroll
+    for (int k = 0; k < R; ++k) gx0[k][0] = gx0[k][1] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&S.P.w1[dy][dx][0][0]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&S.P.w1[dy][dx][1][0]);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const float4 g = S.g[(warp + k * NW - dy + 2) * 34 + (lane - dx + 2)];
+                gx0[k][0] += g.x * w0.x + g.y * w0.y + g.z * w0.z + g.w * w0.w;
+                gx0[k][1] += g.x * w1.x + g.y * w1.y + g.z * w1.z + g.w * w1.w;
+            }
+        }
 }
 
 // stats: double[16] of this coupling = sum c1[4], sum c1^2[4], sum c2[4], sum c2^2[4] over the batch.
@@ -199,7 +300,7 @@ __device__ __forceinline__ void td_flush(TdSmem& S, double* dst, int lo, int hi)
 template <int STAGE, int NW>
 __device__ __forceinline__ void
 td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, double* stats,
-            const float4* zin, float4* zout, float* ld, long long n, double inv_cnt, bool reuse = false, bool park = false) {
+            const float4* zin, float4* zout, float* ld, long long n, double inv_cnt, bool reuse = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // reuse (fused kernel, one patch per CTA): weights and the mixed patch z' are still in shared memory from the previous stage
     td_load_params(S, d, vars, A, stats, inv_cnt, STAGE - 1, reuse);
@@ -213,11 +314,12 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
             for (int k = threadIdx.x; k < 34 * 34; k += blockDim.x)
                 if (on_ring(k)) S.h2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
+        if (!reuse) td_conv1_rows<NW>(S, warp, lane);
         if (STAGE == 1) {
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
             for (int r = warp; r < 32; r += NW) {
                 float c1[4];
-                td_c1(S, r, lane, c1, reuse, park);
+                td_c1(S, r, lane, c1);
 #pragma unroll
                 for (int o = 0; o < 4; ++o) { s[o] += c1[o]; q[o] = fmaf(c1[o], c1[o], q[o]); }
             }
@@ -226,7 +328,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
             for (int r = warp; r < 32; r += NW) {
                 float c1[4], h1[4];
-                td_c1(S, r, lane, c1, reuse, park);
+                td_c1(S, r, lane, c1);
 #pragma unroll
                 for (int o = 0; o < 4; ++o) h1[o] = fmaxf((c1[o] - S.P.m1[o]) * S.P.is1[o], 0.f);
 #pragma unroll
@@ -242,27 +344,17 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
         } else {
             for (int r = warp; r < 32; r += NW) {
                 float c1hat[4], h1[4], c2hat[4];
-                td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, reuse, park);
+                td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat);
                 S.h2[(r + 1) * 34 + lane + 1] = make_float4(fmaxf(c2hat[0], 0.f), fmaxf(c2hat[1], 0.f), fmaxf(c2hat[2], 0.f), fmaxf(c2hat[3], 0.f));
             }
             __syncthreads();
             float lsum = 0.f;
-            for (int r = warp; r < 32; r += NW) {
-                float pre[4];
+            float pre_rows[32 / NW][4];
+            td_conv3_rows<NW>(S, warp, lane, pre_rows);
 #pragma unroll
-                for (int o = 0; o < 4; ++o) pre[o] = S.P.b3[o];
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int R = r + dy, C = lane + dx;
-                        const float4 h = S.h2[R * 34 + C];
-                        const float ring = (R == 0 || R == 33 || C == 0 || C == 33) ? 1.f : 0.f;
-#pragma unroll
-                        for (int o = 0; o < 4; ++o)
-                            pre[o] += h.x * S.P.w3[dy][dx][0][o] + h.y * S.P.w3[dy][dx][1][o] + h.z * S.P.w3[dy][dx][2][o] +
-                                      h.w * S.P.w3[dy][dx][3][o] + ring * S.P.w3[dy][dx][4][o];
-                    }
+            for (int k = 0; k < 32 / NW; ++k) {
+                const int r = warp + k * NW;
+                const float (&pre)[4] = pre_rows[k];
                 const float sh0 = pre[0] * e3[0], sh1 = pre[1] * e3[1];
                 const float ls0 = S.P.scale * tanhf(pre[2] * e3[2]), ls1 = S.P.scale * tanhf(pre[3] * e3[3]);
                 const float4 zp = S.zp[r * 32 + lane];
@@ -297,7 +389,7 @@ template <int NW>
 __device__ __forceinline__ void
 td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, const double* stats,
            const float4* zin, const float4* gout, float4* gzp, float4* scratch, long long n, float inv_n, double inv_cnt,
-           double* grads, bool park = false) {
+           double* grads) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     td_load_params(S, d, vars, A, stats, inv_cnt, 2);
     __syncthreads();
@@ -309,30 +401,21 @@ td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
         for (int k = threadIdx.x; k < 34 * 34; k += blockDim.x)
             if (on_ring(k)) { S.h2[k] = make_float4(0.f, 0.f, 0.f, 0.f); S.g[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
         __syncthreads();
+        td_conv1_rows<NW>(S, warp, lane);
         for (int r = warp; r < 32; r += NW) {
             float c1hat[4], h1[4], c2hat[4];
-            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, false, park);     // first backward pass of the coupling: parks c1 for B2 / B3
+            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat);
             S.h2[(r + 1) * 34 + lane + 1] = make_float4(fmaxf(c2hat[0], 0.f), fmaxf(c2hat[1], 0.f), fmaxf(c2hat[2], 0.f), fmaxf(c2hat[3], 0.f));
         }
         __syncthreads();
         // conv-3 forward + coupling backward -> g_pre3 image, partial G_z'
         float g_scale = 0.f, g_logs[4] = {0.f, 0.f, 0.f, 0.f}, g_b3[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = warp; r < 32; r += NW) {
-            float pre[4];
+        float pre_rows[32 / NW][4];
+        td_conv3_rows<NW>(S, warp, lane, pre_rows);
 #pragma unroll
-            for (int o = 0; o < 4; ++o) pre[o] = S.P.b3[o];
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int R = r + dy, C = lane + dx;
-                    const float4 h = S.h2[R * 34 + C];
-                    const float ring = (R == 0 || R == 33 || C == 0 || C == 33) ? 1.f : 0.f;
-#pragma unroll
-                    for (int o = 0; o < 4; ++o)
-                        pre[o] += h.x * S.P.w3[dy][dx][0][o] + h.y * S.P.w3[dy][dx][1][o] + h.z * S.P.w3[dy][dx][2][o] +
-                                  h.w * S.P.w3[dy][dx][3][o] + ring * S.P.w3[dy][dx][4][o];
-                }
+        for (int k = 0; k < 32 / NW; ++k) {
+            const int r = warp + k * NW;
+            const float (&pre)[4] = pre_rows[k];
             float h3[4];
 #pragma unroll
             for (int o = 0; o < 4; ++o) h3[o] = pre[o] * e3[o];
@@ -376,18 +459,12 @@ td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
             }
         // g_h2(r, c)[ci] = sum_{dy,dx,o} W3[dy][dx][ci][o] * g_pre3(r-dy+1, c-dx+1)[o] ; ReLU mask ; BatchNorm-2 sums
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = warp; r < 32; r += NW) {
-            float gh[4] = {0.f, 0.f, 0.f, 0.f};
+        float gh_rows[32 / NW][4];
+        td_conv3t_rows<NW>(S, warp, lane, gh_rows);
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const float4 gp = S.g[(r - dy + 2) * 34 + (lane - dx + 2)];   // padded index of pixel (r-dy+1, c-dx+1)
-#pragma unroll
-                    for (int ci = 0; ci < 4; ++ci)
-                        gh[ci] += gp.x * S.P.w3[dy][dx][ci][0] + gp.y * S.P.w3[dy][dx][ci][1] + gp.z * S.P.w3[dy][dx][ci][2] +
-                                  gp.w * S.P.w3[dy][dx][ci][3];
-                }
+        for (int k = 0; k < 32 / NW; ++k) {
+            const int r = warp + k * NW;
+            const float (&gh)[4] = gh_rows[k];
             const float4 h = S.h2[(r + 1) * 34 + lane + 1];
             float gc[4];
 #pragma unroll
@@ -419,7 +496,6 @@ template <int NW>
 __device__ __forceinline__ void
 td_b2_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, const double* stats,
            const float4* zin, float4* scratch, long long n, double inv_cnt, double* grads, bool reuse = false) {
-    const bool park = false;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float bn2[8];
 #pragma unroll
@@ -429,6 +505,7 @@ td_b2_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
     for (long long p = blockIdx.x; p < n; p += gridDim.x) {
         if (!reuse) td_load_mixed<NW>(S, zin + p * NF_PIXELS, warp, lane);
         __syncthreads();
+        if (!reuse) td_conv1_rows<NW>(S, warp, lane);
         float gw2[4][4], gb2[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -436,7 +513,7 @@ td_b2_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
             for (int o = 0; o < 4; ++o) gw2[i][o] = 0.f;
         for (int r = warp; r < 32; r += NW) {
             float c1hat[4], h1[4], c2hat[4];
-            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat, reuse, park);
+            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat);
             const float4 gc4 = scratch[p * NF_PIXELS + r * 32 + lane];
             float gc2[4], gh1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -490,7 +567,6 @@ __device__ __forceinline__ void
 td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* A, const double* stats,
            const float4* zin, const float4* scratch, const float4* gzp, float4* gin, long long n, double inv_cnt, double* grads,
            bool reuse = false) {
-    const bool park = false;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float bn1[8];
 #pragma unroll
@@ -502,10 +578,11 @@ td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
         for (int k = threadIdx.x; k < 34 * 34; k += blockDim.x)
             if (on_ring(k)) S.g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
+        if (!reuse) td_conv1_rows<NW>(S, warp, lane);
         float gb1[4] = {0.f, 0.f, 0.f, 0.f};
         for (int r = warp; r < 32; r += NW) {
             float c1[4];
-            td_c1(S, r, lane, c1, reuse, park);
+            td_c1(S, r, lane, c1);
             const float4 g4 = scratch[p * NF_PIXELS + r * 32 + lane];
             float gc1[4];
 #pragma unroll
@@ -547,18 +624,12 @@ td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int o = 0; o < 4; ++o) gA[i][o] = 0.f;
-        for (int r = warp; r < 32; r += NW) {
-            float gx0[2] = {0.f, 0.f};
+        float gx0_rows[32 / NW][2];
+        td_conv1t_rows<NW>(S, warp, lane, gx0_rows);
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const float4 g = S.g[(r - dy + 2) * 34 + (lane - dx + 2)];
-#pragma unroll
-                    for (int ci = 0; ci < 2; ++ci)
-                        gx0[ci] += g.x * S.P.w1[dy][dx][ci][0] + g.y * S.P.w1[dy][dx][ci][1] + g.z * S.P.w1[dy][dx][ci][2] +
-                                   g.w * S.P.w1[dy][dx][ci][3];
-                }
+        for (int k = 0; k < 32 / NW; ++k) {
+            const int r = warp + k * NW;
+            const float (&gx0)[2] = gx0_rows[k];
             float4 gz = gzp[p * NF_PIXELS + r * 32 + lane];
             gz.x += gx0[0];
             gz.y += gx0[1];
@@ -821,13 +892,15 @@ __global__ void td_chain_kernel(const TdProgram* __restrict__ prog, const float*
                                 const double* __restrict__ sgrads, const double* __restrict__ stats, double inv_cnt,
                                 int batch_stats, long long n_vars, double* __restrict__ red) {
     const int n_ops = prog->n_ops;
-    // (1) coupling tensors: straight copies (checkpoint layouts are the kernel layouts)
-    for (int i = 0; i < n_ops; ++i) {
+    // (1) coupling tensors: straight copies (checkpoint layouts are the kernel layouts); work items = (op, slot of its gradient
+    //     block), all independent, so the loads of every coupling are in flight at once
+    for (int item = threadIdx.x; item < n_ops * NF_G_COUPLING_DOUBLES; item += blockDim.x) {
+        const int i = item / NF_G_COUPLING_DOUBLES, k = item % NF_G_COUPLING_DOUBLES;
         const TdOp& op = prog->ops[i];
         if (op.o.kind != NF_TOP_COUPLING) continue;
         const double* g = cgrads + (size_t)op.cidx * NF_G_COUPLING_DOUBLES;
         const nf_train_op& o = op.o;
-        for (int k = threadIdx.x; k < NF_G_HOST_COUPLING; k += blockDim.x) {
+        if (k < NF_G_HOST_COUPLING) {
             const int src = NF_G_W1 + k;
             int dst;
             if (src < NF_G_B1) dst = o.off_w1 + (src - NF_G_W1);
@@ -839,15 +912,14 @@ __global__ void td_chain_kernel(const TdProgram* __restrict__ prog, const float*
             else if (src < NF_G_SCALE) dst = o.off_logs + (src - NF_G_LOGS);
             else dst = o.off_scale;
             atomicAdd(red + dst, g[src]);
-        }
-        if (threadIdx.x < 16) {
-            const int j = threadIdx.x, st = j >> 3, k = j & 3;   // j: [mean1 4][var1 4][mean2 4][var2 4]
+        } else if (k < NF_G_HOST_COUPLING + 16) {
+            const int j = k - NF_G_HOST_COUPLING, st = j >> 3, c = j & 3;   // j: [mean1 4][var1 4][mean2 4][var2 4]
             double val = 0.0;
             if (batch_stats) {
-                const double mu = stats[op.cidx * 16 + 8 * st + k] * inv_cnt;
+                const double mu = stats[op.cidx * 16 + 8 * st + c] * inv_cnt;
                 if ((j & 4) == 0) val = (double)(float)mu;
                 else {
-                    double v = stats[op.cidx * 16 + 8 * st + 4 + k] * inv_cnt - mu * mu;
+                    double v = stats[op.cidx * 16 + 8 * st + 4 + c] * inv_cnt - mu * mu;
                     val = (double)(float)(v < 0.0 ? 0.0 : v);
                 }
             }
@@ -1013,7 +1085,7 @@ td_step_kernel(const TdStepArgs a) {
             const float* A = a.Amat + op.cidx * 16;
             double* st = a.stats + op.cidx * 16;
             if (a.batch_stats) {
-                td_fwd_body<1, NW>(S, d, a.vars, A, st, in, out, ld, n, inv_cnt, false, true);
+                td_fwd_body<1, NW>(S, d, a.vars, A, st, in, out, ld, n, inv_cnt);
                 grid.sync();
                 td_fwd_body<2, NW>(S, d, a.vars, A, st, in, out, ld, n, inv_cnt, true);
                 grid.sync();
@@ -1037,7 +1109,7 @@ td_step_kernel(const TdStepArgs a) {
             const float* A = a.Amat + op.cidx * 16;
             const double* st = a.stats + op.cidx * 16;
             double* cgr = a.cgrads + (long long)op.cidx * NF_G_COUPLING_DOUBLES;
-            td_b1_body<NW>(S, d, a.vars, A, st, zin, (const float4*)gA, (float4*)gzp, (float4*)scratch, n, inv_n, inv_cnt, cgr, true);
+            td_b1_body<NW>(S, d, a.vars, A, st, zin, (const float4*)gA, (float4*)gzp, (float4*)scratch, n, inv_n, inv_cnt, cgr);
             if (a.batch_stats) grid.sync(); else __syncthreads();      // BatchNorm-2 backward sums over the whole batch
             td_b2_body<NW>(S, d, a.vars, A, st, zin, (float4*)scratch, n, inv_cnt, cgr, true);
             if (a.batch_stats) grid.sync(); else __syncthreads();      // BatchNorm-1 backward sums
@@ -1075,7 +1147,7 @@ struct nf_trainer {
     int64_t dbl_len = 0;
     // CUDA-graph replay of the loss+gradient launch sequence: inputs are staged into trainer-owned buffers so the
     // captured pointers never change; the graph is re-captured only when (n, row, mode, reduce buffer) change
-    int cta_warps = 0;            // 0 = automatic (16 when n <= #SMs, else 8); 8 / 16 = forced (nf_trainer_set_cta_warps)
+    int cta_warps = 0;            // 0 = automatic (= 8); 8 / 16 = forced (nf_trainer_set_cta_warps)
     int fused = 1;                // 1 = one cooperative kernel per loss+gradient when the batch is co-resident (nf_trainer_set_fused)
     int coop_cap[2] = {-1, -1};   // co-resident CTAs of td_step_kernel<8>, <16> (-1 = not queried yet)
     int last_launches = 0, last_mode = -1;   // kernels enqueued by the last loss+gradient, and its batch_stats flag
@@ -1246,8 +1318,7 @@ static int td_enqueue(nf_trainer* t, const float* x, const float* y, const int32
     const float inv_n = 1.f / (float)n;
     const unsigned grid = (unsigned)n;
     const size_t smem = sizeof(nf::TdSmem);
-    // no more patches than SMs (the reference trains on 138 per step): give every patch 16 warps, one CTA per SM
-    const bool wide_cta = t->cta_warps == 16 || (t->cta_warps == 0 && n <= (int64_t)t->sm_count);
+    const bool wide_cta = t->cta_warps == 16;      // automatic = 8: four rows per warp amortise every weight load (0.465 vs 0.489 ms at 138)
     for (int i = 0; i < G; ++i)
         if (t->prog.ops[i].o.kind == NF_TOP_SCALE && t->prog.ops[i].o.token != NF_TOKEN_GAIN4 && !y)
             return nf::set_error(NF_ERR_INVALID, "nf_trainer_loss_and_grad", "clean patch y is required by an sdn layer");
@@ -1277,7 +1348,7 @@ static int td_enqueue(nf_trainer* t, const float* x, const float* y, const int32
                                                 dim3(grid), dim3(wide_cta ? 512 : 256), kargs, smem, s));
             cudaError_t e = nf::launch_reduce(d_nll, d_sdz, n, red + t->n_vars, s);
             if (e != cudaSuccess) return nf::set_error(NF_ERR_CUDA, "reduce launch", cudaGetErrorString(e));
-            nf::td_chain_kernel<<<1, 320, 0, s>>>(t->d_prog, t->d_vars, d_cg, d_sg, d_stats, inv_cnt, batch_stats ? 1 : 0, t->n_vars, red);
+            nf::td_chain_kernel<<<1, 512, 0, s>>>(t->d_prog, t->d_vars, d_cg, d_sg, d_stats, inv_cnt, batch_stats ? 1 : 0, t->n_vars, red);
             TD_CUDA(cudaGetLastError());
             t->last_launches = 3;
             return NF_OK;
@@ -1343,7 +1414,7 @@ static int td_enqueue(nf_trainer* t, const float* x, const float* y, const int32
         }
         float* tmp = gA; gA = gB; gB = tmp;
     }
-    nf::td_chain_kernel<<<1, 320, 0, s>>>(t->d_prog, t->d_vars, d_cg, d_sg, d_stats, inv_cnt, batch_stats ? 1 : 0, t->n_vars, red);
+    nf::td_chain_kernel<<<1, 512, 0, s>>>(t->d_prog, t->d_vars, d_cg, d_sg, d_stats, inv_cnt, batch_stats ? 1 : 0, t->n_vars, red);
     TD_CUDA(cudaGetLastError());
     return NF_OK;
 }
