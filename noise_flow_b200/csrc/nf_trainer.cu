@@ -53,7 +53,8 @@ struct TdCoupling {
 
 struct __align__(16) TdSmem {
     NfTrainCoupling P;                     // raw parameters + BatchNorm statistics in force
-    float acc[NF_G_COUPLING_DOUBLES];      // CTA-level partial sums, NF_G_* layout
+    float acc[16][NF_G_COUPLING_DOUBLES];  // per-warp partial sums, NF_G_* layout (a warp owns its row: no shared atomics)
+    float red[16];                         // per-warp scratch of the log-det sum
     float4 zp[NF_PIXELS];                  // z' = z_in . A
     float4 c1[NF_PIXELS];                  // conv-1 output of the resident patch (kept across the passes of the fused kernel)
     float4 h2[34 * 34];                    // padded h2 image (ring = 0)
@@ -88,11 +89,12 @@ __device__ __forceinline__ float warp_reduce_to_lanes(const float (&v)[K], int l
     }
     return x[0];      // lane l: total of v[l % P]
 }
-// CTA-level accumulation of K consecutive slots: one shared-memory atomic instruction per warp (lane l -> slot l)
+// accumulation of K consecutive slots into THIS WARP'S row of partial sums (lane l -> slot l; shared-memory float atomics are
+// CAS loops on this architecture and were 6 % of the fused kernel's stall samples); td_flush adds the rows in a fixed order
 template <int K>
-__device__ __forceinline__ void cta_acc_vec(float* acc, const float (&v)[K], int lane) {
+__device__ __forceinline__ void cta_acc_vec(float* acc_row, const float (&v)[K], int lane) {
     const float tot = warp_reduce_to_lanes<K>(v, lane);
-    if (lane < K && tot != 0.f) atomicAdd(acc + lane, tot);
+    if (lane < K) acc_row[lane] += tot;
 }
 __device__ __forceinline__ bool on_ring(int k) {
     const int R = k / 34, C = k - R * 34;
@@ -112,7 +114,7 @@ __device__ __forceinline__ void td_conv1_rows(TdSmem& S, int warp, int lane) {
     for (int k = 0; k < R; ++k)
 #pragma unroll
         for (int o = 0; o < 4; ++o) acc[k][o] = S.P.b1[o];
-#pragma unroll
+#pragma unroll 1
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
@@ -163,7 +165,7 @@ __device__ __forceinline__ void td_conv3_rows(const TdSmem& S, int warp, int lan
     for (int k = 0; k < R; ++k)
 #pragma unroll
         for (int o = 0; o < 4; ++o) pre[k][o] = S.P.b3[o];
-#pragma unroll
+#pragma unroll 1
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
@@ -192,7 +194,7 @@ __device__ __forceinline__ void td_conv3t_rows(const TdSmem& S, int warp, int la
     for (int k = 0; k < R; ++k)
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) gh[k][ci] = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
@@ -213,7 +215,7 @@ __device__ __forceinline__ void td_conv1t_rows(const TdSmem& S, int warp, int la
     constexpr int R = 32 / NW;
 #pragma unroll
     for (int k = 0; k < R; ++k) gx0[k][0] = gx0[k][1] = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
@@ -244,7 +246,7 @@ __device__ void td_load_params(TdSmem& S, const TdCoupling& d, const float* __re
         for (int k = t; k < 180; k += blockDim.x) w3[k] = vars[d.off_w3 + k];
         if (t < 16) (&S.P.A[0][0])[t] = d.has_mix ? __ldcg(A + t) : ((t >> 2) == (t & 3) ? 1.f : 0.f);
     }
-    for (int k = t; k < NF_G_COUPLING_DOUBLES; k += blockDim.x) S.acc[k] = 0.f;
+    for (int k = t; k < (int)(blockDim.x >> 5) * NF_G_COUPLING_DOUBLES; k += blockDim.x) (&S.acc[0][0])[k] = 0.f;
     if (t < 4) {
         if (!reuse) {
             S.P.b1[t] = vars[d.off_b1 + t];
@@ -288,7 +290,8 @@ __device__ __forceinline__ void td_load_mixed(TdSmem& S, const float4* zin, int 
 __device__ __forceinline__ void td_flush(TdSmem& S, double* dst, int lo, int hi) {
     __syncthreads();
     for (int k = lo + (int)threadIdx.x; k < hi; k += blockDim.x) {
-        const float v = S.acc[k];
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += S.acc[w][k];
         if (v != 0.f) atomicAdd(dst + k, (double)v);
     }
 }
@@ -323,7 +326,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
 #pragma unroll
                 for (int o = 0; o < 4; ++o) { s[o] += c1[o]; q[o] = fmaf(c1[o], c1[o], q[o]); }
             }
-            { const float v8[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]}; cta_acc_vec<8>(S.acc, v8, lane); }
+            { const float v8[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]}; cta_acc_vec<8>(S.acc[warp], v8, lane); }
         } else if (STAGE == 2) {
             float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
             for (int r = warp; r < 32; r += NW) {
@@ -340,7 +343,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
                     q[o] = fmaf(c2, c2, q[o]);
                 }
             }
-            { const float v8[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]}; cta_acc_vec<8>(S.acc + 8, v8, lane); }
+            { const float v8[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]}; cta_acc_vec<8>(S.acc[warp] + 8, v8, lane); }
         } else {
             for (int r = warp; r < 32; r += NW) {
                 float c1hat[4], h1[4], c2hat[4];
@@ -362,11 +365,11 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
                 lsum += ls0 + ls1;
             }
             lsum = tw_sum(lsum);                      // deterministic: fixed tree per warp, warps added in order
-            if (lane == 0) S.acc[16 + warp] = lsum;
+            if (lane == 0) S.red[warp] = lsum;
             __syncthreads();
             if (threadIdx.x == 0) {
                 float tot = 0.f;
-                for (int w = 0; w < NW; ++w) tot += S.acc[16 + w];
+                for (int w = 0; w < NW; ++w) tot += S.red[w];
                 ld[p] += tot;
             }
         }
@@ -436,7 +439,7 @@ td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
         {   // slots NF_G_B3 .. NF_G_SCALE are consecutive: b3[4], logs[4], scale
             static_assert(NF_G_LOGS == NF_G_B3 + 4 && NF_G_SCALE == NF_G_B3 + 8, "gradient block layout");
             const float v9[9] = {g_b3[0], g_b3[1], g_b3[2], g_b3[3], g_logs[0], g_logs[1], g_logs[2], g_logs[3], g_scale};
-            cta_acc_vec<9>(S.acc + NF_G_B3, v9, lane);
+            cta_acc_vec<9>(S.acc[warp] + NF_G_B3, v9, lane);
         }
         // grad W3[dy][dx][ci][o] = sum_pixels in(r+dy, c+dx)[ci] * g_pre3(r, c)[o]   (ci = 4: ring indicator)
         for (int dy = 0; dy < 3; ++dy)
@@ -455,7 +458,7 @@ td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
 #pragma unroll
                         for (int o = 0; o < 4; ++o) a[ci * 4 + o] = fmaf(hv[ci], gv[o], a[ci * 4 + o]);
                 }
-                cta_acc_vec<20>(S.acc + NF_G_W3 + (dy * 3 + dx) * 20, a, lane);
+                cta_acc_vec<20>(S.acc[warp] + NF_G_W3 + (dy * 3 + dx) * 20, a, lane);
             }
         // g_h2(r, c)[ci] = sum_{dy,dx,o} W3[dy][dx][ci][o] * g_pre3(r-dy+1, c-dx+1)[o] ; ReLU mask ; BatchNorm-2 sums
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -476,7 +479,7 @@ td_b1_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
             }
             scratch[p * NF_PIXELS + r * 32 + lane] = make_float4(gc[0], gc[1], gc[2], gc[3]);
         }
-        { const float v8[8] = {s1[0], s1[1], s1[2], s1[3], s2[0], s2[1], s2[2], s2[3]}; cta_acc_vec<8>(S.acc + NF_G_BN2, v8, lane); }
+        { const float v8[8] = {s1[0], s1[1], s1[2], s1[3], s2[0], s2[1], s2[2], s2[3]}; cta_acc_vec<8>(S.acc[warp] + NF_G_BN2, v8, lane); }
         __syncthreads();
     }
     td_flush(S, grads, 0, NF_G_COUPLING_DOUBLES);
@@ -543,9 +546,9 @@ td_b2_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
                 for (int o = 0; o < 4; ++o) v20[i * 4 + o] = gw2[i][o];
                 v20[16 + i] = gb2[i];
             }
-            cta_acc_vec<20>(S.acc + NF_G_W2, v20, lane);
+            cta_acc_vec<20>(S.acc[warp] + NF_G_W2, v20, lane);
             const float v8[8] = {t1[0], t1[1], t1[2], t1[3], t2[0], t2[1], t2[2], t2[3]};
-            cta_acc_vec<8>(S.acc + NF_G_BN1, v8, lane);
+            cta_acc_vec<8>(S.acc[warp] + NF_G_BN1, v8, lane);
         }
         __syncthreads();
     }
@@ -594,7 +597,7 @@ td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
             S.g[(r + 1) * 34 + lane + 1] = make_float4(gc1[0], gc1[1], gc1[2], gc1[3]);
         }
         __syncthreads();
-        cta_acc_vec<4>(S.acc + NF_G_B1, gb1, lane);
+        cta_acc_vec<4>(S.acc[warp] + NF_G_B1, gb1, lane);
         // grad W1[dy][dx][ci][o] = sum_pixels x0(r+dy-1, c+dx-1)[ci] * g_c1(r, c)[o]
         for (int dy = 0; dy < 3; ++dy) {
             float a[24];                // [dx][ci][o]: the 24 consecutive slots of filter row dy
@@ -616,7 +619,7 @@ td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
                     }
                 }
             }
-            cta_acc_vec<24>(S.acc + NF_G_W1 + dy * 24, a, lane);
+            cta_acc_vec<24>(S.acc[warp] + NF_G_W1 + dy * 24, a, lane);
         }
         // g_x0 (transposed conv), complete g_z', grad A, G_in
         float gA[4][4];
@@ -652,7 +655,7 @@ td_b3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int o = 0; o < 4; ++o) v16[i * 4 + o] = gA[i][o];
-            cta_acc_vec<16>(S.acc + NF_G_A, v16, lane);
+            cta_acc_vec<16>(S.acc[warp] + NF_G_A, v16, lane);
         }
         __syncthreads();
     }
