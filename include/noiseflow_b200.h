@@ -135,8 +135,9 @@ int nf_reduce_sums(const float* nll, const float* sdz, int64_t n, double* sums, 
 /* The whole chain with BATCH-STATISTICS BatchNorm -- the reference's is_training == True path
  * (batch_norm, layers.py:388-398), which is what NoiseFlowWrapper.sample_noise_nf feeds
  * (NoiseFlowWrapper.py:85-86) and what train_thread runs (train_noise_flow.py:64-71).  Patches are not
- * independent in this mode, so the chain executes layer by layer: every coupling is probed twice (batch mean /
- * population variance of its conv-1 and conv-2 outputs) and then applied with those statistics.
+ * independent in this mode: every coupling is probed twice (batch mean / population variance of its conv-1 and
+ * conv-2 outputs) and then applied with those statistics -- layer by layer, or, for small batches, inside one
+ * cooperative kernel (nf_model_set_bs_small).
  * direction 0: x -> z, outputs as nf_log_prob / nf_inverse; direction 1: z = in * temp (in == NULL: Philox
  * as nf_sample) -> x.  `out` ([n][32][32][4], required) doubles as the in-place state buffer; stats_ws is a
  * device double[8] scratch.  batch_stats_host (optional, host) receives [n_couplings][16] =
@@ -146,6 +147,10 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
                          int32_t default_row, int64_t n, float temp, uint64_t seed, uint64_t offset,
                          uint64_t patch_base, float* out, float* logdet, float* nll, float* sdz, double* stats_ws,
                          float* batch_stats_host, void* stream);
+/* 1 (default): nf_chain_batch_stats runs batches of up to one co-resident CTA per patch (296 patches on a B200; width-4
+ * chains of [1x1 conv / permutation +] coupling groups and scale layers) as ONE cooperative kernel -- the reference
+ * sampling script's call pattern is one patch per sess.run (sample_noise_flow.py:44,71); 0: always layer by layer. */
+int nf_model_set_bs_small(nf_model* m, int enable);
 
 /* ---- training step support: loss and its gradient (train_noise_flow.py:187-198, 50-77) -------------------- */
 /* Gradient layout on the host: one block per bijector in add order, offsets[l] .. offsets[l+1] (doubles):

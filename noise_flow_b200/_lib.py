@@ -51,6 +51,7 @@ SIGNATURES = {
     "nf_model_set_affine_coupling": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(NfCouplingWeights)]),
     "nf_model_set_scale": (C.c_int, [C.c_void_p, C.c_int, c_float_p, C.c_int]),
     "nf_model_set_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "nf_model_set_bs_small": (C.c_int, [C.c_void_p, C.c_int]),
     "nf_model_set_tensor_cores": (C.c_int, [C.c_void_p, C.c_int]),
     "nf_log_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

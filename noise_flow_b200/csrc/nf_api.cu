@@ -76,6 +76,7 @@ struct nf_model {
     bool finalized = false;
     int warps_per_cta = NF_MAX_WARPS_PER_CTA;
     int use_tc = 0;              // 1: coupling convolutions on the tensor cores (nf_tc.cu) where supported
+    int bs_small = 1;            // 1: nf_chain_batch_stats runs small batches as one cooperative kernel (nf_model_set_bs_small)
     int num_ctas = 0;
     int sm_count = 0;
     NfModelParams full = {};     // fused program of the whole chain
@@ -697,6 +698,12 @@ int nf_model_set_tensor_cores(nf_model* m, int enable) {
     return NF_OK;
 }
 
+int nf_model_set_bs_small(nf_model* m, int enable) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    m->bs_small = enable ? 1 : 0;
+    return NF_OK;
+}
+
 // ---- hot path -------------------------------------------------------------------------------------
 int nf_log_prob(const nf_model* m, const float* x, const float* y, const int32_t* rows, int32_t default_row, int64_t n,
                 float* nll, float* sdz, float* z, void* stream) {
@@ -911,6 +918,118 @@ int nf_sample_host(const nf_model* cm, const float* y_host, const int32_t* rows_
     return NF_OK;
 }
 
+// ---- batch-statistics BatchNorm, small batches: the whole chain as ONE cooperative kernel ----------------
+// (nf_trainer.cu: td_bs_chain_kernel).  Used by nf_chain_batch_stats when every patch can own a co-resident CTA (296 on a
+// B200) and the chain is made of [mix +] coupling groups and scale layers at width 4; everything else takes the
+// layer-by-layer path below.  The parameter image (raw TF-layout weights, matrices, tables) is rebuilt from the handle on
+// every call -- 12 KB, and it makes the call independent of concurrent callers and of nf_model_set_* updates.
+static int chain_batch_stats_small(const nf_model* m, const std::vector<std::pair<int, int>>& groups, bool inverse, const float* in,
+                                   const float* y, const int32_t* rows, int32_t default_row, int64_t n, float temp, uint64_t seed,
+                                   uint64_t offset, uint64_t patch_base, float* out, float* logdet, float* nll, float* sdz,
+                                   float* batch_stats_host, cudaStream_t stream) {
+    std::vector<nf::BsOp> ops;
+    std::vector<float> vars, amat, tables;
+    std::vector<int> cp_add_index;      // coupling (in execution order) -> its index in add order
+    double ldj_const = 0.0;
+    {
+        std::lock_guard<std::mutex> lock(m->prog_mu);
+        for (const auto& g : groups) {
+            const Layer& L = m->layers[g.second - 1];
+            nf::BsOp op = {};
+            if (L.kind == L_COUPLING) {
+                op.kind = 0;
+                op.cidx = (int)cp_add_index.size();
+                int idx = 0;
+                for (int l = 0; l < g.second - 1; ++l) idx += m->layers[l].kind == L_COUPLING;
+                cp_add_index.push_back(idx);
+                auto push = [&](const float* p, int k) { const int o = (int)vars.size(); vars.insert(vars.end(), p, p + k); return o; };
+                nf::TdCoupling& d = op.d;
+                d.off_w1 = push(L.raw.l1_w, 72); d.off_b1 = push(L.raw.l1_b, 4);
+                d.off_w2 = push(L.raw.l2_w, 16); d.off_b2 = push(L.raw.l2_b, 4);
+                d.off_w3 = push(L.raw.last_w, 180); d.off_b3 = push(L.raw.last_b, 4);
+                d.off_logs = push(L.raw.last_logs, 4); d.off_scale = push(&L.raw.rescaling_scale, 1);
+                d.off_bn[0] = push(L.raw.bn1_mean, 4); d.off_bn[1] = push(L.raw.bn1_var, 4);
+                d.off_bn[2] = push(L.raw.bn2_mean, 4); d.off_bn[3] = push(L.raw.bn2_var, 4);
+                d.has_mix = g.second - g.first == 2;
+                d.batch_stats = 1;
+                d.bn_eps = L.raw.bn_eps;
+                float A[16];
+                for (int k = 0; k < 16; ++k) A[k] = (k >> 2) == (k & 3) ? 1.f : 0.f;
+                if (d.has_mix) {
+                    const Layer& M = m->layers[g.first];
+                    for (int i = 0; i < 4; ++i)
+                        for (int o = 0; o < 4; ++o) A[i * 4 + o] = inverse ? M.a[o][i] : M.ainv[o][i];     // [in][out]
+                    ldj_const += (double)NF_PIXELS * M.log_abs_det;
+                }
+                amat.insert(amat.end(), A, A + 16);
+            } else {
+                op.kind = 1;
+                op.sidx = (int)(tables.size() / (NF_MAX_ROWS * 2));
+                op.is_sdn = L.scale_kind == NF_SCALE_SDN;
+                op.full_sum = L.full_sum;
+                for (int r = 0; r < NF_MAX_ROWS; ++r) { tables.push_back(L.table[r][0]); tables.push_back(op.is_sdn ? L.table[r][1] : 0.f); }
+            }
+            ops.push_back(op);
+        }
+    }
+    const size_t n_cp = cp_add_index.size();
+    // one stream-ordered allocation: [stats 16 n_cp doubles][consts 1 double][ops][vars][amat][tables]
+    auto up8 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t o_stats = 0, o_consts = o_stats + 16 * n_cp * sizeof(double), o_ops = up8(o_consts + sizeof(double)),
+                 o_vars = up8(o_ops + ops.size() * sizeof(nf::BsOp)), o_amat = up8(o_vars + vars.size() * sizeof(float)),
+                 o_tab = up8(o_amat + amat.size() * sizeof(float)), total = up8(o_tab + tables.size() * sizeof(float)) + 16;
+    // host image of everything behind the statistics: ONE upload
+    std::vector<unsigned char> img(total - o_consts, 0);
+    auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) memcpy(img.data() + (off - o_consts), src, bytes); };
+    put(o_consts, &ldj_const, sizeof(double));
+    put(o_ops, ops.data(), ops.size() * sizeof(nf::BsOp));
+    put(o_vars, vars.data(), vars.size() * sizeof(float));
+    put(o_amat, amat.data(), amat.size() * sizeof(float));
+    put(o_tab, tables.data(), tables.size() * sizeof(float));
+    unsigned char* blob = nullptr;
+    NF_CUDA(cudaMallocAsync((void**)&blob, total, stream));
+    int rc = NF_OK;
+    std::vector<double> hst(16 * n_cp + 1);
+    do {
+        cudaError_t e;
+        if ((e = cudaMemsetAsync(blob, 0, o_consts, stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(blob + o_consts, img.data(), img.size(), cudaMemcpyHostToDevice, stream)) != cudaSuccess) {   // pageable: staged before return
+            rc = fail(NF_ERR_CUDA, "small-batch chain upload: %s", cudaGetErrorString(e));
+            break;
+        }
+        nf::BsArgs a = {};
+        a.ops = (const nf::BsOp*)(blob + o_ops); a.n_ops = (int)ops.size(); a.direction = inverse ? 0 : 1;
+        a.vars = (const float*)(blob + o_vars); a.Amat = (const float*)(blob + o_amat); a.tables = (const float*)(blob + o_tab);
+        a.stats = (double*)(blob + o_stats); a.consts = (const double*)(blob + o_consts);
+        a.in = in; a.y = y; a.rows = rows; a.default_row = default_row; a.n = n; a.out = out;
+        a.nll = inverse ? nll : nullptr; a.sdz = inverse ? sdz : nullptr; a.logdet = inverse ? logdet : nullptr;
+        a.ld = inverse ? (logdet ? logdet : nll) : nullptr;      // running log-det (nll doubles as scratch), zeroed below
+        a.temp = temp; a.seed = seed; a.offset = offset; a.patch_base = patch_base;
+        if (a.ld && (e = cudaMemsetAsync(a.ld, 0, (size_t)n * sizeof(float), stream)) != cudaSuccess) { rc = fail(NF_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); break; }
+        if ((e = nf::launch_bs_small(a, stream)) != cudaSuccess) { rc = fail(NF_ERR_CUDA, "small-batch chain launch: %s", cudaGetErrorString(e)); break; }
+        if ((e = cudaMemcpyAsync(hst.data(), blob + o_stats, 16 * n_cp * sizeof(double), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) { rc = fail(NF_ERR_CUDA, "statistics read-back: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    cudaFreeAsync(blob, stream);
+    cudaError_t es = cudaStreamSynchronize(stream);
+    if (rc) return rc;
+    if (es != cudaSuccess) return fail(NF_ERR_CUDA, "small-batch chain: %s", cudaGetErrorString(es));
+    if (batch_stats_host) {
+        const double cnt = (double)n * NF_PIXELS;
+        for (size_t c = 0; c < n_cp; ++c) {
+            float* dst = batch_stats_host + 16 * (size_t)cp_add_index[c];      // {mean1[4], var1[4], mean2[4], var2[4]}
+            for (int st = 0; st < 2; ++st)
+                for (int k = 0; k < 4; ++k) {
+                    const double mean = hst[16 * c + 8 * st + k] / cnt;
+                    double var = hst[16 * c + 8 * st + 4 + k] / cnt - mean * mean;     // population variance (tf.nn.moments)
+                    if (var < 0.0) var = 0.0;
+                    dst[8 * st + k] = (float)mean;
+                    dst[8 * st + 4 + k] = (float)var;
+                }
+        }
+    }
+    return NF_OK;
+}
+
 // ---- batch-statistics BatchNorm: layer-by-layer execution ----------------------------------------------
 // Reference: batch_norm(training=True) normalises every coupling-net activation with the statistics of the
 // CURRENT batch (layers.py:388-398), which makes patches interdependent: 16 batch-wide reductions per
@@ -937,6 +1056,17 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
         else { groups.push_back({l, l + 1}); l += 1; }
     }
     if (!inverse) std::reverse(groups.begin(), groups.end());
+    if (W == 4 && m->bs_small && !(direction == 1 && logdet) && n <= (int64_t)nf::bs_small_capacity(cached_sm_count())) {
+        bool ok = true;       // [mix +] coupling groups and scale layers only
+        for (const auto& g : groups) {
+            const int k = m->layers[g.second - 1].kind;
+            ok = ok && (k == L_COUPLING || (k == L_SCALE && g.second - g.first == 1));
+            if (k == L_SCALE && m->layers[g.second - 1].scale_kind == NF_SCALE_SDN && !y) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
+        }
+        if (ok)
+            return chain_batch_stats_small(m, groups, inverse, in, y, rows, default_row, n, temp, seed, offset, patch_base, out, logdet, nll,
+                                           sdz, batch_stats_host, stream);
+    }
     float* run_ld = logdet ? logdet : nll;   // running log-det (nll doubles as scratch until the last launch)
     const bool want_ld = run_ld != nullptr;
     const double cnt = (double)n * NF_PIXELS;

@@ -55,4 +55,40 @@ cudaError_t launch_train_scale(const float* zout, const float* y, const float* g
 cudaError_t launch_train_mix(const float* zin, const float* gout, float* gin, long long n, const NfTrainMix& M, double* grads,
                              int num_sms, cudaStream_t s);
 cudaError_t launch_train_prior(const float* z, float* g, long long n, int num_sms, cudaStream_t s);
+
+// launch descriptor of one coupling: offsets into the flat variable array (constant from step to step)
+struct TdCoupling {
+    int32_t off_w1, off_b1, off_w2, off_b2, off_w3, off_b3, off_logs, off_scale;
+    int32_t off_bn[4];          // moving mean1, var1, mean2, var2
+    int32_t has_mix;            // A comes from the derived-matrix buffer
+    int32_t batch_stats;
+    float bn_eps;
+    int32_t pad_;
+};
+
+// ---- small-batch chain with batch-statistics BatchNorm as one cooperative kernel (nf_trainer.cu: td_bs_chain_kernel)
+struct BsOp {
+    int32_t kind;               // 0 = coupling (+ the mix in front of it), 1 = scale layer
+    int32_t cidx, sidx;         // statistics / matrix index, table index
+    int32_t is_sdn, full_sum;
+    int32_t pad_[3];
+    TdCoupling d;               // offsets into the flat parameter array
+};
+struct BsArgs {
+    const BsOp* ops;
+    int32_t n_ops, direction;
+    const float *vars, *Amat, *tables;          // Amat: [n_couplings][in][out], A (direction 0) or A^-1 (direction 1)
+    double* stats;                              // [n_couplings][16], zeroed
+    const double* consts;                       // [0] = constant log-det of the chain
+    const float *in, *y;
+    const int32_t* rows;
+    int32_t default_row, pad_;
+    long long n;
+    float *out, *ld, *nll, *sdz, *logdet;       // ld: [n] zeroed scratch (may alias nll or logdet); the rest as NfChainArgs
+    float temp, pad2_;
+    unsigned long long seed, offset, patch_base;
+};
+
+int bs_small_capacity(int sm_count);                       // patches that can own a co-resident CTA (0: unavailable)
+cudaError_t launch_bs_small(const BsArgs& a, cudaStream_t s);
 }  // namespace nf

@@ -33,6 +33,7 @@
 #include "nf_params.h"
 #include "nf_train.h"
 #include "nf_train_common.cuh"
+#include "nf_rng.cuh"
 
 namespace nf {
 
@@ -40,16 +41,6 @@ namespace nf {
 #define TD_WARPS (TD_THREADS / 32)
 #define TD_MAX_OPS 40
 #define TD_BN_MOMENTUM 0.1f     // layers.py:394-395
-
-// launch descriptor of one coupling: offsets into the flat variable array (constant from step to step)
-struct TdCoupling {
-    int32_t off_w1, off_b1, off_w2, off_b2, off_w3, off_b3, off_logs, off_scale;
-    int32_t off_bn[4];          // moving mean1, var1, mean2, var2
-    int32_t has_mix;            // A comes from the derived-matrix buffer
-    int32_t batch_stats;
-    float bn_eps;
-    int32_t pad_;
-};
 
 struct __align__(16) TdSmem {
     NfTrainCoupling P;                     // raw parameters + BatchNorm statistics in force
@@ -370,7 +361,7 @@ td_fwd_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, cons
             if (threadIdx.x == 0) {
                 float tot = 0.f;
                 for (int w = 0; w < NW; ++w) tot += S.red[w];
-                ld[p] += tot;
+                if (ld) ld[p] += tot;
             }
         }
         __syncthreads();
@@ -707,7 +698,7 @@ td_scale_fwd_body(float* sh, const float* table, int is_sdn, int full_sum, const
             }
         }
         const float tot = cta_sum_det(lsum, sh, warp, lane);
-        if (threadIdx.x == 0) ld[p] += is_sdn ? tot : -(full_sum ? (float)NF_DIMS : 1.f) * logf(a);
+        if (threadIdx.x == 0 && ld) ld[p] += is_sdn ? tot : -(full_sum ? (float)NF_DIMS : 1.f) * logf(a);
     }
 }
 __global__ void __launch_bounds__(TD_THREADS)
@@ -780,18 +771,18 @@ td_nll_body(float* sh, const float4* z, const float* ld, const double* consts, f
             const float4 v = z[p * NF_PIXELS + k];
             s1 += v.x + v.y + v.z + v.w;
             s2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-            g[p * NF_PIXELS + k] = make_float4(v.x * inv_n, v.y * inv_n, v.z * inv_n, v.w * inv_n);
+            if (g) g[p * NF_PIXELS + k] = make_float4(v.x * inv_n, v.y * inv_n, v.z * inv_n, v.w * inv_n);
         }
         const float t1 = cta_sum_det(s1, sh, warp, lane);
         const float t2 = cta_sum_det(s2, sh, warp, lane);
         if (threadIdx.x == 0) {
             const double S1 = t1, S2 = t2;
             const double logp = -0.5 * ((double)NF_DIMS * 1.8378770664093453 + S2);
-            nll[p] = (float)(-((double)ld[p] + __ldcg(consts) + logp));
+            if (nll) nll[p] = (float)(-((double)ld[p] + __ldcg(consts) + logp));
             const double mean = S1 / NF_DIMS;
             double var = S2 / NF_DIMS - mean * mean;
             if (var < 0.0) var = 0.0;
-            sdz[p] = (float)sqrt(var);
+            if (sdz) sdz[p] = (float)sqrt(var);
         }
     }
 }
@@ -1124,6 +1115,161 @@ td_step_kernel(const TdStepArgs a) {
         __syncthreads();
         float* tmp = gA; gA = gB; gB = tmp;
     }
+}
+
+// ---------------------------------------------------------------------------------------------- small-batch chain, batch statistics
+// nf_chain_batch_stats (NoiseFlow / NoiseFlowWrapper with is_training == True) for batches that fit one co-resident CTA per
+// patch: the whole chain, both BatchNorm probes of every coupling included, as ONE cooperative kernel built from the pass
+// bodies above -- instead of three launches, two device-to-host copies and two stream synchronisations per coupling.  This is
+// the reference sampling script's call pattern (sample_noise_flow.py:44,71: batch_size = 1, one sess.run per patch).
+//   direction 0 (data -> latent): per op F1 | F2 | F3 exactly as the trainer's forward, then prior / NLL.
+//   direction 1 (latent -> data): ops arrive reversed; a coupling's net sees its INPUT's first two channels (they pass
+//     through unchanged), so F1 / F2 run unchanged on the un-mixed patch, then x1 = (y1 - shift) exp(-ls) and the 1x1 conv /
+//     permutation is applied last with the inverse matrix.
+// last stage of a coupling in the sampling direction: y1 -> (y1 - shift) * exp(-ls), then the mix with the inverse matrix
+template <int NW>
+__device__ __forceinline__ void td_sample3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* Ainv,
+                                                int has_mix, const double* stats, float4* zout, float* ld, long long n, double inv_cnt) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    td_load_params(S, d, vars, nullptr, stats, inv_cnt, 2, true);      // weights and the (un-mixed) patch are resident
+    __shared__ float Ai[16];
+    if (threadIdx.x < 16) Ai[threadIdx.x] = has_mix ? __ldcg(Ainv + threadIdx.x) : ((threadIdx.x >> 2) == (threadIdx.x & 3) ? 1.f : 0.f);
+    __syncthreads();
+    float e3[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) e3[o] = expf(3.f * S.P.logs[o]);
+    for (long long p = blockIdx.x; p < n; p += gridDim.x) {
+        for (int k = threadIdx.x; k < 34 * 34; k += blockDim.x)
+            if (on_ring(k)) S.h2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        for (int r = warp; r < 32; r += NW) {
+            float c1hat[4], h1[4], c2hat[4];
+            td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat);
+            S.h2[(r + 1) * 34 + lane + 1] = make_float4(fmaxf(c2hat[0], 0.f), fmaxf(c2hat[1], 0.f), fmaxf(c2hat[2], 0.f), fmaxf(c2hat[3], 0.f));
+        }
+        __syncthreads();
+        float pre_rows[32 / NW][4];
+        td_conv3_rows<NW>(S, warp, lane, pre_rows);
+        float lsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32 / NW; ++k) {
+            const int r = warp + k * NW;
+            const float (&pre)[4] = pre_rows[k];
+            const float sh0 = pre[0] * e3[0], sh1 = pre[1] * e3[1];
+            const float ls0 = S.P.scale * tanhf(pre[2] * e3[2]), ls1 = S.P.scale * tanhf(pre[3] * e3[3]);
+            const float4 zp = S.zp[r * 32 + lane];
+            float4 v = make_float4(zp.x, zp.y, (zp.z - sh0) * expf(-ls0), (zp.w - sh1) * expf(-ls1));     // layers.py:296-301
+            if (has_mix) v = mix_fwd(v, Ai);
+            zout[p * NF_PIXELS + r * 32 + lane] = v;
+            lsum -= ls0 + ls1;
+        }
+        if (ld) {
+            lsum = tw_sum(lsum);
+            if (lane == 0) S.red[warp] = lsum;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float tot = 0.f;
+                for (int w = 0; w < NW; ++w) tot += S.red[w];
+                ld[p] += tot;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// scale layer in the sampling direction: z * scale (AffineCouplingSdnEx5._forward etc.)
+__device__ __forceinline__ void td_scale_sample_body(const float* table, int is_sdn, const float4* zin, const float4* __restrict__ y,
+                                                     float4* zout, const int* __restrict__ rows, int default_row, long long n) {
+    for (long long p = blockIdx.x; p < n; p += gridDim.x) {
+        int row = rows ? rows[p] : default_row;
+        row = min(max(row, 0), NF_MAX_ROWS - 1);
+        const float a = __ldcg(table + row * 2), b = __ldcg(table + row * 2 + 1);
+        for (int k = threadIdx.x; k < NF_PIXELS; k += blockDim.x) {
+            const long long idx = p * NF_PIXELS + k;
+            const float4 z = zin[idx];
+            if (is_sdn) {
+                const float4 yv = y[idx];
+                zout[idx] = make_float4(z.x * sqrtf(fmaf(a, yv.x, b)), z.y * sqrtf(fmaf(a, yv.y, b)), z.z * sqrtf(fmaf(a, yv.z, b)),
+                                        z.w * sqrtf(fmaf(a, yv.w, b)));
+            } else {
+                zout[idx] = make_float4(z.x * a, z.y * a, z.z * a, z.w * a);
+            }
+        }
+    }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 2)
+td_bs_chain_kernel(const BsArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TdSmem& S = *reinterpret_cast<TdSmem*>(smem_raw);
+    __shared__ float sh[16];
+    const long long n = a.n;
+    const double inv_cnt = 1.0 / ((double)n * NF_PIXELS);
+    const float4* cur = (const float4*)a.in;
+    float4* out = (float4*)a.out;
+    if (a.direction == 1) {     // z = eps * temp (noise_flow_model.py:499-504); eps given or Philox4x32-10 as nf_sample
+        for (long long p = blockIdx.x; p < n; p += gridDim.x)
+            for (int k = threadIdx.x; k < NF_PIXELS; k += blockDim.x) {
+                float4 v = cur ? cur[p * NF_PIXELS + k] : philox_normal4(a.seed, a.offset, a.patch_base + (unsigned long long)p, (unsigned int)k);
+                v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp;
+                out[p * NF_PIXELS + k] = v;
+            }
+        __syncthreads();
+        cur = out;
+    }
+    for (int i = 0; i < a.n_ops; ++i) {
+        const BsOp& op = a.ops[i];
+        if (op.kind == 0) {
+            TdCoupling d = op.d;
+            const float* A = a.Amat + op.cidx * 16;
+            double* st = a.stats + op.cidx * 16;
+            const int has_mix = d.has_mix;
+            if (a.direction == 1) d.has_mix = 0;          // the net sees the un-mixed input; the mix comes last
+            td_fwd_body<1, NW>(S, d, a.vars, A, st, cur, out, a.ld, n, inv_cnt);
+            grid.sync();
+            td_fwd_body<2, NW>(S, d, a.vars, A, st, cur, out, a.ld, n, inv_cnt, true);
+            grid.sync();
+            if (a.direction == 0) td_fwd_body<3, NW>(S, d, a.vars, A, st, cur, out, a.ld, n, inv_cnt, true);
+            else td_sample3_body<NW>(S, d, a.vars, A, has_mix, st, out, a.ld, n, inv_cnt);
+        } else if (a.direction == 0) {
+            td_scale_fwd_body(sh, a.tables + op.sidx * NF_MAX_ROWS * 2, op.is_sdn, op.full_sum, cur, (const float4*)a.y, out, a.ld, a.rows,
+                              a.default_row, n);
+        } else {
+            td_scale_sample_body(a.tables + op.sidx * NF_MAX_ROWS * 2, op.is_sdn, cur, (const float4*)a.y, out, a.rows, a.default_row, n);
+        }
+        __syncthreads();
+        cur = out;
+    }
+    if (a.direction == 0 && (a.nll || a.sdz || a.logdet)) {
+        if (a.logdet && a.logdet != a.ld)
+            for (long long p = blockIdx.x; p < n; p += gridDim.x)
+                if (threadIdx.x == 0) a.logdet[p] = a.ld[p] + (float)__ldcg(a.consts);
+        td_nll_body(sh, cur, a.ld, a.consts, nullptr, a.nll, a.sdz, n, 0.f);
+        if (a.logdet && a.logdet == a.ld) {
+            __syncthreads();
+            for (long long p = blockIdx.x; p < n; p += gridDim.x)
+                if (threadIdx.x == 0) a.logdet[p] = a.ld[p] + (float)__ldcg(a.consts);
+        }
+    }
+}
+
+int bs_small_capacity(int sm_count) {
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        if (cudaFuncSetAttribute(td_bs_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TdSmem)) != cudaSuccess) return 0;
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, td_bs_chain_kernel<8>, 256, sizeof(TdSmem)) != cudaSuccess) return 0;
+        per_sm = v;
+    }
+    return per_sm * sm_count;
+}
+
+cudaError_t launch_bs_small(const BsArgs& a, cudaStream_t s) {
+    void* kargs[] = {(void*)&a};
+    return cudaLaunchCooperativeKernel((const void*)td_bs_chain_kernel<8>, dim3((unsigned)a.n), dim3(256), kargs, sizeof(TdSmem), s);
 }
 
 }  // namespace nf

@@ -201,6 +201,13 @@ class NoiseFlow(object):
                    "nf_model_set_tensor_cores")
         return self
 
+    def set_batch_stats_fused(self, enable: bool = True):
+        """``is_training=True`` calls on small batches (one co-resident CTA per patch, <= 296 on a B200) run the whole chain
+        incl. the BatchNorm probes as ONE cooperative kernel (default); ``False`` forces the layer-by-layer path."""
+        self.build()
+        _lib.check(self._engine.lib.nf_model_set_bs_small(self._engine.handle, 1 if enable else 0), "nf_model_set_bs_small")
+        return self
+
     # ------------------------------------------------------------------ helpers
     def _check_training(self, is_training) -> bool:
         """Resolve the reference's ``is_training`` placeholder (constructor value unless overridden per call)."""

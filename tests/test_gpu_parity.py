@@ -355,6 +355,43 @@ def test_training_mode_batch_stat_bn_matches_oracle(shipped, n):
     assert np.abs(nll2.cpu().numpy() - nll2_o.numpy()).max() / 4096 < NLL_TOL_PER_DIM
 
 
+@pytest.mark.parametrize("n", [1, 5, 37, 300])
+def test_batch_stat_chain_cooperative_kernel_equals_layer_by_layer(shipped, n):
+    """Small batches run the batch-statistics chain as ONE cooperative kernel (nf_trainer.cu: td_bs_chain_kernel); larger
+    ones (300 > 296 co-resident CTAs) and `set_batch_stats_fused(False)` go layer by layer.  Both directions, injected and
+    Philox noise, per-patch (camera, ISO) rows: same results, same moving-statistics side effect, both within the oracle
+    tolerance."""
+    hps, ck = shipped
+    x, y = synth_batch(n, seed=71)
+    eps = np.random.RandomState(72).randn(n, 32, 32, 4).astype(np.float32)
+    isos = [(100.0, 400.0, 800.0, 1600.0, 3200.0)[k % 5] for k in range(n)]
+    cams = [float((k // 5) % 5) for k in range(n)]
+    res = {}
+    for fused in (True, False):
+        nf = _nf(hps, ck, first_call="inverse").set_batch_stats_fused(fused)
+        nll, sd_z, z = nf._loss(x, y, iso=[100.0], cam=[2.0], is_training=True, return_z=True)
+        stats_after_loss = {k: v.copy() for k, v in nf.variables.items() if "/bn_nvp_conv_" in k}
+        z2, obj = nf.inverse(x, torch.zeros(n, device="cuda:0"), yy=y, iso=isos, cam=cams, is_training=True)
+        xs = nf.sample(y, 0.6, y, iso=[800.0], cam=[1.0], eps=eps, is_training=True)
+        xp = nf.sample(y, 1.0, y, iso=isos, cam=cams, seed=5, offset=3, is_training=True)
+        xf = nf.forward(eps * 0.7, None, yy=y, iso=[100.0], cam=[2.0], is_training=True)
+        res[fused] = [t.cpu().numpy() for t in (nll, z, z2, obj, xs, xp, xf)] + [float(sd_z), stats_after_loss]
+    a, b = res[True], res[False]
+    assert np.abs(a[0] - b[0]).max() / 4096 < 2e-6 and abs(a[7] - b[7]) < 1e-5
+    for i in (1, 2, 4, 5, 6):
+        assert _close(a[i], b[i], rel=2e-5), i
+    assert np.abs(a[3] - b[3]).max() / 4096 < 2e-6
+    for k in a[8]:
+        assert np.allclose(a[8][k], b[8][k], rtol=1e-5, atol=1e-7), k
+    if n <= 37:
+        orc = make_oracle(hps, ck)
+        nll_o, sd_o = orc._loss(x, y, iso=[100.0], cam=[2.0], is_training=True)
+        assert np.abs(a[0] - nll_o.numpy()).max() / 4096 < NLL_TOL_PER_DIM and abs(a[7] - float(sd_o)) < 1e-4
+        assert _close(a[1], orc.last_z.numpy(), rel=1e-4)
+        xo = make_oracle(hps, ck).sample(eps, 0.6, y, iso=[800.0], cam=[1.0], is_training=True).numpy()
+        assert _close(a[4], xo, rel=1e-4)
+
+
 def test_training_mode_sampling_and_wrapper_default(golden_dir, shipped):
     """NoiseFlowWrapper.sample_noise_nf feeds is_training=True (NoiseFlowWrapper.py:85-86)."""
     from noise_flow_b200.NoiseFlowWrapper import NoiseFlowWrapper
