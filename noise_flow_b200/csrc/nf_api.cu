@@ -77,6 +77,10 @@ struct nf_model {
     int warps_per_cta = NF_MAX_WARPS_PER_CTA;
     int use_tc = 0;              // 1: coupling convolutions on the tensor cores (nf_tc.cu) where supported
     int bs_small = 1;            // 1: nf_chain_batch_stats runs small batches as one cooperative kernel (nf_model_set_bs_small)
+    // parameter-image / statistics buffers of the small-batch chain: a call takes one (or allocates it) and gives it back
+    // after its stream synchronisation, so concurrent callers never share one and no call pays for cudaMalloc
+    mutable std::mutex bs_mu;
+    mutable std::vector<std::pair<unsigned char*, size_t>> bs_free;
     int num_ctas = 0;
     int sm_count = 0;
     NfModelParams full = {};     // fused program of the whole chain
@@ -513,6 +517,7 @@ int nf_model_destroy(nf_model* m) {
     if (m->d_sums) cudaFree(m->d_sums);
     if (m->h_tmp) cudaFreeHost(m->h_tmp);
     if (m->d_wide_full) cudaFree(m->d_wide_full);
+    for (auto& b : m->bs_free) cudaFree(b.first);
     delete m;
     return NF_OK;
 }
@@ -973,7 +978,7 @@ static int chain_batch_stats_small(const nf_model* m, const std::vector<std::pai
         }
     }
     const size_t n_cp = cp_add_index.size();
-    // one stream-ordered allocation: [stats 16 n_cp doubles][consts 1 double][ops][vars][amat][tables]
+    // one device buffer: [stats 16 n_cp doubles][consts 1 double][ops][vars][amat][tables]
     auto up8 = [](size_t b) { return (b + 15) & ~(size_t)15; };
     const size_t o_stats = 0, o_consts = o_stats + 16 * n_cp * sizeof(double), o_ops = up8(o_consts + sizeof(double)),
                  o_vars = up8(o_ops + ops.size() * sizeof(nf::BsOp)), o_amat = up8(o_vars + vars.size() * sizeof(float)),
@@ -987,7 +992,13 @@ static int chain_batch_stats_small(const nf_model* m, const std::vector<std::pai
     put(o_amat, amat.data(), amat.size() * sizeof(float));
     put(o_tab, tables.data(), tables.size() * sizeof(float));
     unsigned char* blob = nullptr;
-    NF_CUDA(cudaMallocAsync((void**)&blob, total, stream));
+    size_t blob_bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(m->bs_mu);
+        if (!m->bs_free.empty()) { blob = m->bs_free.back().first; blob_bytes = m->bs_free.back().second; m->bs_free.pop_back(); }
+    }
+    if (blob && blob_bytes < total) { cudaFree(blob); blob = nullptr; }
+    if (!blob) { NF_CUDA(cudaMalloc((void**)&blob, total)); blob_bytes = total; }
     int rc = NF_OK;
     std::vector<double> hst(16 * n_cp + 1);
     do {
@@ -1009,8 +1020,11 @@ static int chain_batch_stats_small(const nf_model* m, const std::vector<std::pai
         if ((e = nf::launch_bs_small(a, stream)) != cudaSuccess) { rc = fail(NF_ERR_CUDA, "small-batch chain launch: %s", cudaGetErrorString(e)); break; }
         if ((e = cudaMemcpyAsync(hst.data(), blob + o_stats, 16 * n_cp * sizeof(double), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) { rc = fail(NF_ERR_CUDA, "statistics read-back: %s", cudaGetErrorString(e)); break; }
     } while (0);
-    cudaFreeAsync(blob, stream);
     cudaError_t es = cudaStreamSynchronize(stream);
+    {
+        std::lock_guard<std::mutex> lock(m->bs_mu);
+        m->bs_free.push_back({blob, blob_bytes});
+    }
     if (rc) return rc;
     if (es != cudaSuccess) return fail(NF_ERR_CUDA, "small-batch chain: %s", cudaGetErrorString(es));
     if (batch_stats_host) {

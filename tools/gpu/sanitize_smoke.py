@@ -26,8 +26,15 @@ if CHAIN:
     nll, sdz, z = nf._loss(x, y, iso=[100.0], cam=[2.0], return_z=True)
     xs = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], seed=3, offset=0)
     xr = nf.forward(z, None, yy=y, iso=[100.0], cam=[2.0])
-    nll_b, _ = nf._loss(x, y, iso=[100.0], cam=[2.0], is_training=True)            # batch-statistics probes
+    nf.set_batch_stats_fused(False)
+    nll_b, _ = nf._loss(x, y, iso=[100.0], cam=[2.0], is_training=True)            # batch-statistics probes, layer by layer
+    nf.set_batch_stats_fused(True)
     zz, ld = nf.run_layers(0, 3, "inverse", x, yy=y, iso=[100.0], cam=[2.0])
+# batch-statistics chain of a small batch: one cooperative kernel (td_bs_chain_kernel), both directions
+nb = min(n, 9)
+nll_c, _ = nf._loss(x[:nb], y[:nb], iso=[100.0], cam=[2.0], is_training=True)
+xs_c = nf.sample(y[:nb], 0.6, y[:nb], iso=[100.0] * nb, cam=[2.0] * (nb - 1) + [0.0], seed=3, offset=0, is_training=True)
+print("cooperative batch-statistics chain: nll/dim %.4f sample std %.4f" % (float(nll_c.mean()) / 4096, float(xs_c.std())))
 nf2 = NoiseFlow([32, 32, 4], False, make_hps(arch="sdn5|gain4"), device="cuda:0", first_call="inverse")
 nll_s, _ = nf2._loss(x, y, iso=[100.0], cam=[2.0])                              # streaming kernel
 if CHAIN and os.environ.get("NF_SANITIZE_TRAIN", "1") == "1":
