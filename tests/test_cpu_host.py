@@ -278,3 +278,37 @@ def test_device_train_program_layout(shipped):
     spec3.create_scale_variables()
     ops3 = build_train_program(spec3)[4]
     assert [op.kind for op in ops3] == [2, 1, 2] and ops3[1].mix_kind == 2 and list(ops3[1].perm) == [3, 2, 1, 0]
+
+
+def test_result_logger_writes_the_reference_tsv(tmp_path):
+    """borealisflows/utils.py:89-107 + the column sets of train_noise_flow.py:336-348: header without trailing newline, every
+    row prefixed by one, str.format of the values, append mode skips the header, a missing column raises KeyError."""
+    from noise_flow_b200.utils import SAMPLE_COLUMNS, TEST_COLUMNS, TRAIN_COLUMNS, ResultLogger
+    assert TRAIN_COLUMNS == ["epoch", "NLL", "NLL_G", "NLL_SDN", "sdz", "train_time"]
+    assert TEST_COLUMNS[-1] == "msg" and SAMPLE_COLUMNS[-4:] == ["KLD_G", "KLD_NLF", "KLD_NF", "KLD_R"]
+    p = str(tmp_path / "train.txt")
+    lg = ResultLogger(p, TRAIN_COLUMNS)
+    lg.log({"epoch": 1, "NLL": -2.5, "NLL_G": np.float32(-2.25), "NLL_SDN": -2.4, "sdz": 1.0, "train_time": 12})
+    del lg
+    lg = ResultLogger(p, TRAIN_COLUMNS, append=True)
+    lg.log({"epoch": 2, "NLL": -2.75, "NLL_G": -2.25, "NLL_SDN": -2.4, "sdz": 0.5, "train_time": 11, "extra": "ignored"})
+    with pytest.raises(KeyError):
+        lg.log({"epoch": 3})
+    del lg
+    assert open(p).read() == ("epoch\tNLL\tNLL_G\tNLL_SDN\tsdz\ttrain_time\n1\t-2.5\t-2.25\t-2.4\t1.0\t12\n"
+                              "2\t-2.75\t-2.25\t-2.4\t0.5\t11")       # rows START with the newline
+    ref = "/root/reference/borealisflows/utils.py"
+    if os.path.exists(ref):      # the reference's own class (its module imports matplotlib + tensorflow: executed over the stand-ins)
+        import importlib, sys
+        from oracle import tf1_shim
+        tf1_shim.install()
+        sys.path.insert(0, "/root/reference")
+        RefLogger = importlib.import_module("borealisflows.utils").ResultLogger
+        q = str(tmp_path / "ref.txt")
+        rl = RefLogger(q, TRAIN_COLUMNS)
+        rl.log({"epoch": 1, "NLL": -2.5, "NLL_G": np.float32(-2.25), "NLL_SDN": -2.4, "sdz": 1.0, "train_time": 12})
+        del rl
+        rl = RefLogger(q, TRAIN_COLUMNS, append=True)
+        rl.log({"epoch": 2, "NLL": -2.75, "NLL_G": -2.25, "NLL_SDN": -2.4, "sdz": 0.5, "train_time": 11})
+        del rl
+        assert open(q).read() == open(p).read()
