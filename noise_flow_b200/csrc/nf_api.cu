@@ -1031,7 +1031,11 @@ static int chain_batch_stats_small(const nf_model* m, const std::vector<std::pai
         a.ld = inverse ? (logdet ? logdet : nll) : nullptr;      // running log-det (nll doubles as scratch), zeroed below
         a.temp = temp; a.seed = seed; a.offset = offset; a.patch_base = patch_base;
         if (a.ld && (e = cudaMemsetAsync(a.ld, 0, (size_t)n * sizeof(float), stream)) != cudaSuccess) { rc = fail(NF_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); break; }
-        if ((e = nf::launch_bs_small(a, stream)) != cudaSuccess) { rc = fail(NF_ERR_CUDA, "small-batch chain launch: %s", cudaGetErrorString(e)); break; }
+        if ((e = nf::launch_bs_small(a, stream)) != cudaSuccess) {
+            if (e == cudaErrorCooperativeLaunchTooLarge) { cudaGetLastError(); rc = 1; break; }   // e.g. SMs partitioned by MPS: layer by layer
+            rc = fail(NF_ERR_CUDA, "small-batch chain launch: %s", cudaGetErrorString(e));
+            break;
+        }
         if ((e = cudaMemcpyAsync(hst.data(), blob + o_stats, 16 * n_cp * sizeof(double), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) { rc = fail(NF_ERR_CUDA, "statistics read-back: %s", cudaGetErrorString(e)); break; }
     } while (0);
     cudaError_t es = cudaStreamSynchronize(stream);
@@ -1091,9 +1095,11 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
             ok = ok && (k == L_COUPLING || (k == L_SCALE && g.second - g.first == 1));
             if (k == L_SCALE && m->layers[g.second - 1].scale_kind == NF_SCALE_SDN && !y) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
         }
-        if (ok)
-            return chain_batch_stats_small(m, groups, inverse, in, y, rows, default_row, n, temp, seed, offset, patch_base, out, logdet, nll,
-                                           sdz, batch_stats_host, stream);
+        if (ok) {
+            rc = chain_batch_stats_small(m, groups, inverse, in, y, rows, default_row, n, temp, seed, offset, patch_base, out, logdet, nll,
+                                         sdz, batch_stats_host, stream);
+            if (rc != 1) return rc;     // 1: the cooperative grid does not fit right now -> the path below
+        }
     }
     float* run_ld = logdet ? logdet : nll;   // running log-det (nll doubles as scratch until the last launch)
     const bool want_ld = run_ld != nullptr;
