@@ -874,7 +874,7 @@ __device__ __forceinline__ void td_prep_body(const TdProgram* __restrict__ prog,
     }
   }
 }
-__global__ void td_prep_kernel(const TdProgram* __restrict__ prog, const float* __restrict__ vars, float* Amat, float* tables,
+__global__ void __launch_bounds__(256) td_prep_kernel(const TdProgram* __restrict__ prog, const float* __restrict__ vars, float* Amat, float* tables,
                                double* consts) {
     td_prep_body(prog, vars, Amat, tables, consts);
 }
@@ -882,7 +882,7 @@ __global__ void td_prep_kernel(const TdProgram* __restrict__ prog, const float* 
 // Chain rules from the kernel-level gradients to the TF variables, all into the flat reduce buffer:
 //   red[0 .. n_vars)              d loss / d variable
 //   red[n_vars + 3 + 16 c + j]    batch statistics of coupling c (mean1, var1, mean2, var2) for the moving averages
-__global__ void td_chain_kernel(const TdProgram* __restrict__ prog, const float* __restrict__ vars, const double* __restrict__ cgrads,
+__global__ void __launch_bounds__(512) td_chain_kernel(const TdProgram* __restrict__ prog, const float* __restrict__ vars, const double* __restrict__ cgrads,
                                 const double* __restrict__ sgrads, const double* __restrict__ stats, double inv_cnt,
                                 int batch_stats, long long n_vars, double* __restrict__ red) {
     const int n_ops = prog->n_ops;
@@ -920,12 +920,13 @@ __global__ void td_chain_kernel(const TdProgram* __restrict__ prog, const float*
             red[n_vars + 3 + op.cidx * 16 + j] = val;
         }
     }
-    // (2) one thread per op: LU chain rule (train.lu_chain) and the scale-variable chain rules
-    const int i = threadIdx.x;
-    if (i >= n_ops) return;
+    // (2) work items (op, table row): the LU chain rule (train.lu_chain) of a coupling is item (op, 0); the 25 rows of a scale
+    //     layer chain to its variables independently (a loop over rows in one thread serialised 25 dependent L2 round trips)
+    for (int item = threadIdx.x; item < n_ops * NF_MAX_ROWS; item += blockDim.x) {
+    const int i = item / NF_MAX_ROWS, row = item % NF_MAX_ROWS;
     const TdOp& op = prog->ops[i];
     const nf_train_op& o = op.o;
-    if (o.kind == NF_TOP_COUPLING && o.mix_kind == 1) {
+    if (o.kind == NF_TOP_COUPLING && o.mix_kind == 1 && row == 0) {
         double P[4][4], L[4][4], U[4][4], sd[4], G[4][4], ptg[4][4], dL[4][4], dU[4][4];
         td_build_lu(o, prog->tri_lo, prog->tri_up, vars, P, L, U, sd);
         const double* g = cgrads + (size_t)op.cidx * NF_G_COUPLING_DOUBLES + NF_G_A;
@@ -949,7 +950,7 @@ __global__ void td_chain_kernel(const TdProgram* __restrict__ prog, const float*
     } else if (o.kind == NF_TOP_SCALE) {
         const double* sg = sgrads + (size_t)op.sidx * NF_MAX_ROWS * 2;
         const double c = o.c_i;
-        for (int row = 0; row < 25; ++row) {
+        if (row < 25) {
             const double da = sg[row * 2], db = sg[row * 2 + 1];
             if (da == 0.0 && db == 0.0) continue;
             const int cam = row / 5, isoi = row % 5;
@@ -979,6 +980,7 @@ __global__ void td_chain_kernel(const TdProgram* __restrict__ prog, const float*
             }
         }
     }
+    }
 }
 
 // Adam with TensorFlow's update rule + BatchNorm moving averages; one CTA so that the step counter has one writer
@@ -987,7 +989,10 @@ td_apply_kernel(const TdProgram* __restrict__ prog, float* __restrict__ vars, co
                 double* __restrict__ am, double* __restrict__ av, long long* __restrict__ step, const double* __restrict__ red,
                 long long n_vars, double lr, double b1, double b2, double eps, double inv_world, int update_bn) {
     const long long t = step[0] + 1;
-    const double lr_t = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
+    __shared__ double lr_t_s;
+    if (threadIdx.x == 0) lr_t_s = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
+    __syncthreads();
+    const double lr_t = lr_t_s;
     for (long long k = threadIdx.x; k < n_vars; k += blockDim.x) {
         if (!trainable[k]) continue;
         const double g = red[k] * inv_world;
@@ -998,10 +1003,10 @@ td_apply_kernel(const TdProgram* __restrict__ prog, float* __restrict__ vars, co
         vars[k] = (float)((double)vars[k] - lr_t * m / (sqrt(v) + eps));
     }
     if (update_bn) {
-        for (int i = 0; i < prog->n_ops; ++i) {
-            const TdOp& op = prog->ops[i];
-            if (op.o.kind != NF_TOP_COUPLING || threadIdx.x >= 16) continue;
-            const int j = threadIdx.x;
+        for (int item = threadIdx.x; item < prog->n_ops * 16; item += blockDim.x) {     // (op, statistic): all independent
+            const TdOp& op = prog->ops[item >> 4];
+            if (op.o.kind != NF_TOP_COUPLING) continue;
+            const int j = item & 15;
             const int offs[4] = {op.o.off_bn1_mean, op.o.off_bn1_var, op.o.off_bn2_mean, op.o.off_bn2_var};
             const int dst = offs[j >> 2] + (j & 3);
             const float batch = (float)(red[n_vars + 3 + op.cidx * 16 + j] * inv_world);
