@@ -300,6 +300,52 @@ def squeeze_goldens():
     return out
 
 
+def metrics_goldens():
+    """The evaluation metrics the training driver logs next to the NLL, from the reference's own numpy code:
+    `sidd_utils.get_histogram / kl_div_forward / kl_div_inverse / kl_div_sym / kl_div_3_data` (:1202-1274) with the 66-bin
+    edges of `kldiv_patch_set` (:1044-1046), `pack_raw / unpack_raw` (:732-764), and
+    `PatchStatsCalculator.calc_baselines` (PatchStatsCalculator.py:92-121) fed through a queue as the driver does."""
+    import queue
+    import tempfile
+    from types import SimpleNamespace
+    import sidd.sidd_utils as su
+    from sidd.PatchStatsCalculator import PatchStatsCalculator
+    rng = np.random.RandomState(51)
+    out = {}
+    x, y = synth_batch(6, cam=2, iso=800, seed=52)
+    xs = (x * 1.3 + rng.randn(*x.shape).astype(np.float32) * 0.004).astype(np.float32)       # a "sampled" noise batch
+    out["x"], out["y"], out["x_sampled"] = x, y, xs
+    bw = 0.2 / 64
+    bin_edges = np.concatenate(([-1000.0], np.arange(-0.1, 0.1 + 1e-9, bw), [1000.0]), axis=0)   # sidd_utils.py:1044-1046
+    out["bin_edges"] = bin_edges
+    hp, centers = su.get_histogram(x, bin_edges=bin_edges)
+    hq, _ = su.get_histogram(xs, bin_edges=bin_edges)
+    out["hist_p"], out["hist_q"], out["bin_centers"] = hp, hq, centers
+    out["kl_forward"], out["kl_inverse"], out["kl_sym"] = su.kl_div_forward(hp, hq), su.kl_div_inverse(hp, hq), su.kl_div_sym(hp, hq)
+    out["kl_3_data_edges"] = np.array(su.kl_div_3_data(x, xs, bin_edges=bin_edges))
+    out["kl_3_data_default"] = np.array(su.kl_div_3_data(np.abs(x) * 5, np.abs(xs) * 5))         # default 1000 bins on [0, 1]
+    h1000, c1000 = su.get_histogram(np.abs(x) * 5)
+    out["hist_default_1000"] = h1000
+    raw = rng.rand(8, 12).astype(np.float32)
+    out["bayer"], out["packed"] = raw, su.pack_raw(raw.copy())
+    out["unpacked"] = su.unpack_raw(out["packed"])
+    # baselines: two test minibatches through the queue, as initialize_data_stats_queues_baselines_histograms does
+    with tempfile.TemporaryDirectory() as tmp:
+        psc = PatchStatsCalculator(None, patch_height=32, n_channels=4, save_dir=tmp, file_postfix="", n_threads=1,
+                                   hps=SimpleNamespace(test_its=2))
+        psc.stats["sc_in_vr"] = np.float64(np.var(x))
+        q = queue.Queue()
+        nlf0, nlf1 = 0.003696, 0.000002
+        x64, y64 = x.astype(np.float64), y.astype(np.float64)      # the minibatch sampler allocates float64 (MiniBatchSampler.py:54-55)
+        q.put({"_x": x64[:3], "_y": y64[:3], "nlf0": nlf0, "nlf1": nlf1})
+        q.put({"_x": x64[3:], "_y": y64[3:], "nlf0": nlf0, "nlf1": nlf1})
+        nll_gauss, _, nll_sdn, _ = psc.calc_baselines(q)
+    out["var_gauss"], out["nlf0"], out["nlf1"] = np.float64(np.var(x)), np.float64(nlf0), np.float64(nlf1)
+    out["nll_gauss_mean"], out["nll_sdn_mean"] = np.float64(nll_gauss), np.float64(nll_sdn)
+    out["bpd_of_nll_sdn"] = np.float64(su.bpd(nll_sdn, 256, 4096))
+    return out
+
+
 def save(name, d):
     path = os.path.join(GOLD, name)
     np.savez_compressed(path, **d)
@@ -317,6 +363,7 @@ def main():
             cases[tag + "::" + k] = v
     save("ref_arch_cases.npz", cases)
     save("ref_squeeze.npz", squeeze_goldens())
+    save("ref_metrics.npz", metrics_goldens())
 
 
 if __name__ == "__main__":

@@ -208,3 +208,28 @@ def test_squeeze_matches_reference_bit_exact():
             key = "unsqueeze_%d_%s" % (factor, kind)
             if key in sq.files:
                 assert np.array_equal(unsqueeze2d(s, factor, kind).numpy(), sq[key])
+
+
+def test_metrics_match_reference_numpy_code():
+    """The evaluation metrics next to the path: the oracle's restatements and the host-side functions of
+    `noise_flow_b200.metrics` against the reference's own `sidd_utils` / `PatchStatsCalculator` code (ref_metrics.npz)."""
+    from noise_flow_b200 import metrics
+    from oracle.noise_flow_oracle import calc_baselines, get_histogram, kl_div_forward
+    g = _load("ref_metrics.npz")
+    x, y, xs, edges = g["x"], g["y"], g["x_sampled"], g["bin_edges"]
+    assert len(edges) == 67                                      # 64 bins on [-0.1, 0.1] + two catch-all bins
+    hp, hq = get_histogram(x, edges), get_histogram(xs, edges)
+    assert np.array_equal(hp, g["hist_p"]) and np.array_equal(hq, g["hist_q"])          # counts / n: exact
+    assert abs(kl_div_forward(hp, hq) - float(g["kl_forward"])) < 1e-15
+    for fn, key in ((metrics.kl_div_forward, "kl_forward"), (metrics.kl_div_inverse, "kl_inverse"), (metrics.kl_div_sym, "kl_sym")):
+        assert abs(fn(g["hist_p"], g["hist_q"]) - float(g[key])) < 1e-15, key
+    assert np.allclose(g["kl_3_data_edges"], [g["kl_forward"], g["kl_inverse"], g["kl_sym"]], rtol=1e-12, atol=1e-15)
+    nll_g, nll_s = calc_baselines(x, y, float(g["nlf0"]), float(g["nlf1"]), float(g["var_gauss"]))
+    # the reference averages per minibatch (two minibatches of three patches): same as the mean over the six patches
+    assert abs(nll_g.mean() - float(g["nll_gauss_mean"])) < 1e-9 * abs(float(g["nll_gauss_mean"]))
+    assert abs(nll_s.mean() - float(g["nll_sdn_mean"])) < 1e-9 * abs(float(g["nll_sdn_mean"]))
+    # bits per dimension as logged by the driver (sidd_utils.py:879-881)
+    bpd = (float(g["nll_sdn_mean"]) / 4096 + np.log(256)) / np.log(2.0)
+    assert abs(bpd - float(g["bpd_of_nll_sdn"])) < 1e-12
+    # Bayer packing used around the sampler (sample_noise_flow.py:74-79): pack -> unpack is the identity
+    assert np.array_equal(g["unpacked"], g["bayer"]) and g["packed"].shape == (4, 6, 4)
