@@ -312,3 +312,25 @@ def test_result_logger_writes_the_reference_tsv(tmp_path):
         rl.log({"epoch": 2, "NLL": -2.75, "NLL_G": -2.25, "NLL_SDN": -2.4, "sdz": 0.5, "train_time": 11})
         del rl
         assert open(q).read() == open(p).read()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/borealisflows/utils.py"), reason="needs the reference checkout")
+def test_hps_logger_bytes_equal_the_reference_function(tmp_path, golden_dir):
+    """hps.txt written by ours and by the reference's `hps_logger` (borealisflows/utils.py:110-119, executed over the
+    import stand-ins) from the same Hps object are byte-identical, and the reference's `hps_loader` reads ours back."""
+    import importlib
+    from types import SimpleNamespace
+    from noise_flow_b200.hps import hps_loader, hps_logger
+    from oracle import tf1_shim
+    tf1_shim.install()
+    sys.path.insert(0, "/root/reference")
+    ref_utils = importlib.import_module("borealisflows.utils")
+    hps = hps_loader(os.path.join(golden_dir, "NoiseFlow", "hps.txt"))
+    plain = SimpleNamespace(**{k: v for k, v in vars(hps).items() if k != "param_inits"})
+    names = ["sdn_0", "Conv2d_1x1_1", "unc_1"]
+    a, b = str(tmp_path / "ours.txt"), str(tmp_path / "ref.txt")
+    hps_logger(a, plain, names, 2433)
+    ref_utils.hps_logger(b, plain, names, 2433)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    back = ref_utils.hps_loader(a)
+    assert back.arch == hps.arch and back.width == "4" and back.flow_permutation == "1"      # utils.hps_loader keeps strings
