@@ -12,25 +12,31 @@ SAMPLE_COLUMNS_DO_SAMPLE = LOG_COLUMNS + ["sample_time", "KLD_G", "KLD_NLF", "KL
 
 
 class ResultLogger(object):
-    """``ResultLogger(path, columns, append=False)``: a tab-separated log whose header line is written WITHOUT a trailing
-    newline (only when the file is created) and whose rows each start with one (``utils.py:96-107``) -- files written by
-    the reference and by this class are byte-identical, so a run continued here appends cleanly to a reference log."""
+    """``ResultLogger(path, columns, append=False)``: a tab-separated log.  Format contract (``utils.py:96-107``): the
+    header is written only when the file is created and carries NO trailing newline; every row is written as a newline
+    followed by the tab-joined ``str.format`` of the values -- files written by the reference and by this class are
+    byte-identical, so a run continued here appends cleanly to a reference log."""
 
     def __init__(self, path: str, columns: Iterable[str], append: bool = False):
-        self.columns: List[str] = list(columns)
-        mode = "a" if append else "w"
-        self.f_log = open(path, mode)
-        if mode == "w":
-            self.f_log.write("\t".join(self.columns))
+        self.columns: List[str] = [str(c) for c in columns]
+        self._fh = open(path, "a" if append else "w")
+        if not append:
+            self._fh.write("\t".join(self.columns))
+
+    def log(self, run_info: Dict[str, object]) -> None:
+        """One row; a column missing from ``run_info`` raises ``KeyError`` (as the reference), extra keys are ignored."""
+        cells = []
+        for name in self.columns:
+            cells.append("{0}".format(run_info[name]))
+        self._fh.write("\n" + "\t".join(cells))
+        self._fh.flush()
+
+    def close(self) -> None:
+        if not self._fh.closed:
+            self._fh.close()
 
     def __del__(self):
         try:
-            self.f_log.close()
+            self.close()
         except Exception:
             pass
-
-    def log(self, run_info: Dict[str, object]) -> None:
-        run_strings = ["{0}".format(run_info[lc]) for lc in self.columns]      # KeyError for a missing column, as the reference
-        self.f_log.write("\n")
-        self.f_log.write("\t".join(run_strings))
-        self.f_log.flush()
