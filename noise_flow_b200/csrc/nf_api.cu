@@ -388,20 +388,6 @@ int launch_wide_range(const nf_model* m, int first, int last, bool inverse, NfCh
         a.last_layer = wp.n_layers;
         a.ldj_const = ldj;
         float* d = nullptr;
-        {   // keep freed blobs in the device's default pool: its default release threshold (0) hands the memory back to
-            // the driver at every stream synchronisation, which turns each of these small allocations into a real
-            // cudaMalloc / cudaFree (~0.2 ms; measured on the small-batch chain before it got its own free list)
-            static std::once_flag pool_once;
-            std::call_once(pool_once, [] {
-                int dev = 0;
-                cudaMemPool_t pool;
-                if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                    uint64_t keep = 64ull << 20;
-                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-                }
-                cudaGetLastError();
-            });
-        }
         NF_CUDA(cudaMallocAsync((void**)&d, blob.size() * sizeof(float), stream));
         NF_CUDA(cudaMemcpyAsync(d, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice, stream));   // pageable: staged before return
         e = nf::launch_chain_wide(wp, d, a, inverse, num_ctas_for(m), stream);
