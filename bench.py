@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--width", type=int, default=4,
                     help="coupling-net width (reference --width): 4 = shipped weights; 8 / 16 / 32 = CTA-per-patch kernel on a "
                          "randomly initialised net of the shipped arch")
+    ap.add_argument("--clean", default="uniform", choices=["uniform", "dark"],
+                    help="clean patches y ~ U[0, 1) (default, the quoted workload) or the dark variant y ~ Beta(2, 5)")
     ap.add_argument("--arch", default=None, help="override hps.arch, e.g. \"sdn5|gain4\" (HBM-bound streaming kernel)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -235,6 +237,12 @@ def main():
     B = args.batch
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     y = torch.rand((B, 32, 32, 4), device=dev, generator=g)
+    if args.clean == "dark":      # SURVEY 8d's second clean-image distribution: y ~ Beta(2, 5) = G1 / (G1 + G2), mean 0.29
+        torch.manual_seed(4321 + rank)
+        conc = torch.tensor([2.0, 5.0], device=dev).view(2, 1, 1, 1, 1).expand(2, B, 32, 32, 4)
+        ga = torch._standard_gamma(conc)
+        y = (ga[0] / (ga[0] + ga[1])).contiguous()
+        del ga, conc
     x = torch.randn((B, 32, 32, 4), device=dev, generator=g) * torch.sqrt(0.000479 * y + 0.000002)
     nll = torch.empty(B, device=dev)
     sdz = torch.empty(B, device=dev)
@@ -405,7 +413,7 @@ def main():
            "config": {"workload": "%s Noise Flow (shipped weights, arch %s), batch %d 32x32x4 patches per GPU, "
                                   "cam S6 / ISO 100" % (args.mode, hps.arch, B),
                       "per_gpu_batch": B, "global_batch": world * B, "parallelism": "dp%d" % world,
-                      "width": args.width,
+                      "width": args.width, "clean": args.clean,
                       "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (2 * B * 16384 / 2 ** 30),
                       "mean_nll_per_dim": mean_nll},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
