@@ -6,7 +6,6 @@ unmodified `borealisflows/*.py` (including its `NoiseFlowWrapper` class) execute
 `train_noise_flow.py` / `NoiseFlowWrapper.py`.  Here the independently written restatement `oracle/noise_flow_oracle.py`
 (fp64) must reproduce them to round-off, which is what pins it; the GPU suite then checks the CUDA path against the same
 files (tests/test_gpu_reference_goldens.py)."""
-import copy
 import os
 
 import numpy as np

@@ -6,7 +6,6 @@ rules in TensorFlow's / TensorFlow-Probability's documentation (quoted in the do
 (direct loops), independently of both the oracle and the CUDA path."""
 import numpy as np
 import pytest
-import torch
 
 from oracle import tf1_shim as tf
 
