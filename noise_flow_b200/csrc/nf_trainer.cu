@@ -5,7 +5,8 @@
 // stay in device memory; the parameterisations that the host-synchronous path (nf_train.cu + train.py) handles
 // on the CPU -- LU assembly of the 1x1 matrices, per-(camera, ISO) scale tables, BatchNorm batch statistics,
 // the chain rules back to the LU / scale variables, Adam, the BatchNorm moving averages -- are small kernels
-// between the heavy passes, so a step is one stream of ~60 launches with no cudaStreamSynchronize in it.
+// next to the heavy passes, so a step has no cudaStreamSynchronize in it: one cooperative kernel (td_step_kernel) plus the
+// reduce / chain-rule / Adam kernels when the batch is co-resident, ~60 per-pass launches otherwise.
 //
 // Mapping: ONE CTA OWNS ONE PATCH (8 warps, 16 selectable; warp w owns image rows w, w+NW, ...; lane = column).  A train batch
 // is 138-207 patches per GPU (job_noise_flow.sh:37), far fewer than the 148 x 16 resident warps of the
