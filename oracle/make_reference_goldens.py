@@ -285,6 +285,55 @@ def arch_case_goldens(tag, arch, perm, cam, iso, width=4):
     return out
 
 
+# legacy `revnet2d` models (noise_flow_model.py:237-392; hps.arch unset): (tag, sidd_cond, flow_permutation, append_* flags).
+# The CUDA engine does not implement them; the goldens pin the oracle's restatement for the round that will.
+# (The ISO-polynomial layers create `model/p1 ... q4` without reuse, cond_utils.py:13-35: two of them in one graph -- `fitSDN`
+# at depth > 1, or `fitSDN` / append_sdn together with append_sdn2 -- cannot be built in the reference.)
+LEGACY_CASES = [
+    ("condY", "condY", 1, {}),
+    ("condYG", "condYG", 0, {}),
+    ("condXY_cY", "condXY", 1, {"append_cY": True}),
+    ("condXYG_sdn", "condXYG", 1, {"append_sdn": True}),
+    ("condSDN_sdnfirst", "condSDN", 0, {"append_sdn_first": True}),
+    ("fitSDN_depth1", "fitSDN", 2, {"depth": 1}),
+    ("condXY_sdn2", "condXY", 1, {"append_sdn2": True}),
+    ("uncond", "uncond", 1, {}),
+]
+
+
+def legacy_case_goldens(tag, cond, perm, flags):
+    tf.reset_default_graph()
+    np.random.seed(7)
+    hps = ref_hps()
+    hps.arch, hps.depth, hps.sidd_cond, hps.flow_permutation = None, int(flags.get("depth", 2)), cond, perm
+    for f in ("append_sdn2", "append_sdn_first", "append_cY", "append_sdn"):
+        setattr(hps, f, bool(flags.get(f, False)))
+    n, iso, cam, nlf0, nlf1 = 2, 100.0, 2.0, 0.0012, 0.000004
+    x, y = synth_batch(n, cam=2, iso=100, seed=61)
+    eps = np.random.RandomState(62).randn(n, 32, 32, 4).astype(np.float32)
+    is_training = tf.placeholder(tf.bool, name='is_training')
+    nf = NoiseFlow(hps.x_shape[1:], is_training, hps)
+    a = dict(nlf0=c([nlf0]), nlf1=c([nlf1]), iso=c([iso]), cam=c([cam]))
+    nll_t, sd_t = nf._loss(c(x), c(y), **a)
+    if cond == "uncond":
+        xs_t = nf.sample(c(y), 0.6)
+    else:
+        xs_t = nf.sample(c(y), 0.6, c(y), a["nlf0"], a["nlf1"], a["iso"], a["cam"])
+    perturb(np.random.RandomState(63))
+    out = {"sidd_cond": np.array(cond), "flow_permutation": np.int64(perm), "x": x, "y": y, "eps": eps,
+           "iso": np.float32(iso), "cam": np.float32(cam), "nlf0": np.float64(nlf0), "nlf1": np.float64(nlf1),
+           "flags": np.array([f for f in sorted(flags) if f != "depth" and flags[f]]), "depth": np.int64(hps.depth), "layer_names": np.array(nf.get_layer_names()),
+           "num_params": np.int64(sum(int(np.prod(v.get_shape().as_list())) for v in tf.trainable_variables()))}
+    for name, v in var_snapshot().items():
+        out["var/" + name] = v.astype(np.float32)
+    sess = tf.Session()
+    inject_eps(eps)
+    out["nll"], out["sd_z"], xs = sess.run([nll_t, sd_t, xs_t], feed_dict={is_training: False})
+    out["sample_T0.6"] = xs.astype(np.float32)
+    out["nll_batch"], out["sd_z_batch"] = sess.run([nll_t, sd_t], feed_dict={is_training: True})
+    return out
+
+
 def squeeze_goldens():
     rng = np.random.RandomState(41)
     out = {}
@@ -361,6 +410,11 @@ def main():
         for k, v in arch_case_goldens(*case).items():
             cases[tag + "::" + k] = v
     save("ref_arch_cases.npz", cases)
+    legacy = {}
+    for tag, cond, perm, flags in LEGACY_CASES:
+        for k, v in legacy_case_goldens(tag, cond, perm, flags).items():
+            legacy[tag + "::" + k] = v
+    save("ref_legacy_cases.npz", legacy)
     save("ref_squeeze.npz", squeeze_goldens())
     save("ref_metrics.npz", metrics_goldens())
 

@@ -397,6 +397,76 @@ class RealNVPConvTemplate(_Template):
         return shift, log_scale
 
 
+def conv2d_iso(store, scope, name, x, width, iso0, filter_size=(3, 3)):
+    """layers.py:616-648: filter and bias are affine in the ISO, ``W = B1 * iso[0] + B2``, ``b = C1 * iso[0] + C2``
+    (all four N(0, 0.05^2)-initialised, :628); pad SAME, no edge bias."""
+    n_in = x.shape[3]
+    shp = tuple(filter_size) + (n_in, width)
+    rnd = lambda sh: (lambda: store.rng.randn(*sh) * 0.05)
+    b1 = store.get("%s/%s/B1" % (scope, name), shp, rnd(shp))
+    b2 = store.get("%s/%s/B2" % (scope, name), shp, rnd(shp))
+    x = _conv_nhwc(x, b1 * iso0 + b2, "SAME")                                         # :633,:639
+    c1 = store.get("%s/%s/C1" % (scope, name), (1, 1, 1, width), rnd((1, 1, 1, width)))
+    c2 = store.get("%s/%s/C2" % (scope, name), (1, 1, 1, width), rnd((1, 1, 1, width)))
+    return x + (c1 * iso0 + c2)                                                       # :647
+
+
+class RealNVPConvTemplateIso(_Template):
+    """layers.py:501-547: ``real_nvp_conv_template`` with ISO-conditioned first two convolutions."""
+
+    def __init__(self, store, x_shape, width):
+        super().__init__(store, "real_nvp_conv_template_iso")
+        self.x_shape, self.width = x_shape, width
+
+    def __call__(self, x, iso, is_training, current_scope="model"):
+        s = self.ensure_scope(current_scope)
+        st = self.store
+        iso0 = torch.as_tensor(np.asarray(iso, dtype=np.float64), dtype=st.dtype).reshape(-1)[0]
+        num_output = 2 * int(self.x_shape[2] / 2)                                     # :516
+        x = conv2d_iso(st, s, "l_1", x, self.width, iso0)                             # :518
+        x = torch.relu(batch_norm(st, s, x, is_training, name="bn_nvp_conv_1"))       # :519-527
+        x = conv2d_iso(st, s, "l_2", x, self.width, iso0, filter_size=(1, 1))         # :529
+        x = torch.relu(batch_norm(st, s, x, is_training, name="bn_nvp_conv_2"))       # :530-538
+        x = conv2d_zeros(st, s, "l_last", x, num_output)                              # :540
+        return x[..., :num_output // 2], x[..., num_output // 2:]                     # :543
+
+
+class CondCoupling:
+    """The clean-image-conditioned couplings reachable through ``revnet2d`` (noise_flow_model.py:305-348):
+    ``AffineCouplingCondY`` / ``CondYG`` -- the net sees only the clean patch and shifts / scales ALL channels
+    (AffineCouplingCondY.py:44-72) -- and ``AffineCouplingCondXY`` / ``CondXYG`` -- the net sees
+    ``concat(x0, yy)`` and transforms ``x1`` (AffineCouplingCondXY.py:45-79).  The ``G`` variants pass the ISO to a
+    ``real_nvp_conv_template_iso``."""
+
+    def __init__(self, mode, store, scope, x_shape, fn, layer_id=0, name="real_nvp"):
+        assert mode in ("Y", "YG", "XY", "XYG")
+        self.mode, self.name, self._fn, self.store = mode, name, fn, store
+        self.i0, self.i1, self.ic = x_shape
+        self.scale = store.get("%s/rescaling_scale%d" % (scope, layer_id), (), 1e-4)
+
+    def _net(self, x, yy, iso, is_training):
+        inp = yy if self.mode in ("Y", "YG") else torch.cat([x[..., :self.ic // 2], yy], dim=-1)
+        if self.mode.endswith("G"):
+            shift, log_scale = self._fn(inp, iso, is_training)
+        else:
+            shift, log_scale = self._fn(inp, is_training)
+        return shift, self.scale * torch.tanh(log_scale)
+
+    def _inverse_and_log_det_jacobian(self, y, yy, nlf0=None, nlf1=None, iso=None, cam=None, is_training=False):
+        shift, ls = self._net(y, yy, iso, is_training)
+        if self.mode in ("Y", "YG"):
+            return y * torch.exp(ls) + shift, ls.sum(dim=(1, 2, 3))
+        y0, y1 = y[..., :self.ic // 2], y[..., self.ic // 2:]
+        return torch.cat([y0, y1 * torch.exp(ls) + shift], dim=-1), ls.sum(dim=(1, 2, 3))
+
+    def _forward(self, x, yy, nlf0=None, nlf1=None, iso=None, cam=None, is_training=False):
+        shift, ls = self._net(x, yy, iso, is_training)
+        if self.mode in ("Y", "YG"):
+            return (x - shift) * torch.exp(-ls)
+        x0, x1 = x[..., :self.ic // 2], x[..., self.ic // 2:]
+        return torch.cat([x0, (x1 - shift) * torch.exp(-ls)], dim=-1)
+
+
 class AffineCoupling:
     """layers.py:251-375."""
 
@@ -473,6 +543,16 @@ def scale_fn(kind, store, model_scope, yy, nlf0, nlf1, iso, cam, gain_init, para
     g = store.get
     sc = model_scope
     iso_t = torch.as_tensor(np.asarray(iso, dtype=np.float64), dtype=store.dtype) if iso is not None else None
+    if kind in ("sdngain", "fitsdngain2"):                                            # cond_utils.py:11-38 (ISO polynomials)
+        i0 = iso_t.reshape(-1)[0]
+        e = lambda n: torch.exp(g(sc + "/" + n, (1,), -6.0))
+        if kind == "sdngain":                                                         # sdn_iso_model_params_3 (:11-24)
+            beta1 = e("p1") * i0 ** 2 + e("p2") * i0 + e("p3")
+            beta2 = e("q1") * i0 ** 3 + e("q2") * i0 ** 2 + e("q3") * i0 + e("q4")
+        else:                                                                         # sdn_iso_model_params_2 (:27-38)
+            beta1 = e("p2") * i0 + e("p3")
+            beta2 = e("q2") * i0 ** 2 + e("q3") * i0 + e("q4")
+        return torch.sqrt(beta1 * yy + beta2), True                                   # AffineCouplingSdnGain.py:46-47
     if kind == "sdn":                                                                 # cond_utils.py:41-52
         b1 = _sigmoid(g(sc + "/b1", (1,), -3.0))
         b2 = _sigmoid(g(sc + "/b2", (1,), 3.0))
@@ -597,7 +677,8 @@ def default_param_inits(arch):
 
 
 class OracleNoiseFlow:
-    """``NoiseFlow`` (noise_flow_model.py:44-513) for ``hps.arch`` models (n_levels == 1)."""
+    """``NoiseFlow`` (noise_flow_model.py:44-513), n_levels == 1: ``hps.arch`` models and, with ``hps.arch = None``, the
+    legacy ``revnet2d`` assembly (oracle only: the CUDA engine implements the ``hps.arch`` path)."""
 
     def __init__(self, x_shape, hps, variables=None, dtype=torch.float64, seed=0):
         self.x_shape = list(x_shape)
@@ -606,12 +687,54 @@ class OracleNoiseFlow:
         self.store = VariableStore(variables, dtype=dtype, seed=seed)
         if getattr(hps, "n_levels", 1) != 1:
             raise NotImplementedError("n_levels > 1 (split2d) is not on the hot path")
-        if not hasattr(hps, "param_inits") or isinstance(hps.param_inits, str):
+        if (not hasattr(hps, "param_inits") or isinstance(hps.param_inits, str)) and getattr(hps, "arch", None) is not None:
             hps.param_inits = default_param_inits(hps.arch)
         shape = list(self.x_shape)
         if hps.squeeze_factor != 1:                                                   # :58-60
             shape = [shape[0] // 2, shape[1] // 2, shape[2] * 4]
-        self.model = [self.noise_flow_arch("level0", shape, hps.flow_permutation, hps.arch)]
+        if getattr(hps, "arch", None) is not None:                                   # :63-68
+            self.model = [self.noise_flow_arch("level0", shape, hps.flow_permutation, hps.arch)]
+        else:
+            self.model = [self.revnet2d("level0", shape, hps.flow_permutation)]
+
+    # ---- noise_flow_model.py:237-392 (legacy: only reachable with hps.arch unset)
+    def revnet2d(self, name, x_shape, flow_permutation):
+        h, st, depth = self.hps, self.store, self.hps.depth
+        wide = list(x_shape[:-1]) + [x_shape[-1] * 2]                                # "double outputs" (:275,:313)
+        tmpl = lambda shp: RealNVPConvTemplate(st, shp, h.width)
+        tmpl_iso = lambda shp: RealNVPConvTemplateIso(st, shp, h.width)
+        scale = lambda kind, scope, nm: ScaleBijector(kind, st, scope, x_shape, 0, nm, getattr(h, "gain_init", 0.0), None)
+        b = []
+        if getattr(h, "append_sdn2", False):                                          # :243-253
+            b.append(scale("fitsdngain2", name + "/bijector_sdn2", "ac_fitSdnGain2_%d" % depth))
+        if getattr(h, "append_sdn_first", False):                                     # :255-265
+            b.append(scale("sdngain", name + "/bijector_sdn", "ac_fitSdnGain_%d" % depth))
+        if getattr(h, "append_cY", False):                                            # :267-279
+            b.append(CondCoupling("Y", st, name + "/bijector_cy", x_shape, tmpl(wide), name="ac_cY_first"))
+        for i in range(depth):                                                        # :280-378
+            scope = "%s/bijector%d" % (name, i)
+            if flow_permutation == 0:
+                b.append(Permute(x_shape[-1], name="permute"))
+            elif flow_permutation == 1:
+                b.append(Conv2d1x1(st, scope, x_shape, decomp=h.decomp, layer_id=i, name="Conv2d_1x1_%d" % i))
+            cond = h.sidd_cond
+            if cond == "condY":
+                b.append(CondCoupling("Y", st, scope, x_shape, tmpl(wide), name="ac_cY_%d" % i))
+            elif cond == "condYG":
+                b.append(CondCoupling("YG", st, scope, x_shape, tmpl_iso(wide), name="ac_cYG_%d" % i))
+            elif cond == "condXY":
+                b.append(CondCoupling("XY", st, scope, x_shape, tmpl(x_shape), name="ac_cXY_%d" % i))
+            elif cond == "condXYG":
+                b.append(CondCoupling("XYG", st, scope, x_shape, tmpl_iso(x_shape), name="ac_cXYG_%d" % i))
+            elif cond == "condSDN":
+                b.append(scale("camsdn", scope, "ac_cSDN_%d" % i))
+            elif cond == "fitSDN":
+                b.append(scale("sdngain", scope, "ac_fitSDN_%d" % i))
+            else:                                                                     # uncond | unc_sdn
+                b.append(AffineCoupling(st, scope, x_shape, tmpl(x_shape), name="ac_unc_%d" % i))
+        if getattr(h, "append_sdn", False):                                           # :379-390
+            b.append(scale("sdngain", "%s/bijector%d" % (name, depth), "ac_fitSDN_%d" % depth))
+        return b
 
     # ---- noise_flow_model.py:71-235
     def noise_flow_arch(self, name, x_shape, flow_permutation, arch):
@@ -653,6 +776,8 @@ class OracleNoiseFlow:
         for b in self.model[0]:
             if isinstance(b, ScaleBijector):
                 z, ldj = b._inverse_and_log_det_jacobian(z, yy, nlf0, nlf1, iso, cam)
+            elif isinstance(b, CondCoupling):
+                z, ldj = b._inverse_and_log_det_jacobian(z, yy, nlf0, nlf1, iso, cam, is_training)
             elif isinstance(b, AffineCoupling):
                 z, ldj = b._inverse_and_log_det_jacobian(z, is_training)
             else:
@@ -667,6 +792,8 @@ class OracleNoiseFlow:
         for b in reversed(self.model[0]):
             if isinstance(b, ScaleBijector):
                 x = b._forward(x, yy, nlf0, nlf1, iso, cam)
+            elif isinstance(b, CondCoupling):
+                x = b._forward(x, yy, nlf0, nlf1, iso, cam, is_training)
             elif isinstance(b, AffineCoupling):
                 x = b._forward(x, is_training)
             else:

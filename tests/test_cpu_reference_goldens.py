@@ -232,3 +232,41 @@ def test_metrics_match_reference_numpy_code():
     assert abs(bpd - float(g["bpd_of_nll_sdn"])) < 1e-12
     # Bayer packing used around the sampler (sample_noise_flow.py:74-79): pack -> unpack is the identity
     assert np.array_equal(g["unpacked"], g["bayer"]) and g["packed"].shape == (4, 6, 4)
+
+
+def _legacy_tags():
+    lc = _load("ref_legacy_cases.npz")
+    return sorted({k.split("::")[0] for k in lc.files})
+
+
+@pytest.mark.parametrize("tag", _legacy_tags())
+def test_oracle_reproduces_reference_legacy_revnet2d_cases(tag):
+    """`hps.arch` unset -> `revnet2d` (noise_flow_model.py:237-392): the clean-image-conditioned couplings CondY / CondYG /
+    CondXY / CondXYG (the G variants with ISO-conditioned convolutions), CamSdn, the ISO-polynomial SdnGain / FitSdnGain2
+    layers and the append_* options.  Oracle only (the CUDA engine implements the `hps.arch` path); the goldens are the
+    reference's own classes executed over the TF stand-in."""
+    from types import SimpleNamespace
+    lc = _load("ref_legacy_cases.npz")
+    g = {k.split("::", 1)[1]: lc[k] for k in lc.files if k.startswith(tag + "::")}
+    hps = SimpleNamespace(arch=None, depth=int(g["depth"]), sidd_cond=str(g["sidd_cond"]), flow_permutation=int(g["flow_permutation"]),
+                          width=4, decomp="LU", squeeze_factor=1, squeeze_type="chessboard", n_levels=1, gain_init=-5.0,
+                          x_shape=[None, 32, 32, 4], append_sdn2=False, append_sdn_first=False, append_cY=False, append_sdn=False)
+    for f in g["flags"]:
+        setattr(hps, str(f), True)
+    variables = {k[len("var/"):]: v for k, v in g.items() if k.startswith("var/")}
+    orc = make_oracle(hps, variables)
+    assert orc.get_layer_names() == list(g["layer_names"])
+    a = dict(nlf0=[float(g["nlf0"])], nlf1=[float(g["nlf1"])], iso=[float(g["iso"])], cam=[float(g["cam"])])
+    nll, sd_z = orc._loss(g["x"], g["y"], **a)
+    assert not orc.store.created, "variables the reference graph does not have: %s" % orc.store.created[:4]
+    assert set(orc.store.vars) == set(variables) and orc.store.num_trainable() == int(g["num_params"])
+    scale = max(1.0, np.abs(g["nll"]).max())
+    assert np.abs(nll.numpy() - g["nll"]).max() < 1e-9 * scale and abs(float(sd_z) - float(g["sd_z"])) < 1e-9 * max(1.0, float(g["sd_z"]))
+    if str(g["sidd_cond"]) == "uncond":
+        xs = orc.sample(g["eps"], 0.6).numpy()
+    else:
+        xs = orc.sample(g["eps"], 0.6, g["y"], **a).numpy()
+    assert np.abs(xs - g["sample_T0.6"]).max() < 1e-6 * max(1.0, np.abs(g["sample_T0.6"]).max())       # stored as fp32
+    nll_b, sd_b = orc._loss(g["x"], g["y"], is_training=True, **a)
+    assert np.abs(nll_b.numpy() - g["nll_batch"]).max() < 1e-9 * max(1.0, np.abs(g["nll_batch"]).max())
+    assert abs(float(sd_b) - float(g["sd_z_batch"])) < 1e-9 * max(1.0, float(g["sd_z_batch"]))
