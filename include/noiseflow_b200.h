@@ -5,10 +5,12 @@
  * no FFI of its own, so each entry point cites the Python interface it replaces; paths are relative
  * to the reference repository root).  Plain pointers and sizes only: no torch / CUDA types in the
  * signatures (streams travel as void*).  Unless a function name ends in _host, every data pointer
- * is a DEVICE pointer owned by the caller; the library owns only the opaque model handle (host
- * memory -- parameters are passed to each kernel launch by value) and never allocates device
- * memory behind the caller's back.  The _host entry points take host buffers and own a bounded
- * staging pool for the duration of the call.
+ * is a DEVICE pointer owned by the caller.  Width-4 models live in host memory only (parameters are passed
+ * to each kernel launch by value).  Device memory the library does own, all bounded and released by
+ * nf_model_destroy / nf_trainer_destroy: the folded parameter blob of a wide-net model (width != 4; a few hundred KB,
+ * plus a stream-ordered temporary of the same size for partial-range / batch-statistics launches), the <= 16 KB
+ * parameter images of the small-batch batch-statistics chain, the trainer's variables / Adam slots / workspace, and
+ * the staging pool of the _host entry points (which take host buffers).
  *
  * All functions return 0 on success and a negative nf_status otherwise; nf_last_error() returns a
  * thread-local human-readable message.  Nothing here throws, exits or prints.  Entry points are
@@ -77,7 +79,9 @@ const char* nf_last_error(void);
 int nf_device_info(int* sm_count, int* max_smem_optin, int* cc_major, int* cc_minor);
 
 /* ---- model construction: mirrors NoiseFlow.noise_flow_arch (noise_flow_model.py:71-235) -------- */
-/* x_shape must be 32x32x4 and width 4 (the shipped configuration); anything else -> NF_ERR_UNSUPPORTED. */
+/* x_shape must be 32x32x4; net_width (hps.width, sidd/ArgParser.py:43) 4 (the shipped configuration: fused warp-per-patch
+ * kernel), 8 / 16 (CTA-per-patch CUDA-core kernel), 32 / 64 / 128 (tensor-core kernel, tcgen05; 32 also has the
+ * CUDA-core kernel); anything else -> NF_ERR_UNSUPPORTED. */
 int nf_model_create(int height, int width, int channels, int net_width, nf_model** out);
 int nf_model_destroy(nf_model* m);
 /* Conv2d1x1 (layers.py:74-145, bias=False): A / A_inv are [in][out] row-major as produced by
@@ -95,11 +99,20 @@ int nf_model_num_layers(const nf_model* m);
 int nf_model_set_conv1x1(nf_model* m, int layer, const float* A, const float* A_inv, float log_abs_det);
 int nf_model_set_affine_coupling(nf_model* m, int layer, const nf_coupling_weights* w);
 int nf_model_set_scale(nf_model* m, int layer, const float* table, int n_rows);
+/* Batched update: between begin and end the nf_model_set_* calls only store; end folds and uploads once (wide nets keep
+ * their folded program in a device blob: the new one is uploaded beside the old one, swapped, and the old one retired
+ * after the launches that read it). */
+int nf_model_begin_update(nf_model* m);
+int nf_model_end_update(nf_model* m);
 /* Launch tuning: resident patches (warps) per CTA in [1, 16] and CTA count (0 = one per SM). */
 int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas);
-/* enable != 0: run the two 3x3 convolutions of every coupling net on the tensor cores (tcgen05.mma with bf16
+/* Width 4 -- enable != 0: run the two 3x3 convolutions of every coupling net on the tensor cores (tcgen05.mma with bf16
  * hi/lo-split operands, fp32 accumulation in TMEM; csrc/nf_tc.cu) for full-chain calls with explicit inputs;
- * other calls (partial ranges, in-kernel Philox, batch-statistics probes) keep the fp32 CUDA-core kernel. */
+ * other calls (partial ranges, in-kernel Philox, batch-statistics probes) keep the fp32 CUDA-core kernel (default 0:
+ * at 4 output channels the tensor pipe does not pay).
+ * Widths 32 / 64 / 128 -- the tensor-core kernel (csrc/nf_wide_tc.cu: all three convolutions as tcgen05.mma GEMMs,
+ * activations and accumulators in tensor memory) is the default; enable == 0 selects the CUDA-core kernel at width 32
+ * and is refused (NF_ERR_UNSUPPORTED) at 64 / 128, which have no other kernel. */
 int nf_model_set_tensor_cores(nf_model* m, int enable);
 
 /* ---- hot path (device pointers) ---------------------------------------------------------------- */

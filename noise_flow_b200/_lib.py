@@ -50,6 +50,8 @@ SIGNATURES = {
     "nf_model_set_conv1x1": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p, C.c_float]),
     "nf_model_set_affine_coupling": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(NfCouplingWeights)]),
     "nf_model_set_scale": (C.c_int, [C.c_void_p, C.c_int, c_float_p, C.c_int]),
+    "nf_model_begin_update": (C.c_int, [C.c_void_p]),
+    "nf_model_end_update": (C.c_int, [C.c_void_p]),
     "nf_model_set_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "nf_model_set_bs_small": (C.c_int, [C.c_void_p, C.c_int]),
     "nf_model_set_tensor_cores": (C.c_int, [C.c_void_p, C.c_int]),

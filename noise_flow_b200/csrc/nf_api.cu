@@ -104,6 +104,12 @@ struct nf_model {
     NfWideProgram wide_full = {};
     float* d_wide_full = nullptr;
     size_t wide_full_floats = 0;
+    // ... and, for widths the tensor-core kernel covers (32 / 64 / 128, nf_wide_tc.cu), the same chain folded into bf16
+    // (hi, lo) UMMA operand blocks.  use_tc_wide = 0 forces the CUDA-core kernel where one exists (width 32).
+    NfWideProgram wide_tc_full = {};
+    float* d_wide_tc = nullptr;
+    int use_tc_wide = 1;
+    int defer_finalize = 0;      // nf_model_begin_update .. nf_model_end_update: set many layers, fold / upload once
 };
 
 namespace {
@@ -313,9 +319,102 @@ int fold_wide(const Layer& L, int W, const float* bn, const Layer* mixl, float* 
     return NF_OK;
 }
 
+// ---- tensor-core kernel: fold one coupling into its UMMA operand block (NfWideTcLayout), double precision, then bf16 (hi, lo)
+uint16_t bf16_rn(float f) {            // round to nearest even
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);
+    return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+float bf16_to_f(uint16_t b) {
+    const uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+void bf16_split(double v, uint16_t* hi, uint16_t* lo) {
+    *hi = bf16_rn((float)v);
+    *lo = bf16_rn((float)(v - (double)bf16_to_f(*hi)));
+}
+
+int fold_wide_tc(const Layer& L, int W, const float* bn, const Layer* mixl, float* out) {
+    using T = NfWideTcLayout;
+    const WideRawView r(L.wraw.data(), W);
+    const float *m1 = bn ? bn : r.bn1_mean, *v1 = bn ? bn + W : r.bn1_var, *m2 = bn ? bn + 2 * W : r.bn2_mean,
+                *v2 = bn ? bn + 3 * W : r.bn2_var;
+    const double eps = L.raw.bn_eps;
+    std::vector<double> s1(W), s2(W);
+    for (int o = 0; o < W; ++o) {
+        if (!((double)v1[o] + eps > 0.0) || !((double)v2[o] + eps > 0.0)) return fail(NF_ERR_INVALID, "batch-norm variance + eps must be positive");
+        s1[o] = 1.0 / sqrt((double)v1[o] + eps);
+        s2[o] = 1.0 / sqrt((double)v2[o] + eps);
+    }
+    double e[4];
+    for (int o = 0; o < 4; ++o) e[o] = exp(3.0 * (double)r.last_logs[o]);
+    memset(out, 0, (size_t)T::block_bytes(W));
+    for (int o = 0; o < 4; ++o)
+        for (int i = 0; i < 4; ++i) {
+            out[T::H_A + o * 4 + i] = mixl ? mixl->a[o][i] : (o == i ? 1.f : 0.f);
+            out[T::H_AINV + o * 4 + i] = mixl ? mixl->ainv[o][i] : (o == i ? 1.f : 0.f);
+        }
+    out[T::H_META] = mixl ? 1.f : 0.f;
+    out[T::H_META + 1] = L.raw.rescaling_scale;
+    for (int rc = 0; rc < 3; ++rc)        // edge indicator -> bias table by (row class, column class), as fold_coupling
+        for (int cc = 0; cc < 3; ++cc)
+            for (int o = 0; o < 4; ++o) {
+                double acc = r.last_b[o];
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const bool ring = (rc == 0 && dy == 0) || (rc == 2 && dy == 2) || (cc == 0 && dx == 0) || (cc == 2 && dx == 2);
+                        if (ring) acc += (double)r.last_w[((dy * 3 + dx) * (W + 1) + W) * 4 + o];
+                    }
+                out[T::H_B3 + (rc * 3 + cc) * 4 + o] = (float)(acc * e[o]);
+            }
+    unsigned char* base = reinterpret_cast<unsigned char*>(out);
+    auto at = [](unsigned char* mat, int N, int n, int k) { return reinterpret_cast<uint16_t*>(mat) + ((size_t)(k / 8) * N + n) * 8 + k % 8; };
+    uint16_t hi, lo;
+    // B1: K rows [W1_hi (tap, in) | W1_hi | W1_lo | b_hi | b_lo]
+    unsigned char* B1 = base + T::off_b1();
+    for (int o = 0; o < W; ++o) {
+        for (int t = 0; t < 9; ++t)
+            for (int i = 0; i < 2; ++i) {
+                bf16_split((double)r.l1_w[(t * 2 + i) * W + o] * s1[o], &hi, &lo);
+                *at(B1, W, o, t * 2 + i) = hi;
+                *at(B1, W, o, 18 + t * 2 + i) = hi;
+                *at(B1, W, o, 36 + t * 2 + i) = lo;
+            }
+        bf16_split(((double)r.l1_b[o] - (double)m1[o]) * s1[o], &hi, &lo);
+        *at(B1, W, o, 54) = hi;
+        *at(B1, W, o, 55) = lo;
+    }
+    // B2: N rows [W2_hi | W2_lo], BB2: bias rows 6, 7
+    unsigned char *B2 = base + T::off_b2(W), *BB2 = base + T::off_bb2(W);
+    for (int o = 0; o < W; ++o) {
+        for (int i = 0; i < W; ++i) {
+            bf16_split((double)r.l2_w[i * W + o] * s2[o], &hi, &lo);
+            *at(B2, 2 * W, o, i) = hi;
+            *at(B2, 2 * W, W + o, i) = lo;
+        }
+        bf16_split(((double)r.l2_b[o] - (double)m2[o]) * s2[o], &hi, &lo);
+        *at(BB2, W, o, 6) = hi;
+        *at(BB2, W, o, 7) = lo;
+    }
+    // B3: N row dy*16 + dx*4 + o (hi), 48 + ... (lo)
+    unsigned char* B3 = base + T::off_b3(W);
+    for (int t = 0; t < 9; ++t)
+        for (int i = 0; i < W; ++i)
+            for (int o = 0; o < 4; ++o) {
+                bf16_split((double)r.last_w[(t * (W + 1) + i) * 4 + o] * e[o], &hi, &lo);
+                const int n = (t / 3) * 16 + (t % 3) * 4 + o;
+                *at(B3, 96, n, i) = hi;
+                *at(B3, 96, 48 + n, i) = lo;
+            }
+    return NF_OK;
+}
+
 // kernel program + parameter blob of the bijectors [first, last) of a wide model (same fusion rule as build_program)
 int build_wide_program(const nf_model* m, int first, int last, NfWideProgram* wp, std::vector<float>* blob, float* ldj_const,
-                       int bn_layer = -1, const float* bn_stats = nullptr) {
+                       int bn_layer = -1, const float* bn_stats = nullptr, bool tc = false) {
     const int W = m->width;
     memset(wp, 0, sizeof(*wp));
     wp->width = W;
@@ -334,9 +433,10 @@ int build_wide_program(const nf_model* m, int first, int last, NfWideProgram* wp
             memcpy(blob->data() + off + 16, L.ainv, sizeof(L.ainv));
             wp->op[n_ops] = NF_KOP_MIX;
         } else if (L.kind == L_COUPLING) {
-            blob->resize(off + (size_t)nf_wide_coupling_floats(W));
+            blob->resize(off + (size_t)(tc ? nf_wide_tc_coupling_floats(W) : nf_wide_coupling_floats(W)));
             const bool fused = l > first && (m->layers[l - 1].kind == L_CONV1X1 || m->layers[l - 1].kind == L_PERMUTE);
-            int rc = fold_wide(L, W, l == bn_layer ? bn_stats : nullptr, fused ? &m->layers[l - 1] : nullptr, blob->data() + off);
+            int rc = tc ? fold_wide_tc(L, W, l == bn_layer ? bn_stats : nullptr, fused ? &m->layers[l - 1] : nullptr, blob->data() + off)
+                        : fold_wide(L, W, l == bn_layer ? bn_stats : nullptr, fused ? &m->layers[l - 1] : nullptr, blob->data() + off);
             if (rc) return rc;
             wp->op[n_ops] = NF_KOP_COUPLING;
         } else if (L.kind == L_SCALE) {
@@ -361,19 +461,20 @@ int num_ctas_for(const nf_model* m) { return m->num_ctas > 0 ? m->num_ctas : m->
 
 // Wide model: launch the bijectors [first, last).  The full chain with the stored statistics uses the handle's resident
 // blob; partial ranges and batch-statistics re-folds upload their own blob, stream-ordered (cudaMallocAsync).
+// Tensor-core kernel (nf_wide_tc.cu) where the width has one (probes of the batch-statistics mode included).
 int launch_wide_range(const nf_model* m, int first, int last, bool inverse, NfChainArgs& a, int bn_layer, const float* bn,
                       cudaStream_t stream) {
     cudaError_t e;
+    const bool tc = nf::wide_tc_width_supported(m->width) && (m->use_tc_wide || !nf::wide_width_supported(m->width));
     if (first == 0 && last == (int)m->layers.size() && bn_layer < 0) {
-        NfWideProgram wp;
-        {
-            std::lock_guard<std::mutex> lock(m->prog_mu);
-            wp = m->wide_full;
-            a.ldj_const = m->full_ldj_const;
-        }
+        // the launch is enqueued under the lock: nf_model_finalize swaps and retires the blob under the same lock
+        std::lock_guard<std::mutex> lock(m->prog_mu);
+        const NfWideProgram& wp = tc ? m->wide_tc_full : m->wide_full;
+        a.ldj_const = m->full_ldj_const;
         a.first_layer = 0;
         a.last_layer = wp.n_layers;
-        e = nf::launch_chain_wide(wp, m->d_wide_full, a, inverse, num_ctas_for(m), stream);
+        e = tc ? nf::launch_chain_wide_tc(wp, m->d_wide_tc, a, inverse, num_ctas_for(m), stream)
+               : nf::launch_chain_wide(wp, m->d_wide_full, a, inverse, num_ctas_for(m), stream);
     } else {
         NfWideProgram wp;
         std::vector<float> blob;
@@ -381,7 +482,7 @@ int launch_wide_range(const nf_model* m, int first, int last, bool inverse, NfCh
         int rc;
         {
             std::lock_guard<std::mutex> lock(m->prog_mu);
-            rc = build_wide_program(m, first, last, &wp, &blob, &ldj, bn_layer, bn);
+            rc = build_wide_program(m, first, last, &wp, &blob, &ldj, bn_layer, bn, tc);
         }
         if (rc) return rc;
         a.first_layer = 0;
@@ -390,7 +491,8 @@ int launch_wide_range(const nf_model* m, int first, int last, bool inverse, NfCh
         float* d = nullptr;
         NF_CUDA(cudaMallocAsync((void**)&d, blob.size() * sizeof(float), stream));
         NF_CUDA(cudaMemcpyAsync(d, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice, stream));   // pageable: staged before return
-        e = nf::launch_chain_wide(wp, d, a, inverse, num_ctas_for(m), stream);
+        e = tc ? nf::launch_chain_wide_tc(wp, d, a, inverse, num_ctas_for(m), stream)
+               : nf::launch_chain_wide(wp, d, a, inverse, num_ctas_for(m), stream);
         NF_CUDA(cudaFreeAsync(d, stream));
     }
     if (e != cudaSuccess) return fail(NF_ERR_CUDA, "wide chain kernel launch: %s", cudaGetErrorString(e));
@@ -492,9 +594,9 @@ int nf_model_create(int height, int width, int channels, int net_width, nf_model
     if (height != NF_PATCH_H || width != NF_PATCH_W || channels != NF_PATCH_C)
         return fail(NF_ERR_UNSUPPORTED, "kernels are built for %dx%dx%d patches, got %dx%dx%d", NF_PATCH_H, NF_PATCH_W,
                     NF_PATCH_C, height, width, channels);
-    if (net_width != 4 && !nf::wide_width_supported(net_width))
-        return fail(NF_ERR_UNSUPPORTED, "kernels are built for coupling-net width 4 (fused warp-per-patch kernel) and 8 / 16 / 32 "
-                                        "(CTA-per-patch kernel), got %d", net_width);
+    if (net_width != 4 && !nf::wide_width_supported(net_width) && !nf::wide_tc_width_supported(net_width))
+        return fail(NF_ERR_UNSUPPORTED, "kernels are built for coupling-net width 4 (fused warp-per-patch kernel), 8 / 16 / 32 "
+                                        "(CTA-per-patch kernel) and 32 / 64 / 128 (tensor-core kernel), got %d", net_width);
     nf_model* m = new (std::nothrow) nf_model();
     if (!m) return fail(NF_ERR_INVALID, "out of host memory");
     m->width = net_width;
@@ -517,6 +619,7 @@ int nf_model_destroy(nf_model* m) {
     if (m->d_sums) cudaFree(m->d_sums);
     if (m->h_tmp) cudaFreeHost(m->h_tmp);
     if (m->d_wide_full) cudaFree(m->d_wide_full);
+    if (m->d_wide_tc) cudaFree(m->d_wide_tc);
     for (auto& b : m->bs_free) cudaFree(b.first);
     delete m;
     return NF_OK;
@@ -617,20 +720,32 @@ int nf_model_add_scale(nf_model* m, int kind, int logdet_full_sum, const float* 
 int nf_model_finalize(nf_model* m) {
     if (!m) return fail(NF_ERR_INVALID, "null model");
     if (m->layers.empty()) return fail(NF_ERR_STATE, "model has no layers");
-    int rc;
-    if (m->width != 4) {   // wide net: fold the whole chain and (re-)upload it to the handle's device blob
-        std::vector<float> blob;
-        std::lock_guard<std::mutex> lock(m->prog_mu);
-        rc = build_wide_program(m, 0, (int)m->layers.size(), &m->wide_full, &blob, &m->full_ldj_const);
-        if (rc) return rc;
-        if (blob.size() > m->wide_full_floats) {
-            if (m->d_wide_full) cudaFree(m->d_wide_full);
-            m->d_wide_full = nullptr;
-            m->wide_full_floats = 0;
-            NF_CUDA(cudaMalloc((void**)&m->d_wide_full, blob.size() * sizeof(float)));
-            m->wide_full_floats = blob.size();
+    int rc = NF_OK;
+    if (m->width != 4) {   // wide net: fold the whole chain and upload it to a FRESH device blob, then swap and retire the old one
+        // (kernels already enqueued keep reading the old blob; cudaFree waits for them)
+        for (int tc = 0; tc < 2; ++tc) {
+            if (tc ? !nf::wide_tc_width_supported(m->width) : !nf::wide_width_supported(m->width)) continue;
+            std::vector<float> blob;
+            NfWideProgram wp;
+            float ldj = 0.f;
+            {
+                std::lock_guard<std::mutex> lock(m->prog_mu);
+                rc = build_wide_program(m, 0, (int)m->layers.size(), &wp, &blob, &ldj, -1, nullptr, tc != 0);
+            }
+            if (rc) return rc;
+            float* fresh = nullptr;
+            NF_CUDA(cudaMalloc((void**)&fresh, blob.size() * sizeof(float)));
+            cudaError_t ce = cudaMemcpy(fresh, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (ce != cudaSuccess) { cudaFree(fresh); return fail(NF_ERR_CUDA, "wide blob upload: %s", cudaGetErrorString(ce)); }
+            float* old = nullptr;
+            {
+                std::lock_guard<std::mutex> lock(m->prog_mu);
+                if (tc) { old = m->d_wide_tc; m->d_wide_tc = fresh; m->wide_tc_full = wp; }
+                else { old = m->d_wide_full; m->d_wide_full = fresh; m->wide_full = wp; m->wide_full_floats = blob.size(); }
+                m->full_ldj_const = ldj;
+            }
+            if (old) cudaFree(old);
         }
-        NF_CUDA(cudaMemcpy(m->d_wide_full, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
     } else {
         std::lock_guard<std::mutex> lock(m->prog_mu);
         rc = build_program(m, 0, (int)m->layers.size(), &m->full, &m->full_ldj_const);
@@ -648,7 +763,18 @@ int nf_model_finalize(nf_model* m) {
 
 int nf_model_num_layers(const nf_model* m) { return m ? (int)m->layers.size() : fail(NF_ERR_INVALID, "null model"); }
 
-static int refinalize(nf_model* m) { return m->finalized ? nf_model_finalize(m) : NF_OK; }
+static int refinalize(nf_model* m) { return (m->finalized && !m->defer_finalize) ? nf_model_finalize(m) : NF_OK; }
+
+int nf_model_begin_update(nf_model* m) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    m->defer_finalize = 1;
+    return NF_OK;
+}
+int nf_model_end_update(nf_model* m) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    m->defer_finalize = 0;
+    return m->finalized ? nf_model_finalize(m) : NF_OK;
+}
 
 int nf_model_set_conv1x1(nf_model* m, int layer, const float* A, const float* A_inv, float log_abs_det) {
     if (!m || layer < 0 || layer >= (int)m->layers.size() || m->layers[layer].kind != L_CONV1X1)
@@ -699,7 +825,12 @@ int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas) {
 
 int nf_model_set_tensor_cores(nf_model* m, int enable) {
     if (!m) return fail(NF_ERR_INVALID, "null model");
-    m->use_tc = enable ? 1 : 0;
+    if (m->width == 4) m->use_tc = enable ? 1 : 0;
+    else {
+        if (!enable && !nf::wide_width_supported(m->width))
+            return fail(NF_ERR_UNSUPPORTED, "width %d has no CUDA-core kernel: the tensor-core kernel cannot be switched off", m->width);
+        m->use_tc_wide = enable ? 1 : 0;
+    }
     return NF_OK;
 }
 

@@ -31,8 +31,29 @@ struct NfWideProgram {           // by-value kernel argument; the parameters the
     int32_t off[NF_MAX_LAYERS];  // float offset of the op's block in the blob
 };
 
+// ---- tensor-core kernel (nf_wide_tc.cu): one coupling = one block, laid out exactly as it sits in shared memory so that
+// the TMA engine copies it verbatim (byte offsets, every one a multiple of 128):
+//   header  128 floats : A [4][4] | AINV [4][4] | META (has_mix, rescaling_scale, 0, 0) | B3 [3][3][4] edge-bias table
+//   B1   [64/8][W][8]   bf16   conv-1, K rows: W1_hi (18) | W1_hi (18) | W1_lo (18) | b1_hi | b1_lo | 0 x 8   (BN-1 folded)
+//   B2   [W/8][2W][8]   bf16   conv-2, N rows 0..W-1: W2_hi[o][k], rows W..2W-1: W2_lo[o][k]                  (BN-2 folded)
+//   BB2  [16/8][W][8]   bf16   conv-2 bias: K row 6 = b2_hi, row 7 = b2_lo (the constant-one slots of A1's K chunk 3)
+//   B3   [W/8][96][8]   bf16   conv-3 as a 1x1 GEMM, N row dy*16 + dx*4 + o: W3_hi ; row 48 + ...: W3_lo      (* exp(3 logs))
+// "K-major, no swizzle": element (n, k) of an [K/8][N][8] matrix at ((k / 8) * N + n) * 8 + k % 8.
+struct NfWideTcLayout {
+    static constexpr int H_A = 0, H_AINV = 16, H_META = 32, H_B3 = 36, HDR_FLOATS = 128;
+    __host__ __device__ static constexpr int off_b1() { return HDR_FLOATS * 4; }
+    __host__ __device__ static constexpr int off_b2(int W) { return off_b1() + 128 * W; }
+    __host__ __device__ static constexpr int off_bb2(int W) { return off_b2(W) + 4 * W * W; }
+    __host__ __device__ static constexpr int off_b3(int W) { return off_bb2(W) + 32 * W; }
+    __host__ __device__ static constexpr int block_bytes(int W) { return off_b3(W) + 192 * W; }
+};
+inline int nf_wide_tc_coupling_floats(int W) { return NfWideTcLayout::block_bytes(W) / 4; }
+
 namespace nf {
 bool wide_width_supported(int width);
+bool wide_tc_width_supported(int width);
+cudaError_t launch_chain_wide_tc(const NfWideProgram& prog, const float* blob, const NfChainArgs& args, bool inverse, int num_sms,
+                                 cudaStream_t stream);
 cudaError_t launch_chain_wide(const NfWideProgram& prog, const float* blob, const NfChainArgs& args, bool inverse, int num_sms,
                               cudaStream_t stream);
 }  // namespace nf

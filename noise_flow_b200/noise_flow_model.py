@@ -89,16 +89,20 @@ class _Engine:
     def refresh_parameters(self, extra=None):
         """Re-upload every layer from the variable store (after an optimizer step / BN update)."""
         lib, h = self.lib, self.handle
-        for idx, l in enumerate(self.spec.layers):
-            if l.kind == "conv1x1":
-                a, a_inv, lad = self.spec.conv1x1_matrices(l)
-                a32, i32 = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(a_inv, np.float32)
-                _lib.check(lib.nf_model_set_conv1x1(h, idx, _fp(a32), _fp(i32), lad), "nf_model_set_conv1x1")
-            elif l.kind == "coupling":
-                st, keep = self._coupling_struct(l)
-                _lib.check(lib.nf_model_set_affine_coupling(h, idx, C.byref(st)), "nf_model_set_affine_coupling")
-                del keep
-        self.update_scale_tables(extra)
+        _lib.check(lib.nf_model_begin_update(h), "nf_model_begin_update")     # set every layer, fold / upload once
+        try:
+            for idx, l in enumerate(self.spec.layers):
+                if l.kind == "conv1x1":
+                    a, a_inv, lad = self.spec.conv1x1_matrices(l)
+                    a32, i32 = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(a_inv, np.float32)
+                    _lib.check(lib.nf_model_set_conv1x1(h, idx, _fp(a32), _fp(i32), lad), "nf_model_set_conv1x1")
+                elif l.kind == "coupling":
+                    st, keep = self._coupling_struct(l)
+                    _lib.check(lib.nf_model_set_affine_coupling(h, idx, C.byref(st)), "nf_model_set_affine_coupling")
+                    del keep
+            self.update_scale_tables(extra)
+        finally:
+            _lib.check(lib.nf_model_end_update(h), "nf_model_end_update")
 
     def __del__(self):
         try:
@@ -193,9 +197,9 @@ class NoiseFlow(object):
         _lib.check(self._engine.lib.nf_model_set_launch(self._engine.handle, warps_per_cta, num_ctas), "nf_model_set_launch")
 
     def set_tensor_cores(self, enable: bool = True):
-        """Run the coupling-net 3x3 convolutions on the tensor cores (tcgen05, bf16 hi/lo split operands)."""
-        if int(self.spec.width) != 4:
-            raise NotImplementedError("the tensor-core formulation is built for width 4")
+        """Width 4: run the coupling-net 3x3 convolutions on the tensor cores (tcgen05, bf16 hi/lo split operands;
+        experimental, default off).  Widths 32 / 64 / 128: the tensor-core kernel is the default; ``False`` selects the
+        CUDA-core kernel (width 32 only)."""
         self.build()
         _lib.check(self._engine.lib.nf_model_set_tensor_cores(self._engine.handle, 1 if enable else 0),
                    "nf_model_set_tensor_cores")

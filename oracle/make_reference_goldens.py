@@ -219,6 +219,17 @@ ARCH_CASES = [
 ]
 
 
+# widths of the tensor-core kernels (csrc/nf_wide_tc.cu: 32 / 64 / 128 resident weights, 256 / 512 streamed weights), up to the
+# reference's default `--width 512` (sidd/ArgParser.py:43).  Kept in their own file (ref_wide_cases.npz): the l_2/W tensors
+# are W x W.  Few couplings at the large widths bound the fixture size.
+WIDE_CASES = [
+    ("width64", "sdn5|unc|gain4|unc", 1, 2, 100, 64),
+    ("width128", "sdn5|unc|unc|gain4", 1, 1, 800, 128),
+    ("width256", "sdn5|unc|gain4", 1, 3, 100, 256),
+    ("width512", "unc|gain4", 1, 0, 400, 512),
+]
+
+
 def perturb(rng, width=4):
     """Fresh variables make every coupling the identity (W3 = 0): move everything off its initial value (activations
     kept O(1) at any width)."""
@@ -402,6 +413,13 @@ def save(name, d):
 
 def main():
     tf1_shim.checkpoint_reader = load_checkpoint
+    wide = {}
+    for case in WIDE_CASES:
+        for k, v in arch_case_goldens(*case).items():
+            wide[case[0] + "::" + k] = v
+    save("ref_wide_cases.npz", wide)
+    if "--wide-only" in sys.argv:
+        return
     save("ref_training_graph.npz", training_graph_goldens())
     save("ref_wrapper_graph.npz", wrapper_goldens())
     cases = {}

@@ -163,18 +163,20 @@ def test_wrapper_graph_template_order_and_samples(shipped):
     assert np.abs(other - wg["sample"]).max() > 1e-3
 
 
-def _arch_cases():
-    ac = _load("ref_arch_cases.npz")
+def _arch_cases(fname="ref_arch_cases.npz"):
+    ac = _load(fname)
     tags = sorted({k.split("::")[0] for k in ac.files})
     return ac, tags
 
 
-@pytest.mark.parametrize("tag", _arch_cases()[1])
-def test_oracle_reproduces_reference_arch_cases(tag):
+@pytest.mark.parametrize("fname,tag", [("ref_arch_cases.npz", t) for t in _arch_cases()[1]] +
+                         [("ref_wide_cases.npz", t) for t in _arch_cases("ref_wide_cases.npz")[1]])
+def test_oracle_reproduces_reference_arch_cases(fname, tag):
     """Every token `noise_flow_arch` parses (all sdn* / gain* layers incl. the log-det quirks and the unknown-ISO
-    fall-backs, the three `flow_permutation` settings), perturbed variables, both BatchNorm modes."""
+    fall-backs, the three `flow_permutation` settings), perturbed variables, both BatchNorm modes; coupling-net widths
+    4 ... 512 (ref_wide_cases.npz: 64 / 128 / 256 / 512, the reference's default `--width`)."""
     from noise_flow_b200 import make_hps
-    ac, _ = _arch_cases()
+    ac, _ = _arch_cases(fname)
     g = {k.split("::", 1)[1]: ac[k] for k in ac.files if k.startswith(tag + "::")}
     hps = make_hps(arch=str(g["arch"]), flow_permutation=int(g["flow_permutation"]), width=int(g["width"]))
     variables = {k[len("var/"):]: v for k, v in g.items() if k.startswith("var/")}

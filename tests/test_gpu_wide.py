@@ -1,5 +1,7 @@
-"""Coupling nets wider than the shipped width 4 (``--width`` 8 / 16 / 32, sidd/ArgParser.py:43, job_noise_flow.sh:19):
-the CTA-per-patch kernel (csrc/nf_wide.cu) against the CPU oracle in both directions and both BatchNorm modes."""
+"""Coupling nets wider than the shipped width 4 (``--width``, sidd/ArgParser.py:43, job_noise_flow.sh:19): the CTA-per-patch
+CUDA-core kernel (csrc/nf_wide.cu, widths 8 / 16 / 32) and the tensor-core kernel (csrc/nf_wide_tc.cu, widths 32 / 64 / 128:
+tcgen05.mma with activations and accumulators in tensor memory; the default where it exists) against the CPU oracle in
+both directions and both BatchNorm modes."""
 import copy
 
 import numpy as np
@@ -36,11 +38,13 @@ def _perturbed_model(width, arch="sdn5|unc|unc|gain4|unc", perm=1, seed=11):
     return hps, vs
 
 
-@pytest.mark.parametrize("width", [8, 16, 32])
-def test_wide_log_prob_and_sample_match_oracle(width):
+@pytest.mark.parametrize("width,tensor_cores", [(8, None), (16, None), (32, False), (32, True), (64, True), (128, True)])
+def test_wide_log_prob_and_sample_match_oracle(width, tensor_cores):
     from noise_flow_b200 import NoiseFlow
     hps, vs = _perturbed_model(width)
     nf = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+    if tensor_cores is not None:
+        nf.set_tensor_cores(tensor_cores)
     orc = make_oracle(hps, vs)
     x, y = synth_batch(5, cam=2, iso=100, seed=31)
     x = (x * 20).astype(np.float32)                 # O(1) inputs so that the coupling nets are exercised
@@ -83,13 +87,15 @@ def test_wide_per_bijector_and_permutation():
     assert float((total - ld_all).abs().max()) / 4096 < 1e-5
 
 
-@pytest.mark.parametrize("width", [8, 32])
-def test_wide_batch_statistics_mode_matches_oracle(width):
+@pytest.mark.parametrize("width,tensor_cores", [(8, None), (32, False), (32, True), (64, True), (128, True)])
+def test_wide_batch_statistics_mode_matches_oracle(width, tensor_cores):
     """is_training=True: BatchNorm on the statistics of the batch, moving statistics updated (layers.py:388-398)."""
     from noise_flow_b200 import NoiseFlow
     hps, vs = _perturbed_model(width, arch="sdn5|unc|gain4|unc")
     nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables={k: v.copy() for k, v in vs.items()}, device="cuda:0",
                    first_call="inverse")
+    if tensor_cores is not None:
+        nf.set_tensor_cores(tensor_cores)
     orc = make_oracle(hps, vs)
     x, y = synth_batch(6, cam=2, iso=100, seed=35)
     x = (x * 20).astype(np.float32)
@@ -117,6 +123,40 @@ def test_wide_philox_sampling_statistics_and_large_batch():
     assert torch.equal(xs, xs2)                                  # counter-based RNG: same (seed, offset) -> same draw
     nll, sd_z, z = nf._loss(xs, y, iso=[100.0], cam=[2.0], return_z=True)
     assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3 and abs(float(sd_z) - 1.0) < 2e-2
+
+
+def test_tensor_core_kernel_equals_cuda_core_kernel_on_many_patches():
+    """Width 32 has both kernels: more patches than one wave of the tensor-core kernel (148 CTAs x 4 groups), ragged last
+    round, per-patch conditioning rows, explicit and in-kernel (Philox) noise."""
+    from noise_flow_b200 import NoiseFlow
+    hps, vs = _perturbed_model(32, arch="sdn5|unc|unc|gain4|unc")
+    nf = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+    n = 1501
+    g = torch.Generator(device="cuda").manual_seed(1)
+    y = torch.rand((n, 32, 32, 4), device="cuda", generator=g)
+    x = torch.randn((n, 32, 32, 4), device="cuda", generator=g) * 0.3
+    cams = (np.arange(n) % 5).astype(np.float64)
+    isos = np.asarray([100.0, 400.0, 800.0, 1600.0, 3200.0])[(np.arange(n) // 5) % 5]
+    res = {}
+    for tc in (True, False):
+        nf.set_tensor_cores(tc)
+        nll, sd_z, z = nf._loss(x, y, iso=isos, cam=cams, return_z=True)
+        xs = nf.sample(y, 1.0, y, iso=isos, cam=cams, seed=3, offset=0)
+        res[tc] = (nll, z, xs)
+    assert float((res[True][0] - res[False][0]).abs().max()) / 4096 < 2e-5
+    assert float((res[True][1] - res[False][1]).abs().max()) < 2e-4 * max(1.0, float(res[False][1].abs().max()))
+    assert float((res[True][2] - res[False][2]).abs().max()) < 2e-4 * max(1.0, float(res[False][2].abs().max()))
+    nf.set_tensor_cores(True)
+    assert torch.equal(nf._loss(x, y, iso=isos, cam=cams)[0], res[True][0])       # fixed reduction order: bit-identical reruns
+
+
+def test_wide_unsupported_widths_and_switches_raise():
+    from noise_flow_b200 import NoiseFlow, make_hps
+    with pytest.raises(RuntimeError):
+        NoiseFlow([32, 32, 4], False, make_hps(arch="unc", width=24), device="cuda:0", first_call="inverse")
+    nf = NoiseFlow([32, 32, 4], False, make_hps(arch="unc", width=64), device="cuda:0", first_call="inverse")
+    with pytest.raises(RuntimeError):
+        nf.set_tensor_cores(False)            # width 64 has no CUDA-core kernel
 
 
 def test_wide_training_is_refused_loudly():
