@@ -80,8 +80,8 @@ int nf_device_info(int* sm_count, int* max_smem_optin, int* cc_major, int* cc_mi
 
 /* ---- model construction: mirrors NoiseFlow.noise_flow_arch (noise_flow_model.py:71-235) -------- */
 /* x_shape must be 32x32x4; net_width (hps.width, sidd/ArgParser.py:43) 4 (the shipped configuration: fused warp-per-patch
- * kernel), 8 / 16 (CTA-per-patch CUDA-core kernel), 32 / 64 / 128 (tensor-core kernel, tcgen05; 32 also has the
- * CUDA-core kernel); anything else -> NF_ERR_UNSUPPORTED. */
+ * kernel), 8 / 16 (CTA-per-patch CUDA-core kernel), 32 / 64 / 128 / 256 / 512 (tensor-core kernels, tcgen05; 32 also has
+ * the CUDA-core kernel; 512 is the reference's default); anything else -> NF_ERR_UNSUPPORTED. */
 int nf_model_create(int height, int width, int channels, int net_width, nf_model** out);
 int nf_model_destroy(nf_model* m);
 /* Conv2d1x1 (layers.py:74-145, bias=False): A / A_inv are [in][out] row-major as produced by
@@ -110,9 +110,9 @@ int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas);
  * hi/lo-split operands, fp32 accumulation in TMEM; csrc/nf_tc.cu) for full-chain calls with explicit inputs;
  * other calls (partial ranges, in-kernel Philox, batch-statistics probes) keep the fp32 CUDA-core kernel (default 0:
  * at 4 output channels the tensor pipe does not pay).
- * Widths 32 / 64 / 128 -- the tensor-core kernel (csrc/nf_wide_tc.cu: all three convolutions as tcgen05.mma GEMMs,
- * activations and accumulators in tensor memory) is the default; enable == 0 selects the CUDA-core kernel at width 32
- * and is refused (NF_ERR_UNSUPPORTED) at 64 / 128, which have no other kernel. */
+ * Widths 32 ... 512 -- the tensor-core kernels (csrc/nf_wide_tc.cu, nf_wide_tcs.cu: all three convolutions as tcgen05.mma
+ * GEMMs, activations and accumulators in tensor memory) are the default; enable == 0 selects the CUDA-core kernel at
+ * width 32 and is refused (NF_ERR_UNSUPPORTED) at 64 ... 512, which have no other kernel. */
 int nf_model_set_tensor_cores(nf_model* m, int enable);
 
 /* ---- hot path (device pointers) ---------------------------------------------------------------- */

@@ -26,6 +26,7 @@ UNITS = [
     ("nf_tc.cu", ["-use_fast_math"]),
     ("nf_wide.cu", ["-use_fast_math"]),
     ("nf_wide_tc.cu", ["-use_fast_math"]),
+    ("nf_wide_tcs.cu", ["-use_fast_math"]),
     ("nf_train.cu", []),
     ("nf_trainer.cu", []),
     ("nf_api.cu", []),

@@ -374,30 +374,43 @@ int fold_wide_tc(const Layer& L, int W, const float* bn, const Layer* mixl, floa
     auto at = [](unsigned char* mat, int N, int n, int k) { return reinterpret_cast<uint16_t*>(mat) + ((size_t)(k / 8) * N + n) * 8 + k % 8; };
     uint16_t hi, lo;
     // B1: K rows [W1_hi (tap, in) | W1_hi | W1_lo | b_hi | b_lo]
+    // widths 256 / 512 (nf_wide_tcs.cu, streamed weights): the same matrices cut into the blocks the ring carries --
+    // B1 by 64 output channels, B2 by (pass of 256 outputs, 64 input channels), the bias by pass; B3 is unchanged
+    const bool streamed = W >= 256;
+    const int NK = W / 64;
     unsigned char* B1 = base + T::off_b1();
     for (int o = 0; o < W; ++o) {
+        unsigned char* m = streamed ? B1 + (size_t)(o / 64) * 8192 : B1;
+        const int N = streamed ? 64 : W, n = streamed ? o % 64 : o;
         for (int t = 0; t < 9; ++t)
             for (int i = 0; i < 2; ++i) {
                 bf16_split((double)r.l1_w[(t * 2 + i) * W + o] * s1[o], &hi, &lo);
-                *at(B1, W, o, t * 2 + i) = hi;
-                *at(B1, W, o, 18 + t * 2 + i) = hi;
-                *at(B1, W, o, 36 + t * 2 + i) = lo;
+                *at(m, N, n, t * 2 + i) = hi;
+                *at(m, N, n, 18 + t * 2 + i) = hi;
+                *at(m, N, n, 36 + t * 2 + i) = lo;
             }
         bf16_split(((double)r.l1_b[o] - (double)m1[o]) * s1[o], &hi, &lo);
-        *at(B1, W, o, 54) = hi;
-        *at(B1, W, o, 55) = lo;
+        *at(m, N, n, 54) = hi;
+        *at(m, N, n, 55) = lo;
     }
     // B2: N rows [W2_hi | W2_lo], BB2: bias rows 6, 7
     unsigned char *B2 = base + T::off_b2(W), *BB2 = base + T::off_bb2(W);
     for (int o = 0; o < W; ++o) {
         for (int i = 0; i < W; ++i) {
             bf16_split((double)r.l2_w[i * W + o] * s2[o], &hi, &lo);
-            *at(B2, 2 * W, o, i) = hi;
-            *at(B2, 2 * W, W + o, i) = lo;
+            if (streamed) {
+                unsigned char* m = B2 + ((size_t)(o / 256) * NK + i / 64) * 65536;
+                *at(m, 512, o % 256, i % 64) = hi;
+                *at(m, 512, 256 + o % 256, i % 64) = lo;
+            } else {
+                *at(B2, 2 * W, o, i) = hi;
+                *at(B2, 2 * W, W + o, i) = lo;
+            }
         }
         bf16_split(((double)r.l2_b[o] - (double)m2[o]) * s2[o], &hi, &lo);
-        *at(BB2, W, o, 6) = hi;
-        *at(BB2, W, o, 7) = lo;
+        unsigned char* mb = streamed ? BB2 + (size_t)(o / 256) * 8192 : BB2;
+        *at(mb, streamed ? 256 : W, streamed ? o % 256 : o, 6) = hi;
+        *at(mb, streamed ? 256 : W, streamed ? o % 256 : o, 7) = lo;
     }
     // B3: N row dy*16 + dx*4 + o (hi), 48 + ... (lo)
     unsigned char* B3 = base + T::off_b3(W);
@@ -596,7 +609,7 @@ int nf_model_create(int height, int width, int channels, int net_width, nf_model
                     NF_PATCH_C, height, width, channels);
     if (net_width != 4 && !nf::wide_width_supported(net_width) && !nf::wide_tc_width_supported(net_width))
         return fail(NF_ERR_UNSUPPORTED, "kernels are built for coupling-net width 4 (fused warp-per-patch kernel), 8 / 16 / 32 "
-                                        "(CTA-per-patch kernel) and 32 / 64 / 128 (tensor-core kernel), got %d", net_width);
+                                        "(CTA-per-patch kernel) and 32 / 64 / 128 / 256 / 512 (tensor-core kernels), got %d", net_width);
     nf_model* m = new (std::nothrow) nf_model();
     if (!m) return fail(NF_ERR_INVALID, "out of host memory");
     m->width = net_width;

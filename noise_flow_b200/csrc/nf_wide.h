@@ -39,6 +39,9 @@ struct NfWideProgram {           // by-value kernel argument; the parameters the
 //   BB2  [16/8][W][8]   bf16   conv-2 bias: K row 6 = b2_hi, row 7 = b2_lo (the constant-one slots of A1's K chunk 3)
 //   B3   [W/8][96][8]   bf16   conv-3 as a 1x1 GEMM, N row dy*16 + dx*4 + o: W3_hi ; row 48 + ...: W3_lo      (* exp(3 logs))
 // "K-major, no swizzle": element (n, k) of an [K/8][N][8] matrix at ((k / 8) * N + n) * 8 + k % 8.
+// Widths 256 / 512 (nf_wide_tcs.cu) use the same offsets with the matrices cut into the blocks its weight ring carries:
+//   B1 [W/64][8][64][8], B2 [W/256 passes][W/64][8][512][8] (rows 0..255 hi, 256..511 lo of the pass's outputs),
+//   BB2 [W/256][2][256][8], B3 unchanged.
 struct NfWideTcLayout {
     static constexpr int H_A = 0, H_AINV = 16, H_META = 32, H_B3 = 36, HDR_FLOATS = 128;
     __host__ __device__ static constexpr int off_b1() { return HDR_FLOATS * 4; }
@@ -54,6 +57,8 @@ bool wide_width_supported(int width);
 bool wide_tc_width_supported(int width);
 cudaError_t launch_chain_wide_tc(const NfWideProgram& prog, const float* blob, const NfChainArgs& args, bool inverse, int num_sms,
                                  cudaStream_t stream);
+cudaError_t launch_chain_wide_tcs(const NfWideProgram& prog, const float* blob, const NfChainArgs& args, bool inverse, int num_sms,
+                                  cudaStream_t stream);
 cudaError_t launch_chain_wide(const NfWideProgram& prog, const float* blob, const NfChainArgs& args, bool inverse, int num_sms,
                               cudaStream_t stream);
 }  // namespace nf

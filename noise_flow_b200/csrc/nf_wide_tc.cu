@@ -435,7 +435,7 @@ static cudaError_t launch_w(const NfWideProgram& prog, const float* blob, const 
 
 }  // namespace wtc
 
-bool wide_tc_width_supported(int width) { return width == 32 || width == 64 || width == 128; }
+bool wide_tc_width_supported(int width) { return width == 32 || width == 64 || width == 128 || width == 256 || width == 512; }
 
 cudaError_t launch_chain_wide_tc(const NfWideProgram& prog, const float* blob, const NfChainArgs& a, bool inverse, int num_sms,
                                  cudaStream_t stream) {
@@ -444,6 +444,8 @@ cudaError_t launch_chain_wide_tc(const NfWideProgram& prog, const float* blob, c
         case 32: return wtc::launch_w<32>(prog, blob, a, inverse, num_sms, stream);
         case 64: return wtc::launch_w<64>(prog, blob, a, inverse, num_sms, stream);
         case 128: return wtc::launch_w<128>(prog, blob, a, inverse, num_sms, stream);
+        case 256:
+        case 512: return launch_chain_wide_tcs(prog, blob, a, inverse, num_sms, stream);   // streamed weights (nf_wide_tcs.cu)
         default: return cudaErrorInvalidValue;
     }
 }

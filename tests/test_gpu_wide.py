@@ -1,6 +1,7 @@
 """Coupling nets wider than the shipped width 4 (``--width``, sidd/ArgParser.py:43, job_noise_flow.sh:19): the CTA-per-patch
-CUDA-core kernel (csrc/nf_wide.cu, widths 8 / 16 / 32) and the tensor-core kernel (csrc/nf_wide_tc.cu, widths 32 / 64 / 128:
-tcgen05.mma with activations and accumulators in tensor memory; the default where it exists) against the CPU oracle in
+CUDA-core kernel (csrc/nf_wide.cu, widths 8 / 16 / 32) and the tensor-core kernels (csrc/nf_wide_tc.cu, widths 32 / 64 / 128,
+and csrc/nf_wide_tcs.cu, widths 256 / 512 with streamed weights: tcgen05.mma with activations and accumulators in tensor
+memory; the default where they exist) against the CPU oracle in
 both directions and both BatchNorm modes."""
 import copy
 
@@ -38,7 +39,8 @@ def _perturbed_model(width, arch="sdn5|unc|unc|gain4|unc", perm=1, seed=11):
     return hps, vs
 
 
-@pytest.mark.parametrize("width,tensor_cores", [(8, None), (16, None), (32, False), (32, True), (64, True), (128, True)])
+@pytest.mark.parametrize("width,tensor_cores", [(8, None), (16, None), (32, False), (32, True), (64, True), (128, True),
+                                                (256, True), (512, True)])
 def test_wide_log_prob_and_sample_match_oracle(width, tensor_cores):
     from noise_flow_b200 import NoiseFlow
     hps, vs = _perturbed_model(width)
@@ -87,7 +89,8 @@ def test_wide_per_bijector_and_permutation():
     assert float((total - ld_all).abs().max()) / 4096 < 1e-5
 
 
-@pytest.mark.parametrize("width,tensor_cores", [(8, None), (32, False), (32, True), (64, True), (128, True)])
+@pytest.mark.parametrize("width,tensor_cores", [(8, None), (32, False), (32, True), (64, True), (128, True), (256, True),
+                                                (512, True)])
 def test_wide_batch_statistics_mode_matches_oracle(width, tensor_cores):
     """is_training=True: BatchNorm on the statistics of the batch, moving statistics updated (layers.py:388-398)."""
     from noise_flow_b200 import NoiseFlow
