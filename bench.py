@@ -166,6 +166,242 @@ def run_reference(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs 2-5 next to the headline line: each entry is a short timed run of its own (CUDA events around
+# K launches after W warm-up launches, barrier + synchronize on both sides, max over ranks), with its own roofline.
+# ----------------------------------------------------------------------------------------------------------------
+def _timed(fn, steps, warmup, dev, world):
+    """ms per step of fn(i), device-timed on torch's current stream, max over ranks."""
+    for i in range(warmup):
+        fn(i)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t[0])
+
+
+def _hbm_roofline(n, alg_bytes, ms, kernel, traffic=None, note=None):
+    peak, src = measured_peak()
+    ach = n * alg_bytes / (ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+         "peak_source": src, "kernel": kernel, "kernel_ms": ms, "alg_bytes_per_patch": alg_bytes}
+    if note:
+        r["note"] = note
+    return r
+
+
+def _fp32_roofline(n, flop_per_patch, ms, sm_mhz):
+    peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    ach = n * flop_per_patch / (ms * 1e-3) / 1e12
+    return {"bound": "fp32_fma", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": "148 SMs x 128 FMA/clk x 2 x median SM clock under load"}
+
+
+def _traffic(key):
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(tp)).get(key)
+    except Exception:
+        return None
+
+
+def wide_model(hps, ck, width, dev):
+    """A net of the shipped arch at another coupling width: no shipped checkpoint exists, so reference initialisers for the
+    structure and O(1)-activation random weights for the coupling nets."""
+    import copy as _copy
+    from noise_flow_b200 import NoiseFlow
+    h = _copy.copy(hps)
+    h.width = width
+    nf0 = NoiseFlow([32, 32, 4], False, h, variables={k: v for k, v in ck.items() if "real_nvp_conv_template" not in k},
+                    first_call="inverse", device=dev, seed=0)
+    rng = np.random.RandomState(0)
+    vs = {k: v.copy() for k, v in nf0.variables.items()}
+    for k in vs:
+        if k.endswith("/l_1/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.5).astype(np.float32)
+        elif k.endswith("/l_2/W"):
+            vs[k] = (rng.randn(*vs[k].shape) / np.sqrt(width)).astype(np.float32)
+        elif k.endswith("/l_last/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.05 / np.sqrt(width)).astype(np.float32)
+    del nf0
+    return h, vs
+
+
+def tensor_roofline(n, width, n_couplings, ms):
+    """Tensor-pipe roofline of the wide-net kernels.  `achieved` = ALGORITHMIC flops (2 x the fp32 MACs of the three
+    convolutions: 18 W + W^2 + 36 W per pixel and coupling) / time; `issued` counts what the bf16 (hi, lo) emulation really
+    sends through tcgen05.mma (conv-1 K = 64, conv-2 three products + bias chunk, conv-3 N = 96 + 48 of which 72 useful)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        peak, src = float(json.load(open(p))["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    except Exception:
+        peak, src = 1590.0, "fallback (B200_PROFILING.md)"
+    alg = 2.0 * 1024 * n_couplings * (18 * width + width * width + 36 * width)
+    issued = 2.0 * 1024 * n_couplings * (64 * width + 3 * width * width + 16 * width + width * 144)
+    ach = n * alg / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "peak_source": src, "kernel": "nf_wide_tc_kernel" if width <= 128 else "nf_wide_tcs_kernel", "kernel_ms": ms,
+            "alg_flop_per_patch": alg, "issued_tflops": n * issued / (ms * 1e-3) / 1e12,
+            "issued_frac": n * issued / (ms * 1e-3) / 1e12 / peak,
+            "note": "fp32-grade results from bf16 (hi, lo) split operands: 3 tensor-core products per fp32 MAC"}
+
+
+def shard_check(nf, lib, dev, rank, world, n_global=8192):
+    """sharded mean NLL == single-GPU mean NLL.  ONE seeded global batch; rank r evaluates its contiguous
+    slice, one all-reduce of [sum nll, sum sd_z, n] (fp64); rank 0 also evaluates the whole batch alone."""
+    from noise_flow_b200.distributed import allreduce_sums, shard_range
+    g = torch.Generator(device=dev).manual_seed(777)           # same seed on every rank: the same global batch
+    y = torch.rand((n_global, 32, 32, 4), device=dev, generator=g)
+    x = torch.randn((n_global, 32, 32, 4), device=dev, generator=g) * torch.sqrt(0.000479 * y + 0.000002)
+    lo, hi = shard_range(n_global, rank, world)
+    nf._loss(x[lo:hi], y[lo:hi], iso=[100.0], cam=[2.0])
+    sums = nf._tls.last_sums.clone()
+    allreduce_sums(sums)
+    out = None
+    if rank == 0:
+        nf._loss(x, y, iso=[100.0], cam=[2.0])
+        one = nf._tls.last_sums
+        out = {"n_global": n_global, "world": world,
+               "mean_nll_per_dim_sharded": float(sums[0] / sums[2]) / 4096, "mean_nll_per_dim_single": float(one[0] / one[2]) / 4096,
+               "abs_diff_nats_per_dim": abs(float(sums[0] / sums[2]) - float(one[0] / one[2])) / 4096,
+               "sd_z_abs_diff": abs(float(sums[1] / sums[2]) - float(one[1] / one[2])),
+               "count_equal": float(sums[2]) == float(one[2]) == float(n_global), "tolerance": 1e-7}
+        out["ok"] = bool(out["abs_diff_nats_per_dim"] < 1e-7 and out["count_equal"])
+    del x, y
+    return out
+
+
+def run_also(args, nf, hps, ck, x, y, dev, rank, world, sm_mhz, row):
+    """The other BASELINE.json configs, every one at `world` ranks (so the driver's scaling run records them at 8 GPUs)."""
+    from noise_flow_b200 import NoiseFlow, _lib
+    from noise_flow_b200.distributed import allreduce_sums
+    import copy as _copy
+    lib, eng = _lib.load(), nf._engine
+    B = x.shape[0]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    nll = torch.empty(B, device=dev)
+    sdz = torch.empty(B, device=dev)
+    sums = torch.zeros(3, device=dev, dtype=torch.float64)
+    out = {}
+    conv_flop = CONV_FLOP_PER_PATCH * hps.arch.split("|").count("unc") / 8.0
+
+    def log_prob_step(handle, xx, yy, n, reduce=True):
+        _lib.check(lib.nf_log_prob(handle, xx.data_ptr(), yy.data_ptr(), None, row, n, nll.data_ptr(), sdz.data_ptr(), None, stream))
+        if reduce:
+            _lib.check(lib.nf_reduce_sums(nll.data_ptr(), sdz.data_ptr(), n, sums.data_ptr(), stream))
+            if world > 1:
+                allreduce_sums(sums)
+
+    # ---- config 3: sample_noise_flow inverse pass, 65536 patches conditioned on clean + cam / ISO, in-kernel Philox
+    xs = torch.empty_like(x)
+    ms = _timed(lambda i: _lib.check(lib.nf_sample(eng.handle, y.data_ptr(), None, row, B, 0.6, None, 7, i, rank * B, xs.data_ptr(), stream)),
+                20, 3, dev, world)
+    out["sample_%d" % B] = {
+        "metric": "patches_per_sec_sample", "value": world * B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 20,
+        "config": {"workload": "sample (temperature 0.6, in-kernel Philox) Noise Flow, batch %d per GPU, cam S6 / ISO 100" % B,
+                   "baseline_config": 3, "per_gpu_batch": B},
+        "roofline": _hbm_roofline(B, ALG_BYTES_SAMPLE, ms, "nf_chain_kernel<false>", _traffic("sample_%d" % B),
+                                  "binding roof is the FP32 FMA pipe (roofline_fp32)"),
+        "roofline_fp32": _fp32_roofline(B, conv_flop, ms, sm_mhz), "gpu_launches": world * 20}
+    del xs
+    # ---- configs 2 and 4: log_prob at 4096 (config 2) and the batch sweep 1k / 16k / 64k / 256k per GPU (config 4); batches
+    # smaller than the resident one walk through it slice by slice, so consecutive launches never re-read L2-resident inputs
+    for n in (1024, 4096, 16384, 262144):
+        if n <= B:
+            nsl = B // n
+            fn = lambda i, n=n, nsl=nsl: log_prob_step(eng.handle, x[(i % nsl) * n:(i % nsl + 1) * n], y[(i % nsl) * n:(i % nsl + 1) * n], n)   # noqa: E731
+            steps = 50
+            ms = _timed(fn, steps, 3, dev, world)
+            l2 = "slices of the resident %d-patch batch in rotation (footprint %.1f GiB > L2)" % (B, 2 * B * 16384 / 2 ** 30)
+        else:
+            try:
+                reps = n // B
+                xb, yb = x.repeat(reps, 1, 1, 1), y.repeat(reps, 1, 1, 1)
+                nll, sdz = torch.empty(n, device=dev), torch.empty(n, device=dev)
+            except RuntimeError:
+                continue
+            steps = 5
+            ms = _timed(lambda i: log_prob_step(eng.handle, xb, yb, n), steps, 3, dev, world)
+            del xb, yb
+            nll, sdz = torch.empty(B, device=dev), torch.empty(B, device=dev)
+            l2 = "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (2 * n * 16384 / 2 ** 30)
+        out["log_prob_%d" % n] = {
+            "metric": "patches_per_sec_nll", "value": world * n / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": steps,
+            "config": {"workload": "log_prob Noise Flow (kernel + fp64 reduce%s), batch %d per GPU" % (" + all-reduce" if world > 1 else "", n),
+                       "baseline_config": 2 if n == 4096 else 4, "per_gpu_batch": n, "l2": l2},
+            "roofline": _hbm_roofline(n, ALG_BYTES_LOG_PROB, ms, "nf_chain_kernel<true>", None,
+                                      "whole step (kernel + reduce) timed; binding roof is the FP32 FMA pipe (roofline_fp32)"),
+            "roofline_fp32": _fp32_roofline(n, conv_flop, ms, sm_mhz), "gpu_launches": world * steps * 2}
+    # ---- the HBM-bound streaming kernel: the reference's sdn5|gain4 baseline model (job_noise_flow.sh:53); the only chain the
+    # north star's ">= 70 % of HBM" target applies to
+    h2 = _copy.copy(hps)
+    h2.arch = "sdn5|gain4"
+    nf2 = NoiseFlow([32, 32, 4], False, h2, variables=ck, first_call="inverse", device=dev)
+    ms = _timed(lambda i: log_prob_step(nf2._engine.handle, x, y, B, reduce=False), 50, 3, dev, world)
+    out["stream_sdn5_gain4_%d" % B] = {
+        "metric": "patches_per_sec_nll", "value": world * B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 50,
+        "config": {"workload": "log_prob of the scale-layer-only model sdn5|gain4 (job_noise_flow.sh:53), batch %d per GPU" % B,
+                   "per_gpu_batch": B, "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (2 * B * 16384 / 2 ** 30)},
+        "roofline": _hbm_roofline(B, ALG_BYTES_LOG_PROB, ms, "nf_scale_stream_kernel", None, "HBM-bound: ~60 flop per 32 KiB patch"),
+        "gpu_launches": world * 50}
+    del nf2
+    # ---- wide coupling nets on the tensor cores: width 32 ("for Noise Flow it is 32", job_noise_flow.sh:19) and the
+    # reference's default width 512 (sidd/ArgParser.py:43)
+    for width, nb in ((32, 16384), (512, 2048)):
+        hw, vw = wide_model(hps, ck, width, dev)
+        nfw = NoiseFlow([32, 32, 4], False, hw, variables=vw, first_call="inverse", device=dev)
+        steps = 10 if width == 32 else 3
+        ms = _timed(lambda i: log_prob_step(nfw._engine.handle, x[:nb], y[:nb], nb, reduce=False), steps, 3, dev, world)
+        out["wide_w%d_log_prob_%d" % (width, nb)] = {
+            "metric": "patches_per_sec_nll", "value": world * nb / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": steps,
+            "config": {"workload": "log_prob, shipped arch at coupling-net width %d (random weights), batch %d per GPU" % (width, nb),
+                       "per_gpu_batch": nb, "width": width,
+                       "l2": "inputs %.2f GiB per GPU > L2" % (2 * nb * 16384 / 2 ** 30)},
+            "roofline": tensor_roofline(nb, width, hw.arch.split("|").count("unc"), ms), "gpu_launches": world * steps}
+        del nfw
+    # ---- config 5: one Adam step (batch-statistics BN forward + backward + update) on a synthetic SIDD-shaped minibatch of
+    # 138 patches per GPU (job_noise_flow.sh:37), one NCCL all-reduce of the reduce buffer when world > 1
+    from noise_flow_b200.train import DeviceTrainer
+    nb = 138
+    nft = NoiseFlow([32, 32, 4], True, _copy.copy(hps), variables={k: v.copy() for k, v in ck.items()}, first_call="inverse", device=dev)
+    tr = DeviceTrainer(nft, learning_rate=1e-4, max_batch=nb)
+    xt, yt = x[:nb].contiguous(), y[:nb].contiguous()
+    ms = _timed(lambda i: tr.step(xt, yt, iso=[100.0], cam=[2.0]), 100, 5, dev, world)
+    import ctypes as C
+    nbar, us = C.c_int(0), C.c_float(0.0)
+    _lib.check(lib.nf_trainer_barriers_per_step(tr.handle, 1, C.byref(nbar)))
+    _lib.check(lib.nf_probe_grid_barrier(nb, 200, C.byref(us), stream))
+    n_cp = hps.arch.split("|").count("unc")
+    # algorithmic work: forward 248 MAC per pixel and coupling, backward 2x that (input gradients + parameter gradients)
+    train_flop = 3 * 2.0 * 1024 * n_cp * 248
+    fp = _fp32_roofline(nb, train_flop, ms, sm_mhz)
+    floor_ms = nbar.value * us.value * 1e-3
+    out["train_adam_step_%d" % nb] = {
+        "metric": "patches_per_sec_adam_step", "value": world * nb / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 100,
+        "config": {"workload": "one Adam step (sess.run([train_op, loss, sd_z]) equivalent, device-resident), %d patches per GPU" % nb,
+                   "baseline_config": 5, "per_gpu_batch": nb, "global_batch": world * nb,
+                   "collective": "one NCCL all-reduce of [grads | sums | batch statistics] (fp64)" if world > 1 else "none (1 GPU)"},
+        "roofline": {"bound": "latency", "achieved": ms, "peak": floor_ms, "unit": "ms", "frac": floor_ms / ms if ms > 0 else None,
+                     "traffic": None, "kernel": "td_step_kernel<8>", "grid_barriers_per_step": nbar.value,
+                     "us_per_grid_barrier": us.value,
+                     "note": "a %d-patch step is a latency chain: floor = grid barriers x measured barrier cost on a %d-CTA cooperative "
+                             "grid; frac = floor / measured step" % (nb, nb)},
+        "roofline_fp32": fp, "gpu_launches": world * 100 * tr.launches_per_step(True)}
+    del tr, nft
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,6 +425,9 @@ def main():
     ap.add_argument("--clean", default="uniform", choices=["uniform", "dark"],
                     help="clean patches y ~ U[0, 1) (default, the quoted workload) or the dark variant y ~ Beta(2, 5)")
     ap.add_argument("--arch", default=None, help="override hps.arch, e.g. \"sdn5|gain4\" (HBM-bound streaming kernel)")
+    ap.add_argument("--no-also", action="store_true", help="skip the `also` block (BASELINE configs 2-5 next to the headline)")
+    ap.add_argument("--check-shard", action="store_true",
+                    help="add `shard_check`: one seeded global batch, sharded mean NLL (all-reduce) vs rank 0's single-GPU pass")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -214,20 +453,7 @@ def main():
     if args.arch:
         hps.arch = args.arch
     if args.width != 4:     # no shipped checkpoint at other widths: reference initialisers, then non-trivial net weights
-        import numpy as _np
-        hps.width = args.width
-        nf0 = NoiseFlow([32, 32, 4], False, hps, variables={k: v for k, v in ck.items() if "real_nvp_conv_template" not in k},
-                        first_call="inverse", device=dev, seed=0)
-        rng = _np.random.RandomState(0)
-        ck = {k: v.copy() for k, v in nf0.variables.items()}
-        for k in ck:
-            if k.endswith("/l_1/W"):
-                ck[k] = (rng.randn(*ck[k].shape) * 0.5).astype(_np.float32)
-            elif k.endswith("/l_2/W"):
-                ck[k] = (rng.randn(*ck[k].shape) / _np.sqrt(args.width)).astype(_np.float32)
-            elif k.endswith("/l_last/W"):
-                ck[k] = (rng.randn(*ck[k].shape) * 0.05 / _np.sqrt(args.width)).astype(_np.float32)
-        del nf0
+        hps, ck = wide_model(hps, ck, args.width, dev)
     nf = NoiseFlow([32, 32, 4], False, hps, variables=ck, first_call="inverse", device=dev)
     if args.warps:
         nf.set_launch(args.warps, 0)
@@ -383,6 +609,16 @@ def main():
                "path": "nf_%s_host: pinned host buffers, 4096-patch chunks in flight on 4 streams" % args.mode}
         del hx_t, hy_t, hn_t
 
+    # ---- the other BASELINE configs (every rank takes part), sharding check
+    also = shard = None
+    default_workload = args.mode == "log_prob" and args.width == 4 and not args.arch and not args.tc and args.clean == "uniform"
+    sm_mhz_now = 1965.0
+    if rank == 0 and clocks and clocks.get("sm_mhz"):
+        sm_mhz_now = float(clocks["sm_mhz"])
+    if default_workload and not args.no_also and B >= 16384:
+        also = run_also(args, nf, hps, ck, x, y, dev, rank, world, sm_mhz_now, row)
+    if args.check_shard or (default_workload and not args.no_also and world > 1):
+        shard = shard_check(nf, lib, dev, rank, world)
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -426,6 +662,17 @@ def main():
                              "frac": B * conv_flop / (kms * 1e-3) / 1e12 / fp32_peak,
                              "peak_source": "148 SMs x 128 FMA/clk x 2 x median SM clock under load"},
            "e2e": e2e, "gpu_launches": world * args.steps * (2 if args.mode == "log_prob" else 1), "clocks": clocks}
+    out["roofline"]["traffic_source"] = ("profiles/traffic.json: dram bytes of one `ncu --set full` capture of this kernel at this batch "
+                                         "(a constant per build, not re-measured by this run)") if traffic is not None else None
+    if args.width != 4 and args.mode != "train" and n_couplings:
+        from noise_flow_b200.csrc_info import WIDE_TC_WIDTHS
+        if args.width in WIDE_TC_WIDTHS:        # tensor-core kernels: the binding roof is the tensor pipe
+            out["roofline_hbm"] = out["roofline"]
+            out["roofline"] = tensor_roofline(B, args.width, n_couplings, kms)
+    if also is not None:
+        out["also"] = also
+    if shard is not None:
+        out["shard_check"] = shard
     if args.mode == "train":   # a step is ~70 small launches + host chain rules: no single-kernel roofline applies
         n_cp = max(n_couplings, 1)
         out["roofline"] = None

@@ -238,6 +238,11 @@ int nf_trainer_apply(nf_trainer* t, const double* reduce_buf, double lr, double 
 int nf_trainer_get_vars(nf_trainer* t, float* vars_host, void* stream);          /* synchronises */
 int nf_trainer_set_vars(nf_trainer* t, const float* vars_host, void* stream);    /* synchronises */
 int nf_trainer_launches_per_step(const nf_trainer* t, int batch_stats, int* n_launches);
+/* Roofline aids for the fused step (bench.py): grid-wide barriers one loss+gradient evaluation crosses, and the measured
+ * cost of one such barrier on a cooperative grid of n_ctas CTAs shaped like the step kernel (difference of two launches
+ * of reps and 2*reps barriers; synchronises `stream`). */
+int nf_trainer_barriers_per_step(const nf_trainer* t, int batch_stats, int* n_barriers);
+int nf_probe_grid_barrier(int n_ctas, int reps, float* us_per_barrier, void* stream);
 /* enable != 0 (default): nf_trainer_loss_and_grad stages x / y / rows into trainer-owned buffers and replays the
  * launch sequence as ONE CUDA graph (re-captured when n, default_row, batch_stats or reduce_buf change) on an
  * internal stream fenced against `stream` with events; 0: plain launches on `stream`. */

@@ -83,6 +83,8 @@ SIGNATURES = {
     "nf_trainer_get_vars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nf_trainer_set_vars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nf_trainer_launches_per_step": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "nf_trainer_barriers_per_step": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "nf_probe_grid_barrier": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "nf_trainer_set_graph": (C.c_int, [C.c_void_p, C.c_int]),
     "nf_trainer_set_cta_warps": (C.c_int, [C.c_void_p, C.c_int]),
     "nf_trainer_set_fused": (C.c_int, [C.c_void_p, C.c_int]),

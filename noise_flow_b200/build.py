@@ -74,7 +74,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             os.path.getmtime(s) > os.path.getmtime(obj) for s in _sources() if s.endswith((".h", ".cuh")) or s == path)
         if not deps_newer:
             continue
-        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("NF_EXTRA_NVCC_FLAGS", "").split() + \
+            (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]      # NF_EXTRA_NVCC_FLAGS: experiment switches (-DNF_...)
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()

@@ -940,7 +940,8 @@ int nf_unsqueeze2d(const float* x, int64_t n, int H, int W, int C, int factor, i
 
 // ---- evaluation metrics next to the path ---------------------------------------------------------------
 static int cached_sm_count() {
-    static int sms = 0;
+    static int sms_dev[NF_MAX_DEVICES] = {};   // per device
+    int& sms = sms_dev[nf::device_slot()];
     if (!sms) { int v = 0; if (nf_device_info(&v, nullptr, nullptr, nullptr) == NF_OK) sms = v; }
     return sms ? sms : 148;
 }

@@ -384,18 +384,19 @@ cudaError_t launch_chain(const NfModelParams& mp, const NfChainArgs& args, bool 
                          cudaStream_t stream) {
     if (args.n <= 0) return cudaSuccess;
     const size_t smem = (size_t)warps_per_cta * sizeof(WarpSmem);
-    static bool attr_done[2] = {false, false};   // idempotent; a benign race sets the same value twice
+    static bool attr_done[NF_MAX_DEVICES][2] = {};   // per device; idempotent: a benign race sets the same value twice
+    const int dev = device_slot();
     cudaError_t e;
     if (inverse) {
-        if (!attr_done[0]) {
+        if (!attr_done[dev][0]) {
             e = cudaFuncSetAttribute(nf_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NF_MAX_CTA_SMEM);
             if (e != cudaSuccess) return e;
-            attr_done[0] = true;
+            attr_done[dev][0] = true;
         }
-    } else if (!attr_done[1]) {
+    } else if (!attr_done[dev][1]) {
         e = cudaFuncSetAttribute(nf_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NF_MAX_CTA_SMEM);
         if (e != cudaSuccess) return e;
-        attr_done[1] = true;
+        attr_done[dev][1] = true;
     }
     long long ctas = (args.n + warps_per_cta - 1) / warps_per_cta;
     if (ctas > num_sms) ctas = num_sms;

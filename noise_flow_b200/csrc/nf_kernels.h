@@ -20,7 +20,15 @@
 #define NF_TC_GROUPS 3   // patches in flight per CTA (4 warps each); 3 x 144 TMEM columns <= 512
 #define NF_TC_SLOTS 8    // couplings whose B tiles are resident in shared memory
 
+#define NF_MAX_DEVICES 64
 namespace nf {
+// cudaFuncSetAttribute, occupancy and the SM count are PER DEVICE: every "already done" flag / cached value in the
+// launchers is an array indexed by the current device (a process may drive several GPUs through one library).
+inline int device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= NF_MAX_DEVICES) d = 0;
+    return d;
+}
 // thread-local error string behind nf_last_error() (defined in nf_api.cu); returns `code`
 int set_error(int code, const char* what, const char* msg);
 cudaError_t launch_chain(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, int warps_per_cta,

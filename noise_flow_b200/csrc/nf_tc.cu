@@ -400,7 +400,8 @@ bool tc_program_supported(const NfModelParams& mp, const NfChainArgs& a) {
 
 cudaError_t launch_chain_tc(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, cudaStream_t stream) {
     if (args.n <= 0) return cudaSuccess;
-    static bool attr_done[2] = {false, false};
+    static bool attr_done_dev[NF_MAX_DEVICES][2] = {};   // per device
+    bool* attr_done = attr_done_dev[device_slot()];
     cudaError_t e;
     const int k = inverse ? 0 : 1;
     if (!attr_done[k]) {

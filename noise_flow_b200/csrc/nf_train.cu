@@ -373,7 +373,8 @@ __global__ void nf_train_prior_kernel(const float4* __restrict__ z, float4* __re
 
 // ---------------------------------------------------------------------------------------------- launchers
 static cudaError_t train_smem_attr() {
-    static bool done = false;
+    static bool done_dev[NF_MAX_DEVICES] = {};   // per device
+    bool& done = done_dev[device_slot()];
     if (done) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(nf_train_b1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(TrainSmem)));
     if (e != cudaSuccess) return e;

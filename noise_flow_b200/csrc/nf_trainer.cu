@@ -1262,13 +1262,33 @@ td_bs_chain_kernel(const BsArgs a) {
     }
 }
 
+// Measurement aid for the roofline of the fused step (bench.py): `reps` grid-wide barriers of a cooperative grid with the
+// shape of td_step_kernel<8> (256 threads, TdSmem of dynamic shared memory) and nothing else.
+__global__ void __launch_bounds__(256, 2) td_barrier_probe_kernel(int reps, int* sink) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    int v = 0;
+    for (int r = 0; r < reps; ++r) { grid.sync(); v += r; }
+    if (sink && v == -1) *sink = v;
+}
+cudaError_t launch_barrier_probe(int n_ctas, int reps, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(td_barrier_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TdSmem));
+    if (e != cudaSuccess) return e;
+    int* sink = nullptr;
+    void* kargs[] = {(void*)&reps, (void*)&sink};
+    return cudaLaunchCooperativeKernel((const void*)td_barrier_probe_kernel, dim3((unsigned)n_ctas), dim3(256), kargs, sizeof(TdSmem), s);
+}
+
 int bs_small_capacity(int sm_count) {
-    static int per_sm = -1;
+    static int per_sm_dev[NF_MAX_DEVICES] = {};   // per device; 0 = not queried yet, stored as occupancy + 1
+    int& slot = per_sm_dev[device_slot()];
+    int per_sm = slot - 1;
     if (per_sm < 0) {
         if (cudaFuncSetAttribute(td_bs_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TdSmem)) != cudaSuccess) return 0;
         int v = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, td_bs_chain_kernel<8>, 256, sizeof(TdSmem)) != cudaSuccess) return 0;
         per_sm = v;
+        slot = v + 1;
     }
     return per_sm * sm_count;
 }
@@ -1323,7 +1343,8 @@ namespace {
     } while (0)
 
 int td_smem_attr() {
-    static bool done = false;
+    static bool done_dev[NF_MAX_DEVICES] = {};   // per device
+    bool& done = done_dev[nf::device_slot()];
     if (done) return NF_OK;
     const int bytes = (int)sizeof(nf::TdSmem);
 #define TD_ATTR(K) TD_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
@@ -1445,6 +1466,38 @@ int nf_trainer_destroy(nf_trainer* t) {
 int nf_trainer_reduce_len(const nf_trainer* t, int64_t* n_doubles) {
     if (!t || !n_doubles) return nf::set_error(NF_ERR_INVALID, "nf_trainer_reduce_len", "null argument");
     *n_doubles = t->n_vars + 3 + 16 * (int64_t)t->n_cp;
+    return NF_OK;
+}
+
+int nf_probe_grid_barrier(int n_ctas, int reps, float* us_per_barrier, void* stream) {
+    if (n_ctas < 1 || reps < 1 || !us_per_barrier) return nf::set_error(NF_ERR_INVALID, "nf_probe_grid_barrier", "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    TD_CUDA(cudaEventCreate(&e0));
+    TD_CUDA(cudaEventCreate(&e1));
+    cudaError_t e = nf::launch_barrier_probe(n_ctas, 8, s);          // warm-up
+    float ms_a = 0.f, ms_b = 0.f;
+    if (e == cudaSuccess) e = cudaEventRecord(e0, s);
+    if (e == cudaSuccess) e = nf::launch_barrier_probe(n_ctas, reps, s);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, s);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms_a, e0, e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, s);
+    if (e == cudaSuccess) e = nf::launch_barrier_probe(n_ctas, 2 * reps, s);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, s);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms_b, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) return nf::set_error(NF_ERR_CUDA, "nf_probe_grid_barrier", cudaGetErrorString(e));
+    *us_per_barrier = (ms_b - ms_a) * 1e3f / (float)reps;        // the difference removes the launch cost
+    return NF_OK;
+}
+
+int nf_trainer_barriers_per_step(const nf_trainer* t, int batch_stats, int* n_barriers) {
+    if (!t || !n_barriers) return nf::set_error(NF_ERR_INVALID, "nf_trainer_barriers_per_step", "null argument");
+    // fused step: one after prep, two per coupling and direction around the BatchNorm batch sums
+    *n_barriers = 1 + (batch_stats ? 4 * t->n_cp : 0);
     return NF_OK;
 }
 

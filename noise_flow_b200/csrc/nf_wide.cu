@@ -315,7 +315,8 @@ template <int W>
 static cudaError_t launch_wide_w(const NfWideProgram& prog, const float* blob, const NfChainArgs& a, bool inverse, int num_sms,
                                  cudaStream_t stream) {
     const size_t smem = sizeof(WideSmem<W>);
-    static bool attr_done = false;
+    static bool attr_done_dev[NF_MAX_DEVICES] = {};   // per device (and per width: one instance of this template each)
+    bool& attr_done = attr_done_dev[device_slot()];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(nf_wide_chain_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -45,13 +45,21 @@ namespace nf {
 namespace wtc {
 
 
+#ifndef NF_WTC_NB2
+#define NF_WTC_NB2 1     // conv-2 (W <= 64): hi x [W2_hi | W2_lo] as one N = 2W MMA (D2 = [hh | hl], summed in the epilogue)
+#endif
+#ifndef NF_WTC_NB3
+#define NF_WTC_NB3 1     // conv-3: hi x [W3_hi | W3_lo] as one N = 96 MMA (D3 = [hi part | lo part], summed in the epilogue)
+#endif
+
 template <int W>
 struct Cfg {
     static_assert(W == 32 || W == 64 || W == 128, "resident-weights kernel: width 32 / 64 / 128");
     static constexpr int G = W == 32 ? 4 : (W == 64 ? 2 : 1);   // groups (patches in flight) per CTA
     static constexpr int H = 4 / G;                             // warps per TMEM lane quarter (channel split)
     static constexpr int GT = 128 * H;                          // threads per group
-    static constexpr bool NB = W <= 64;                         // conv-2 products batched along N (D2 = [hh | hl])
+    static constexpr bool NB = W <= 64 && NF_WTC_NB2;           // conv-2 products batched along N (D2 = [hh | hl])
+    static constexpr bool NB3 = NF_WTC_NB3 != 0;                // conv-3 products batched along N
     // TMEM columns of a group: A0 = A1 / A3, D = D1 / D2 (and D3 = 96 columns from D on), A2
     static constexpr int C_A0 = 0, C_D = W, C_A2 = C_D + (NB ? 2 * W : W), GROUP_COLS = C_A2 + W;
     static_assert(C_A2 + W - C_D >= 96, "D3 needs 96 columns behind D");
@@ -186,48 +194,67 @@ __device__ __forceinline__ void tc_coupling(const unsigned char* wb, GroupSmem& 
 #pragma unroll
             for (int s = 0; s < W / 16; ++s) {
                 const uint32_t bk = wb_addr + L::off_b3(W) + (uint32_t)s * 2u * (96u * 16u);
-                mma_ts(tD, tA0 + 8u * s, make_desc(bk, 96u * 16u, 128u), idesc(96), s > 0 ? 1u : 0u);
-                mma_ts(tD, tA0 + W / 2 + 8u * s, make_desc(bk, 96u * 16u, 128u), idesc(48), 1u);
+                if (C::NB3) {
+                    mma_ts(tD, tA0 + 8u * s, make_desc(bk, 96u * 16u, 128u), idesc(96), s > 0 ? 1u : 0u);                 // hi x [hi | lo]
+                    mma_ts(tD, tA0 + W / 2 + 8u * s, make_desc(bk, 96u * 16u, 128u), idesc(48), 1u);                       // lo x hi
+                } else {
+                    mma_ts(tD, tA0 + 8u * s, make_desc(bk, 96u * 16u, 128u), idesc(48), s > 0 ? 1u : 0u);                 // hi x hi
+                    mma_ts(tD, tA0 + W / 2 + 8u * s, make_desc(bk, 96u * 16u, 128u), idesc(48), 1u);                       // lo x hi
+                    mma_ts(tD, tA0 + 8u * s, make_desc(bk + 48u * 16u, 96u * 16u, 128u), idesc(48), 1u);                   // hi x lo
+                }
             }
             mma_commit(mbar);
         }
         mbar_wait(mbar, mphase);
         mphase ^= 1u;
         tc_fence_after();
-        // ---------------- epilogue 3: shifted sum.  Pixel (r, c), tap (dy, dx) contributes to output (r - dy + 1, c - dx + 1).
+        // ---------------- epilogue 3: shifted sum.  Pixel (r, c), tap (dy, dx) contributes to output (r - dy + 1, c - dx + 1):
+        // horizontal neighbours by warp shuffle (s_dy = the three dx taps of row r gathered at their output column), vertical
+        // ones through a 4-row exchange buffer -- ONE barrier; rows of the neighbouring tiles are updated in `pre` directly.
         float s_dy[3][4];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             if (h == (dy * H) / 3) {
                 uint32_t a[16], b[16];
                 tmem_ld16(tD + lane_sel + 16u * dy, a);
-                tmem_ld16(tD + lane_sel + 48u + 16u * dy, b);
+                if (C::NB3) tmem_ld16(tD + lane_sel + 48u + 16u * dy, b);
                 tmem_wait_ld();
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
-                    const float d0 = __uint_as_float(a[o]) + __uint_as_float(b[o]);            // dx = 0 -> output column c + 1
-                    const float d1 = __uint_as_float(a[4 + o]) + __uint_as_float(b[4 + o]);    // dx = 1 -> column c
-                    const float d2 = __uint_as_float(a[8 + o]) + __uint_as_float(b[8 + o]);    // dx = 2 -> column c - 1
-                    float fl = __shfl_up_sync(0xffffffffu, d0, 1);      // from column c - 1
-                    float fr = __shfl_down_sync(0xffffffffu, d2, 1);    // from column c + 1
+                    float d0 = __uint_as_float(a[o]), d1 = __uint_as_float(a[4 + o]), d2 = __uint_as_float(a[8 + o]);
+                    if (C::NB3) { d0 += __uint_as_float(b[o]); d1 += __uint_as_float(b[4 + o]); d2 += __uint_as_float(b[8 + o]); }
+                    float fl = __shfl_up_sync(0xffffffffu, d0, 1);      // dx = 0 of column c - 1 lands here
+                    float fr = __shfl_down_sync(0xffffffffu, d2, 1);    // dx = 2 of column c + 1 lands here
                     if (lane == 0) fl = 0.f;
                     if (lane == 31) fr = 0.f;
                     s_dy[dy][o] = d1 + (fl + fr);
                 }
+                if (dy == 0) Gs.ex[0][wq][lane] = make_float4(s_dy[0][0], s_dy[0][1], s_dy[0][2], s_dy[0][3]);   // goes to row r + 1
+                if (dy == 2) Gs.ex[1][wq][lane] = make_float4(s_dy[2][0], s_dy[2][1], s_dy[2][2], s_dy[2][3]);   // goes to row r - 1
             }
         }
         tc_fence_before();   // the next tile's MMAs / stores reuse these TMEM columns
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int tr = r - dy + 1;
-            if (h == (dy * H) / 3 && tr >= 0 && tr <= 31) {
-                float4 p = Gs.pre[tr * 32 + lane];
-                p.x += s_dy[dy][0]; p.y += s_dy[dy][1]; p.z += s_dy[dy][2]; p.w += s_dy[dy][3];
-                Gs.pre[tr * 32 + lane] = p;
-            }
-            group_barrier(g, GT);
+        group_barrier(g, GT);
+        if (h == (1 * H) / 3) {            // own row: dy = 1 of this row + dy = 0 of the row above + dy = 2 of the row below
+            float4 acc = make_float4(s_dy[1][0], s_dy[1][1], s_dy[1][2], s_dy[1][3]);
+            if (wq > 0) { const float4 u = Gs.ex[0][wq - 1][lane]; acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w; }
+            if (wq < 3) { const float4 d = Gs.ex[1][wq + 1][lane]; acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w; }
+            float4 p = Gs.pre[r * 32 + lane];
+            p.x += acc.x; p.y += acc.y; p.z += acc.z; p.w += acc.w;
+            Gs.pre[r * 32 + lane] = p;
+        }
+        if (h == 0 && wq == 3 && r < 31) {            // dy = 0 of the tile's last row -> first row of the next tile
+            float4 p = Gs.pre[(r + 1) * 32 + lane];
+            p.x += s_dy[0][0]; p.y += s_dy[0][1]; p.z += s_dy[0][2]; p.w += s_dy[0][3];
+            Gs.pre[(r + 1) * 32 + lane] = p;
+        }
+        if (h == (2 * H) / 3 && wq == 0 && r > 0) {   // dy = 2 of the tile's first row -> last row of the previous tile
+            float4 p = Gs.pre[(r - 1) * 32 + lane];
+            p.x += s_dy[2][0]; p.y += s_dy[2][1]; p.z += s_dy[2][2]; p.w += s_dy[2][3];
+            Gs.pre[(r - 1) * 32 + lane] = p;
         }
     }
+    group_barrier(g, GT);   // `pre` is complete
     if (STAGE != 0) {   // lane l of warp (wq, h) owns channel 32 h + l of its image rows; the four row-warps meet in shared memory
         atomicAdd(&Gs.sacc[32 * h + lane], acc_s);
         atomicAdd(&Gs.sacc[W + 32 * h + lane], acc_q);

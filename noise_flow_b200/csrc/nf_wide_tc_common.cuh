@@ -16,6 +16,7 @@ constexpr int THREADS = COMPUTE_THREADS + 32;      // + the TMA producer warp
 struct __align__(16) GroupSmem {
     float4 z[NF_PIXELS];        // the patch
     float4 pre[NF_PIXELS];      // conv-3 output being assembled: (shift0, shift1, raw log-scale0, raw log-scale1)
+    float4 ex[2][4][32];        // conv-3 row exchange of the current tile: [0] dy = 0 partial sums (for row r + 1), [1] dy = 2 (row r - 1)
     float hdr[128];             // fp32 header of the current coupling (mix matrices, rescaling scale, edge-bias table)
     float red[64];
     float sacc[256];            // batch-statistics probes: per-channel sum [W] and sum of squares [W] of this patch

@@ -42,6 +42,7 @@ struct __align__(128) SSmem {
     unsigned char slot[2][73728];
     float4 z[NF_PIXELS];
     float4 pre[NF_PIXELS];
+    float4 ex[2][4][32];
     float hdr[128];
     float red[64];
     float sacc[1024];
@@ -290,19 +291,27 @@ __device__ __forceinline__ void tcs_coupling(const float* __restrict__ cblob, SS
                 if (lane == 31) fr = 0.f;
                 s_dy[o] = d1 + (fl + fr);
             }
+            if (h == 0) S.ex[0][wq][lane] = make_float4(s_dy[0], s_dy[1], s_dy[2], s_dy[3]);
+            if (h == 2) S.ex[1][wq][lane] = make_float4(s_dy[0], s_dy[1], s_dy[2], s_dy[3]);
         }
         tc_fence_before();
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int tr = r - dy + 1;
-            if (h == dy && tr >= 0 && tr <= 31) {
-                float4 pv = S.pre[tr * 32 + lane];
-                pv.x += s_dy[0]; pv.y += s_dy[1]; pv.z += s_dy[2]; pv.w += s_dy[3];
-                S.pre[tr * 32 + lane] = pv;
-            }
-            group_barrier(0, GT);
+        group_barrier(0, GT);
+        if (h == 1) {
+            float4 acc = make_float4(s_dy[0], s_dy[1], s_dy[2], s_dy[3]);
+            if (wq > 0) { const float4 u = S.ex[0][wq - 1][lane]; acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w; }
+            if (wq < 3) { const float4 d = S.ex[1][wq + 1][lane]; acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w; }
+            float4 pv = S.pre[r * 32 + lane];
+            pv.x += acc.x; pv.y += acc.y; pv.z += acc.z; pv.w += acc.w;
+            S.pre[r * 32 + lane] = pv;
+        }
+        if ((h == 0 && wq == 3 && r < 31) || (h == 2 && wq == 0 && r > 0)) {
+            const int tr = h == 0 ? r + 1 : r - 1;
+            float4 pv = S.pre[tr * 32 + lane];
+            pv.x += s_dy[0]; pv.y += s_dy[1]; pv.z += s_dy[2]; pv.w += s_dy[3];
+            S.pre[tr * 32 + lane] = pv;
         }
     }
+    group_barrier(0, GT);
     if (STAGE != 0) return;
     const float scale = hdr[L::H_META + 1];
 #pragma unroll 2

@@ -34,5 +34,5 @@ def sharded_loss(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, group=None)
     """``NoiseFlow.loss`` over this rank's shard followed by the single all-reduce: every rank returns the
     global ``(mean NLL, mean sd_z)``."""
     nf._loss(x, y, nlf0, nlf1, iso, cam)
-    mean_nll, sd_z = global_means(nf.last_sums, group)
+    mean_nll, sd_z = global_means(nf._tls.last_sums, group)      # this thread's sums (many threads may share the model)
     return mean_nll.to(torch.float32), sd_z.to(torch.float32)

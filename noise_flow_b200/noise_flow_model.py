@@ -446,7 +446,7 @@ class NoiseFlow(object):
             with torch.cuda.device(self.device):
                 _lib.check(e.lib.nf_reduce_sums(nll.data_ptr(), sdz.data_ptr(), n, sums.data_ptr(),
                                                 _stream_ptr(self.device)), "nf_reduce_sums")
-            self.last_sums = sums
+            self.last_sums = self._tls.last_sums = sums
             sd_z = (sums[1] / max(n, 1)).to(torch.float32)
             return (nll, sd_z, z) if return_z else (nll, sd_z)
         self._fresh()
@@ -459,7 +459,9 @@ class NoiseFlow(object):
                                          rows.data_ptr() if rows is not None else None, drow, n, nll.data_ptr(),
                                          sdz.data_ptr(), z.data_ptr() if z is not None else None, st), "nf_log_prob")
             _lib.check(e.lib.nf_reduce_sums(nll.data_ptr(), sdz.data_ptr(), n, sums.data_ptr(), st), "nf_reduce_sums")
-        self.last_sums = sums                                   # [sum nll, sum sd_z, n] (fp64, deterministic)
+        # [sum nll, sum sd_z, n] (fp64, deterministic).  The calling thread's copy is the one `loss` / `sharded_loss` read:
+        # the reference drives one model from 16-32 threads; `last_sums` (last call of ANY thread) is a debugging aid only
+        self.last_sums = self._tls.last_sums = sums
         sd_z = (sums[1] / max(n, 1)).to(torch.float32)          # tf.reduce_mean(tf.sqrt(var_z))  :478
         if return_z:
             return nll, sd_z, z
@@ -468,7 +470,7 @@ class NoiseFlow(object):
     def loss(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, reuse=False, is_training=None):
         """noise_flow_model.py:482-484 -> ``(mean NLL, sd_z)``; the mean is the fp64 deterministic reduction."""
         nll, sd_z = self._loss(x, y, nlf0, nlf1, iso, cam, reuse, is_training)
-        return (self.last_sums[0] / max(nll.shape[0], 1)).to(torch.float32), sd_z
+        return (self._tls.last_sums[0] / max(nll.shape[0], 1)).to(torch.float32), sd_z
 
     def log_prob(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None):
         """``log p(x | y, cam, iso)`` per patch (= ``-nll``; named by BASELINE.json's north star)."""
