@@ -90,6 +90,20 @@ int nf_model_add_conv1x1(nf_model* m, const float* A, const float* A_inv, float 
 /* tfb.Permute(permutation) (noise_flow_model.py:80-84): forward y[..., i] = x[..., perm[i]]. */
 int nf_model_add_permute(nf_model* m, const int32_t* perm);
 int nf_model_add_affine_coupling(nf_model* m, const nf_coupling_weights* w);
+/* The clean-image-conditioned couplings of the reference's legacy `revnet2d` models (noise_flow_model.py:237-392, reached
+ * when hps.arch is unset).  mode 1 = AffineCouplingCondXY / CondXYG (noise_flow_layers/AffineCouplingCondXY.py:45-79): the net
+ * sees concat(x0, yy) -- l1_w is [3][3][6][W] -- and transforms x1; mode 2 = AffineCouplingCondY / CondYG
+ * (AffineCouplingCondY.py:44-72): the net sees yy only -- l1_w [3][3][4][W] -- and shifts / scales ALL four channels:
+ * last_w [3][3][W+1][8], last_b [8], last_logs [8] (shift = outputs 0..3, log-scale = 4..7).  mode 0 = plain AffineCoupling.
+ * The ISO-conditioned `G` variants (real_nvp_conv_template_iso, layers.py:501-547,616-648: W = B1 * iso + B2, b = C1 * iso + C2)
+ * are the same couplings with the effective weights of the call's ISO (the reference feeds one ISO per minibatch): set them
+ * with nf_model_set_cond_coupling.  Widths 4 / 8 / 16 / 32 (CUDA-core CTA-per-patch kernel); a model that has such a coupling
+ * runs all its launches on that kernel. */
+#define NF_COUPLING_X 0
+#define NF_COUPLING_XY 1
+#define NF_COUPLING_Y 2
+int nf_model_add_cond_coupling(nf_model* m, int mode, const nf_coupling_weights* w);
+int nf_model_set_cond_coupling(nf_model* m, int layer, const nf_coupling_weights* w);
 /* table: [n_rows][2] floats; logdet_full_sum = 0 reproduces the Gain/GainEx1/GainEx3 quirk whose
  * log-det is log(scale) instead of 4096*log(scale) (AffineCouplingGain.py:86,96,111,125). */
 int nf_model_add_scale(nf_model* m, int kind, int logdet_full_sum, const float* table, int n_rows);

@@ -44,6 +44,8 @@ SIGNATURES = {
     "nf_model_add_conv1x1": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_float]),
     "nf_model_add_permute": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "nf_model_add_affine_coupling": (C.c_int, [C.c_void_p, C.POINTER(NfCouplingWeights)]),
+    "nf_model_add_cond_coupling": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(NfCouplingWeights)]),
+    "nf_model_set_cond_coupling": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(NfCouplingWeights)]),
     "nf_model_add_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int]),
     "nf_model_finalize": (C.c_int, [C.c_void_p]),
     "nf_model_num_layers": (C.c_int, [C.c_void_p]),

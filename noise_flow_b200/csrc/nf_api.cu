@@ -54,6 +54,8 @@ struct Layer {
     // coupling of a wide net (width != 4): reference-shaped copy, [l1_w 18W][l1_b W][bn1_mean W][bn1_var W][l2_w W*W]
     // [l2_b W][bn2_mean W][bn2_var W][last_w 36(W+1)][last_b 4][last_logs 4]; rescaling_scale / bn_eps in `raw`
     std::vector<float> wraw;
+    // coupling kind (NF_COUPLING_MODE_*): 0 AffineCoupling, 1 CondXY[G], 2 CondY[G]; input / output channels of its net
+    int cmode = 0, cin = 2, cout = 4;
     // scale
     int scale_kind = 0, full_sum = 1, n_rows = 0;
     float table[NF_MAX_ROWS][4] = {};
@@ -61,12 +63,14 @@ struct Layer {
 
 struct WideRawView {   // sub-arrays of Layer::wraw
     const float *l1_w, *l1_b, *bn1_mean, *bn1_var, *l2_w, *l2_b, *bn2_mean, *bn2_var, *last_w, *last_b, *last_logs;
-    WideRawView(const float* p, int W) {
-        l1_w = p; p += 18 * W; l1_b = p; p += W; bn1_mean = p; p += W; bn1_var = p; p += W;
+    WideRawView(const float* p, int W, int cin = 2, int cout = 4) {
+        l1_w = p; p += 9 * cin * W; l1_b = p; p += W; bn1_mean = p; p += W; bn1_var = p; p += W;
         l2_w = p; p += W * W; l2_b = p; p += W; bn2_mean = p; p += W; bn2_var = p; p += W;
-        last_w = p; p += 36 * (W + 1); last_b = p; p += 4; last_logs = p;
+        last_w = p; p += 9 * cout * (W + 1); last_b = p; p += cout; last_logs = p;
     }
-    static size_t floats(int W) { return (size_t)18 * W + 3 * W + (size_t)W * W + 3 * W + 36 * (size_t)(W + 1) + 8; }
+    static size_t floats(int W, int cin = 2, int cout = 4) {
+        return (size_t)9 * cin * W + 3 * W + (size_t)W * W + 3 * W + 9 * (size_t)cout * (W + 1) + 2 * cout;
+    }
 };
 
 }  // namespace
@@ -74,6 +78,8 @@ struct WideRawView {   // sub-arrays of Layer::wraw
 struct nf_model {
     std::vector<Layer> layers;
     bool finalized = false;
+    bool has_cond = false;       // clean-image-conditioned couplings (legacy revnet2d models): every launch takes the generic
+                                 // CTA-per-patch kernel (nf_wide_cond.cu), at width 4 too
     int warps_per_cta = NF_MAX_WARPS_PER_CTA;
     int use_tc = 0;              // 1: coupling convolutions on the tensor cores (nf_tc.cu) where supported
     int bs_small = 1;            // 1: nf_chain_batch_stats runs small batches as one cooperative kernel (nf_model_set_bs_small)
@@ -264,28 +270,34 @@ int build_program(const nf_model* m, int first, int last, NfModelParams* mp, flo
     return NF_OK;
 }
 
-bool range_has_sdn(const nf_model* m, int first, int last) {
-    for (int l = first; l < last; ++l)
+bool range_has_sdn(const nf_model* m, int first, int last) {      // ... or anything else that reads the clean patch
+    for (int l = first; l < last; ++l) {
         if (m->layers[l].kind == L_SCALE && m->layers[l].scale_kind == NF_SCALE_SDN) return true;
+        if (m->layers[l].kind == L_COUPLING && m->layers[l].cmode != 0) return true;
+    }
     return false;
 }
 
 // ---- wide nets: fold one coupling into its blob block (NfWideLayout), double precision --------------------------
 // bn: explicit BatchNorm statistics [mean1 W][var1 W][mean2 W][var2 W] or null -> the stored moving statistics
 int fold_wide(const Layer& L, int W, const float* bn, const Layer* mixl, float* out) {
-    const WideRawView r(L.wraw.data(), W);
+    const int CIN = L.cin, COUT = L.cout;
+    const NfWideLayoutG lay(W, CIN, COUT);
+    const WideRawView r(L.wraw.data(), W, CIN, COUT);
     const float *m1 = bn ? bn : r.bn1_mean, *v1 = bn ? bn + W : r.bn1_var, *m2 = bn ? bn + 2 * W : r.bn2_mean,
                 *v2 = bn ? bn + 3 * W : r.bn2_var;
     const double eps = L.raw.bn_eps;
-    const int oA = 0, oAINV = 16, oMETA = 32, oB3 = 36, oB1 = 72, oB2 = oB1 + W, oW1 = oB2 + W, oW2 = oW1 + 18 * W, oW3 = oW2 + W * W;
+    const int oA = lay.A, oAINV = lay.AINV, oMETA = lay.META, oB3 = lay.B3, oB1 = lay.B1, oB2 = lay.b2(), oW1 = lay.w1(), oW2 = lay.w2(),
+              oW3 = lay.w3();
     std::vector<double> s1(W), s2(W);
     for (int o = 0; o < W; ++o) {
         if (!((double)v1[o] + eps > 0.0) || !((double)v2[o] + eps > 0.0)) return fail(NF_ERR_INVALID, "batch-norm variance + eps must be positive");
         s1[o] = 1.0 / sqrt((double)v1[o] + eps);
         s2[o] = 1.0 / sqrt((double)v2[o] + eps);
     }
-    double e[4];
-    for (int o = 0; o < 4; ++o) e[o] = exp(3.0 * (double)r.last_logs[o]);
+    memset(out, 0, (size_t)lay.size() * sizeof(float));
+    double e[8];
+    for (int o = 0; o < COUT; ++o) e[o] = exp(3.0 * (double)r.last_logs[o]);
     for (int o = 0; o < 4; ++o)
         for (int i = 0; i < 4; ++i) {
             out[oA + o * 4 + i] = mixl ? mixl->a[o][i] : (o == i ? 1.f : 0.f);
@@ -293,10 +305,11 @@ int fold_wide(const Layer& L, int W, const float* bn, const Layer* mixl, float* 
         }
     out[oMETA] = mixl ? 1.f : 0.f;
     out[oMETA + 1] = L.raw.rescaling_scale;
-    out[oMETA + 2] = out[oMETA + 3] = 0.f;
+    out[oMETA + 2] = (float)L.cmode;
+    out[oMETA + 3] = 0.f;
     for (int t = 0; t < 9; ++t)
         for (int o = 0; o < W; ++o)
-            for (int i = 0; i < 2; ++i) out[oW1 + (t * W + o) * 2 + i] = (float)((double)r.l1_w[(t * 2 + i) * W + o] * s1[o]);
+            for (int i = 0; i < CIN; ++i) out[oW1 + (t * W + o) * CIN + i] = (float)((double)r.l1_w[(t * CIN + i) * W + o] * s1[o]);
     for (int o = 0; o < W; ++o) {
         out[oB1 + o] = (float)(((double)r.l1_b[o] - (double)m1[o]) * s1[o]);
         out[oB2 + o] = (float)(((double)r.l2_b[o] - (double)m2[o]) * s2[o]);
@@ -304,17 +317,17 @@ int fold_wide(const Layer& L, int W, const float* bn, const Layer* mixl, float* 
     }
     for (int t = 0; t < 9; ++t)
         for (int i = 0; i < W; ++i)
-            for (int o = 0; o < 4; ++o) out[oW3 + (t * W + i) * 4 + o] = (float)((double)r.last_w[(t * (W + 1) + i) * 4 + o] * e[o]);
+            for (int o = 0; o < COUT; ++o) out[oW3 + (t * W + i) * COUT + o] = (float)((double)r.last_w[(t * (W + 1) + i) * COUT + o] * e[o]);
     for (int rc = 0; rc < 3; ++rc)        // edge indicator -> bias table by (row class, column class), as fold_coupling
         for (int cc = 0; cc < 3; ++cc)
-            for (int o = 0; o < 4; ++o) {
+            for (int o = 0; o < COUT; ++o) {
                 double acc = r.last_b[o];
                 for (int dy = 0; dy < 3; ++dy)
                     for (int dx = 0; dx < 3; ++dx) {
                         const bool ring = (rc == 0 && dy == 0) || (rc == 2 && dy == 2) || (cc == 0 && dx == 0) || (cc == 2 && dx == 2);
-                        if (ring) acc += (double)r.last_w[((dy * 3 + dx) * (W + 1) + W) * 4 + o];
+                        if (ring) acc += (double)r.last_w[((dy * 3 + dx) * (W + 1) + W) * COUT + o];
                     }
-                out[oB3 + (rc * 3 + cc) * 4 + o] = (float)(acc * e[o]);
+                out[oB3 + (rc * 3 + cc) * COUT + o] = (float)(acc * e[o]);
             }
     return NF_OK;
 }
@@ -446,7 +459,9 @@ int build_wide_program(const nf_model* m, int first, int last, NfWideProgram* wp
             memcpy(blob->data() + off + 16, L.ainv, sizeof(L.ainv));
             wp->op[n_ops] = NF_KOP_MIX;
         } else if (L.kind == L_COUPLING) {
-            blob->resize(off + (size_t)(tc ? nf_wide_tc_coupling_floats(W) : nf_wide_coupling_floats(W)));
+            if (tc && L.cmode != 0) return fail(NF_ERR_UNSUPPORTED, "clean-image-conditioned couplings run on the CUDA-core kernel (widths 4 / 8 / 16 / 32)");
+            if (L.cmode != 0) wp->flags |= NF_WIDE_FLAG_COND;
+            blob->resize(off + (size_t)(tc ? nf_wide_tc_coupling_floats(W) : nf_wide_coupling_floats(W, L.cin, L.cout)));
             const bool fused = l > first && (m->layers[l - 1].kind == L_CONV1X1 || m->layers[l - 1].kind == L_PERMUTE);
             int rc = tc ? fold_wide_tc(L, W, l == bn_layer ? bn_stats : nullptr, fused ? &m->layers[l - 1] : nullptr, blob->data() + off)
                         : fold_wide(L, W, l == bn_layer ? bn_stats : nullptr, fused ? &m->layers[l - 1] : nullptr, blob->data() + off);
@@ -478,7 +493,9 @@ int num_ctas_for(const nf_model* m) { return m->num_ctas > 0 ? m->num_ctas : m->
 int launch_wide_range(const nf_model* m, int first, int last, bool inverse, NfChainArgs& a, int bn_layer, const float* bn,
                       cudaStream_t stream) {
     cudaError_t e;
-    const bool tc = nf::wide_tc_width_supported(m->width) && (m->use_tc_wide || !nf::wide_width_supported(m->width));
+    const bool tc = !m->has_cond && nf::wide_tc_width_supported(m->width) && (m->use_tc_wide || !nf::wide_width_supported(m->width));
+    if (!tc && !nf::wide_width_supported(m->width))
+        return fail(NF_ERR_UNSUPPORTED, "clean-image-conditioned couplings are built for coupling-net widths 4 / 8 / 16 / 32, got %d", m->width);
     if (first == 0 && last == (int)m->layers.size() && bn_layer < 0) {
         // the launch is enqueued under the lock: nf_model_finalize swaps and retires the blob under the same lock
         std::lock_guard<std::mutex> lock(m->prog_mu);
@@ -515,10 +532,10 @@ int launch_wide_range(const nf_model* m, int first, int last, bool inverse, NfCh
 int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainArgs& a, cudaStream_t stream) {
     if (a.n < 0) return fail(NF_ERR_INVALID, "negative patch count");
     if (a.n == 0) return NF_OK;
-    if (!a.y && range_has_sdn(m, first, last)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
+    if (!a.y && range_has_sdn(m, first, last)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer / a clean-image-conditioned coupling");
     if (a.default_row < 0 || a.default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
     cudaError_t e;
-    if (m->width != 4) return launch_wide_range(m, first, last, inverse, a, -1, nullptr, stream);
+    if (m->width != 4 || m->has_cond) return launch_wide_range(m, first, last, inverse, a, -1, nullptr, stream);
     if (first == 0 && last == (int)m->layers.size()) {
         NfModelParams mp;   // snapshot under the lock: parameters travel by value with the launch
         {
@@ -559,7 +576,7 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
 
 // bijectors [lo, hi) with the BatchNorm of coupling `bn_layer` re-folded on explicit statistics (batch-statistics mode)
 int launch_custom(const nf_model* m, int lo, int hi, bool inverse, NfChainArgs& a, int bn_layer, const float* bn, cudaStream_t stream) {
-    if (m->width != 4) return launch_wide_range(m, lo, hi, inverse, a, bn_layer, bn, stream);
+    if (m->width != 4 || m->has_cond) return launch_wide_range(m, lo, hi, inverse, a, bn_layer, bn, stream);
     NfModelParams mp;
     float ldjc = 0.f;
     int rc;
@@ -689,15 +706,51 @@ static int keep_wide_raw(Layer& L, int W, const nf_coupling_weights* w) {
     for (int o = 0; o < W; ++o)
         if (!(w->bn1_var[o] + w->bn_eps > 0.f) || !(w->bn2_var[o] + w->bn_eps > 0.f))
             return fail(NF_ERR_INVALID, "batch-norm variance + eps must be positive");
-    L.wraw.resize(WideRawView::floats(W));
+    const int cin = L.cin, cout = L.cout;
+    L.wraw.resize(WideRawView::floats(W, cin, cout));
     float* p = L.wraw.data();
     auto put = [&](const float* src, size_t n) { memcpy(p, src, n * sizeof(float)); p += n; };
-    put(w->l1_w, 18 * (size_t)W); put(w->l1_b, W); put(w->bn1_mean, W); put(w->bn1_var, W);
+    put(w->l1_w, 9 * (size_t)cin * W); put(w->l1_b, W); put(w->bn1_mean, W); put(w->bn1_var, W);
     put(w->l2_w, (size_t)W * W); put(w->l2_b, W); put(w->bn2_mean, W); put(w->bn2_var, W);
-    put(w->last_w, 36 * (size_t)(W + 1)); put(w->last_b, 4); put(w->last_logs, 4);
+    put(w->last_w, 9 * (size_t)cout * (W + 1)); put(w->last_b, cout); put(w->last_logs, cout);
     L.raw.rescaling_scale = w->rescaling_scale;
     L.raw.bn_eps = w->bn_eps;
     return NF_OK;
+}
+
+static int set_coupling_mode(Layer& L, int mode) {
+    if (mode != NF_COUPLING_MODE_X && mode != NF_COUPLING_MODE_XY && mode != NF_COUPLING_MODE_Y) return fail(NF_ERR_INVALID, "unknown coupling mode %d", mode);
+    L.cmode = mode;
+    L.cin = mode == NF_COUPLING_MODE_X ? 2 : (mode == NF_COUPLING_MODE_XY ? 6 : 4);
+    L.cout = mode == NF_COUPLING_MODE_Y ? 8 : 4;
+    return NF_OK;
+}
+
+int nf_model_add_cond_coupling(nf_model* m, int mode, const nf_coupling_weights* w) {
+    if (!m) return fail(NF_ERR_INVALID, "null model");
+    if (mode == NF_COUPLING_MODE_X) return nf_model_add_affine_coupling(m, w);
+    if (!nf::wide_width_supported(m->width))
+        return fail(NF_ERR_UNSUPPORTED, "clean-image-conditioned couplings are built for coupling-net widths 4 / 8 / 16 / 32, got %d", m->width);
+    Layer L;
+    L.kind = L_COUPLING;
+    int rc = set_coupling_mode(L, mode);
+    if (!rc) rc = keep_wide_raw(L, m->width, w);
+    if (rc) return rc;
+    m->layers.push_back(L);
+    m->has_cond = true;
+    m->finalized = false;
+    return NF_OK;
+}
+
+int nf_model_set_cond_coupling(nf_model* m, int layer, const nf_coupling_weights* w) {
+    if (!m || layer < 0 || layer >= (int)m->layers.size() || m->layers[layer].kind != L_COUPLING || m->layers[layer].cmode == 0)
+        return fail(NF_ERR_INVALID, "layer %d is not a clean-image-conditioned coupling", layer);
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(m->prog_mu);
+        rc = keep_wide_raw(m->layers[layer], m->width, w);
+    }
+    return rc ? rc : ((m->finalized && !m->defer_finalize) ? nf_model_finalize(m) : NF_OK);
 }
 
 int nf_model_add_affine_coupling(nf_model* m, const nf_coupling_weights* w) {
@@ -709,6 +762,7 @@ int nf_model_add_affine_coupling(nf_model* m, const nf_coupling_weights* w) {
     else {
         rc = fold_coupling(w, &L.cp);
         if (!rc) keep_raw(L, w);
+        if (!rc) rc = keep_wide_raw(L, 4, w);     // a model with clean-image-conditioned couplings runs on the generic kernel
     }
     if (rc) return rc;
     m->layers.push_back(L);
@@ -734,10 +788,10 @@ int nf_model_finalize(nf_model* m) {
     if (!m) return fail(NF_ERR_INVALID, "null model");
     if (m->layers.empty()) return fail(NF_ERR_STATE, "model has no layers");
     int rc = NF_OK;
-    if (m->width != 4) {   // wide net: fold the whole chain and upload it to a FRESH device blob, then swap and retire the old one
+    if (m->width != 4 || m->has_cond) {   // wide / generic net: fold the whole chain and upload it to a FRESH device blob, then swap and retire the old one
         // (kernels already enqueued keep reading the old blob; cudaFree waits for them)
         for (int tc = 0; tc < 2; ++tc) {
-            if (tc ? !nf::wide_tc_width_supported(m->width) : !nf::wide_width_supported(m->width)) continue;
+            if (tc ? (m->has_cond || !nf::wide_tc_width_supported(m->width)) : !nf::wide_width_supported(m->width)) continue;
             std::vector<float> blob;
             NfWideProgram wp;
             float ldj = 0.f;
@@ -806,10 +860,12 @@ int nf_model_set_affine_coupling(nf_model* m, int layer, const nf_coupling_weigh
     int rc;
     {
         std::lock_guard<std::mutex> lock(m->prog_mu);
-        if (m->width != 4) rc = keep_wide_raw(m->layers[layer], m->width, w);
+        if (m->layers[layer].cmode != 0) rc = fail(NF_ERR_INVALID, "layer %d is a clean-image-conditioned coupling: use nf_model_set_cond_coupling", layer);
+        else if (m->width != 4) rc = keep_wide_raw(m->layers[layer], m->width, w);
         else {
             rc = fold_coupling(w, &m->layers[layer].cp);
             if (!rc) keep_raw(m->layers[layer], w);
+            if (!rc) rc = keep_wide_raw(m->layers[layer], 4, w);
         }
     }
     return rc ? rc : refinalize(m);
@@ -1219,7 +1275,7 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
         else { groups.push_back({l, l + 1}); l += 1; }
     }
     if (!inverse) std::reverse(groups.begin(), groups.end());
-    if (W == 4 && m->bs_small && !(direction == 1 && logdet) && n <= (int64_t)nf::bs_small_capacity(cached_sm_count())) {
+    if (W == 4 && !m->has_cond && m->bs_small && !(direction == 1 && logdet) && n <= (int64_t)nf::bs_small_capacity(cached_sm_count())) {
         bool ok = true;       // [mix +] coupling groups and scale layers only
         for (const auto& g : groups) {
             const int k = m->layers[g.second - 1].kind;
@@ -1348,6 +1404,7 @@ int nf_loss_and_grad(const nf_model* m, const float* x, const float* y, const in
     int rc = check_ready(m);
     if (rc) return rc;
     if (m->width != 4) return fail(NF_ERR_UNSUPPORTED, "the train-step kernels are built for coupling-net width 4, got %d", m->width);
+    if (m->has_cond) return fail(NF_ERR_UNSUPPORTED, "the train-step kernels do not cover clean-image-conditioned couplings (legacy revnet2d models)");
     if (n <= 0 || !x || !workspace || !dscratch || !grads_host) return fail(NF_ERR_INVALID, "x, workspace, dscratch, grads_host are required and n > 0");
     if (default_row < 0 || default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
     cudaStream_t stream = (cudaStream_t)stream_;

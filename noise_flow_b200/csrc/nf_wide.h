@@ -5,28 +5,50 @@
 #include <stdint.h>
 #include "nf_params.h"
 
-// One folded coupling inside the model's device blob (floats; every offset is a multiple of 4 -> float4 loads):
+// One folded coupling inside the model's device blob (floats; every offset is a multiple of 4 -> float4 loads).
+// CIN = input channels of the coupling net, COUT = its output channels:
+//   AffineCoupling           (layers.py:251-375)                  net(x0)            CIN 2, COUT 4   mode 0
+//   AffineCouplingCondXY[G]  (noise_flow_layers/AffineCouplingCondXY.py:45-79)   net(concat(x0, yy))  CIN 6, COUT 4   mode 1
+//   AffineCouplingCondY[G]   (noise_flow_layers/AffineCouplingCondY.py:44-72)    net(yy), all four channels transformed
+//                                                                                       CIN 4, COUT 8   mode 2
 //   A     [4][4]      mix, inverse direction, [o][i]            (identity when has_mix == 0)
 //   AINV  [4][4]      mix, forward direction, [o][i]
-//   META  has_mix, rescaling_scale, 0, 0
-//   B3    [3][3][4]   (b3 + edge-indicator taps) * exp(3 logs) by (row class, column class)
+//   META  has_mix, rescaling_scale, mode, 0
+//   B3    [3][3][COUT] (b3 + edge-indicator taps) * exp(3 logs) by (row class, column class)   (72 floats reserved)
 //   B1    [W]         (b1 - mean1) / sqrt(var1 + eps)
 //   B2    [W]
-//   W1    [9][W][2]   conv 3x3 2 -> W, BN-1 folded, [tap][o][i]
+//   W1    [9][W][CIN] conv 3x3 CIN -> W, BN-1 folded, [tap][o][i]
 //   W2    [W][W]      conv 1x1 W -> W, BN-2 folded, [o][i]
-//   W3    [9][W][4]   conv 3x3 W -> 4 (zero-padded h2), * exp(3 logs), [tap][i][o]
-template <int W>
-struct NfWideLayout {
-    static constexpr int A = 0, AINV = 16, META = 32, B3 = 36, B1 = 72, B2 = B1 + W, W1 = B2 + W, W2 = W1 + 18 * W,
-                         W3 = W2 + W * W, SIZE = W3 + 36 * W;
+//   W3    [9][W][COUT] conv 3x3 W -> COUT (zero-padded h2), * exp(3 logs), [tap][i][o]
+struct NfWideLayoutG {
+    int W, CIN, COUT;
+    __host__ __device__ constexpr NfWideLayoutG(int w, int cin, int cout) : W(w), CIN(cin), COUT(cout) {}
+    static constexpr int A = 0, AINV = 16, META = 32, B3 = 36, B1 = 108;
+    __host__ __device__ constexpr int b2() const { return B1 + W; }
+    __host__ __device__ constexpr int w1() const { return b2() + W + ((4 - (2 * W) % 4) % 4); }
+    __host__ __device__ constexpr int w2() const { return w1() + 9 * W * CIN + ((4 - (9 * W * CIN) % 4) % 4); }
+    __host__ __device__ constexpr int w3() const { return w2() + W * W; }
+    __host__ __device__ constexpr int size() const { return w3() + 9 * W * COUT; }
 };
-inline int nf_wide_coupling_floats(int W) { return 72 + 2 * W + 18 * W + W * W + 36 * W; }
+template <int W>
+struct NfWideLayout {      // the plain AffineCoupling (CIN 2, COUT 4)
+    static constexpr NfWideLayoutG G = NfWideLayoutG(W, 2, 4);
+    static constexpr int A = 0, AINV = 16, META = 32, B3 = 36, B1 = NfWideLayoutG::B1, B2 = G.b2(), W1 = G.w1(), W2 = G.w2(),
+                         W3 = G.w3(), SIZE = G.size();
+};
+inline int nf_wide_coupling_floats(int W, int cin = 2, int cout = 4) { return NfWideLayoutG(W, cin, cout).size(); }
+#define NF_COUPLING_MODE_X 0
+#define NF_COUPLING_MODE_XY 1
+#define NF_COUPLING_MODE_Y 2
 #define NF_WIDE_SCALE_FLOATS (NF_MAX_ROWS * 4)   // scale op: NfScaleP::t
 #define NF_WIDE_MIX_FLOATS 32                    // stand-alone mix op: a[4][4], ainv[4][4], [o][i]
 
+#define NF_WIDE_FLAG_COND 1      // the program has clean-image-conditioned couplings: stage the clean patch in shared memory
 struct NfWideProgram {           // by-value kernel argument; the parameters themselves live in the device blob
     int32_t width;
     int32_t n_layers;
+    int32_t flags;
+    int32_t pad_;
     int32_t op[NF_MAX_LAYERS];   // NfKernelOp, data -> latent order
     int32_t off[NF_MAX_LAYERS];  // float offset of the op's block in the blob
 };
@@ -54,6 +76,8 @@ inline int nf_wide_tc_coupling_floats(int W) { return NfWideTcLayout::block_byte
 
 namespace nf {
 bool wide_width_supported(int width);
+cudaError_t launch_wide_cond(const NfWideProgram& prog, const float* blob, const NfChainArgs& args, bool inverse, unsigned grid,
+                             cudaStream_t stream);
 bool wide_tc_width_supported(int width);
 cudaError_t launch_chain_wide_tc(const NfWideProgram& prog, const float* blob, const NfChainArgs& args, bool inverse, int num_sms,
                                  cudaStream_t stream);

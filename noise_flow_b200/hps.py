@@ -50,9 +50,9 @@ def hps_loader(path: str) -> Hps:
                     elif val == "False":
                         val = False
             setattr(hps, pair[0], val)
-    if not hasattr(hps, "arch") or hps.arch in ("", None):
-        raise ValueError("%s: no 'arch' entry (the legacy revnet2d path is out of scope)" % path)
-    hps.param_inits = default_param_inits(hps.arch)
+    if not hasattr(hps, "arch") or hps.arch in ("", None, "None"):
+        hps.arch = None                  # legacy revnet2d model (noise_flow_model.py:63-68): depth / sidd_cond / append_* decide
+    hps.param_inits = default_param_inits(hps.arch or "")
     return hps
 
 
@@ -73,7 +73,11 @@ def make_hps(**kw) -> Hps:
              squeeze_factor=1, squeeze_type="chessboard", n_levels=1, depth=-1, gain_init=-5.0,
              sidd_cond="mix", x_shape=[None, 32, 32, 4])
     d.update(kw)
+    if not d.get("arch"):                # legacy revnet2d model: the reference's ArgParser defaults for the keys it reads
+        for k, v in (("append_sdn2", False), ("append_sdn_first", False), ("append_cY", False), ("append_sdn", False)):
+            d.setdefault(k, v)
+        d["arch"] = None
     h = Hps(**d)
     if not hasattr(h, "param_inits"):
-        h.param_inits = default_param_inits(h.arch)
+        h.param_inits = default_param_inits(h.arch or "")
     return h

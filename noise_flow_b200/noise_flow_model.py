@@ -41,8 +41,8 @@ class _Engine:
             self._add(idx, l)
         self._finalized = False
 
-    def _coupling_struct(self, l):
-        w = self.spec.coupling_weights(l)
+    def _coupling_struct(self, l, iso=100.0):
+        w = self.spec.coupling_weights(l, iso)
         st = _lib.NfCouplingWeights()
         keep = []
         for k in ("l1_w", "l1_b", "bn1_mean", "bn1_var", "l2_w", "l2_b", "bn2_mean", "bn2_var", "last_w",
@@ -65,7 +65,11 @@ class _Engine:
             _lib.check(lib.nf_model_add_permute(h, perm), "nf_model_add_permute")
         elif l.kind == "coupling":
             st, keep = self._coupling_struct(l)
-            _lib.check(lib.nf_model_add_affine_coupling(h, C.byref(st)), "nf_model_add_affine_coupling")
+            mode = int(l.data.get("mode", 0))
+            if mode == 0:
+                _lib.check(lib.nf_model_add_affine_coupling(h, C.byref(st)), "nf_model_add_affine_coupling")
+            else:       # clean-image-conditioned couplings of the legacy revnet2d models
+                _lib.check(lib.nf_model_add_cond_coupling(h, mode, C.byref(st)), "nf_model_add_cond_coupling")
             del keep
         elif l.kind == "scale":
             tab = np.ascontiguousarray(self.spec.scale_table(l), np.float32)
@@ -86,8 +90,9 @@ class _Engine:
             tab = np.ascontiguousarray(self.spec.scale_table(self.spec.layers[idx], extra), np.float32)
             _lib.check(self.lib.nf_model_set_scale(self.handle, idx, _fp(tab), tab.shape[0]), "nf_model_set_scale")
 
-    def refresh_parameters(self, extra=None):
-        """Re-upload every layer from the variable store (after an optimizer step / BN update)."""
+    def refresh_parameters(self, extra=None, iso=100.0):
+        """Re-upload every layer from the variable store (after an optimizer step / BN update); ``iso`` = the ISO the
+        ISO-conditioned templates (legacy ``G`` couplings) are evaluated at."""
         lib, h = self.lib, self.handle
         _lib.check(lib.nf_model_begin_update(h), "nf_model_begin_update")     # set every layer, fold / upload once
         try:
@@ -97,8 +102,11 @@ class _Engine:
                     a32, i32 = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(a_inv, np.float32)
                     _lib.check(lib.nf_model_set_conv1x1(h, idx, _fp(a32), _fp(i32), lad), "nf_model_set_conv1x1")
                 elif l.kind == "coupling":
-                    st, keep = self._coupling_struct(l)
-                    _lib.check(lib.nf_model_set_affine_coupling(h, idx, C.byref(st)), "nf_model_set_affine_coupling")
+                    st, keep = self._coupling_struct(l, iso)
+                    if int(l.data.get("mode", 0)) == 0:
+                        _lib.check(lib.nf_model_set_affine_coupling(h, idx, C.byref(st)), "nf_model_set_affine_coupling")
+                    else:
+                        _lib.check(lib.nf_model_set_cond_coupling(h, idx, C.byref(st)), "nf_model_set_cond_coupling")
                     del keep
             self.update_scale_tables(extra)
         finally:
@@ -115,6 +123,21 @@ class _Engine:
 
 def _stream_ptr(device) -> int:
     return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _iso_guarded(fn):
+    """Run a NoiseFlow method under :meth:`NoiseFlow._iso_guard` (a no-op unless the model has ISO-conditioned templates)."""
+    import functools
+    import inspect
+    sig = inspect.signature(fn)
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kw):
+        if not self.spec.has_iso_templates:
+            return fn(self, *args, **kw)
+        with self._iso_guard(sig.bind(self, *args, **kw).arguments.get("iso")):
+            return fn(self, *args, **kw)
+    return wrapper
 
 
 class NoiseFlow(object):
@@ -151,9 +174,13 @@ class NoiseFlow(object):
         self._lock = threading.Lock()
         self._tls = threading.local()
         self._stale = False
-        self._extra_rows: List[tuple] = []
+        self._extra_rows: List[tuple] = []      # slot k <-> conditioning row 25 + k (stable: see _row_for)
+        self._extra_used: Dict[int, int] = {}
+        self._extra_tick = 0
         self._seed = seed
         self._sample_calls = 0
+        self._folded_iso = 100.0         # ISO the ISO-conditioned templates are currently folded at (legacy G couplings)
+        self._iso_lock = threading.RLock()
         if first_call is not None:
             self.build(first_call)
 
@@ -182,8 +209,35 @@ class NoiseFlow(object):
     def refresh_parameters(self):
         if self._engine is not None:
             with self._lock:
-                self._engine.refresh_parameters(self._extra_rows)
+                self._engine.refresh_parameters(self._extra_rows, self._folded_iso)
                 self._stale = False
+
+    class _NoGuard(object):
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    def _iso_guard(self, iso):
+        """Models with ISO-conditioned templates (``real_nvp_conv_template_iso``, layers.py:501-547: ``w = B1 * iso[0] + B2``)
+        evaluate their coupling nets at the minibatch's ISO: re-fold when it changes, and keep concurrent callers with
+        different ISOs apart for the duration of the call.  Every other model: no-op."""
+        if not self.spec.has_iso_templates:
+            return NoiseFlow._NoGuard()
+        arr = np.asarray(100.0 if iso is None else iso, dtype=np.float64).reshape(-1)
+        if len(arr) > 1 and not np.all(arr == arr[0]):
+            raise ValueError("ISO-conditioned coupling nets take ONE iso per call (the reference reads iso[0], layers.py:633)")
+        self._iso_lock.acquire()
+        try:
+            if float(arr[0]) != self._folded_iso:
+                self.build()
+                self._folded_iso = float(arr[0])
+                self.refresh_parameters()
+        except BaseException:
+            self._iso_lock.release()
+            raise
+        return self._iso_lock
 
     def _fresh(self):
         """Re-fold the engine if the BatchNorm moving statistics were moved since the last fold.  A batch-statistics
@@ -332,26 +386,46 @@ class NoiseFlow(object):
             iso_f = np.broadcast_to(iso_a, (n,))
             cam_f = np.broadcast_to(cam_a, (n,))
             rows = np.empty(n, dtype=np.int32)
-            for key in set(zip(cam_f.tolist(), iso_f.tolist())):
-                r = self._row_for(key[0], key[1], float(n0_a[0]), float(n1_a[0]), needs_nlf)
+            keys = sorted(set(zip(cam_f.tolist(), iso_f.tolist())))
+            pinned = set()                # non-standard rows this batch uses: never recycled while the batch is assembled
+            for key in keys:
+                r = self._row_for(key[0], key[1], float(n0_a[0]), float(n1_a[0]), needs_nlf, pinned)
                 rows[(cam_f == key[0]) & (iso_f == key[1])] = r
             return torch.as_tensor(rows, device=self.device), 0
-        return None, self._row_for(float(cam_a[0]), float(iso_a[0]), float(n0_a[0]), float(n1_a[0]), needs_nlf)
+        return None, self._row_for(float(cam_a[0]), float(iso_a[0]), float(n0_a[0]), float(n1_a[0]), needs_nlf, set())
 
-    def _row_for(self, cam, iso, n0, n1, needs_nlf) -> int:
+    def _row_for(self, cam, iso, n0, n1, needs_nlf, pinned) -> int:
+        """Conditioning-table row of (cam, iso[, nlf0, nlf1]).  Rows 0..24 are the standard (camera, ISO) grid; anything else
+        (unknown ISO, explicit camera NLF of `camsdn`) lives in one of MAX_ROWS - 25 = 7 extra slots.  A slot keeps its row id
+        for as long as its key stays: a new key overwrites the least recently used slot IN PLACE, never one the current batch
+        uses (more than 7 distinct non-standard keys in one batch raise)."""
         r = None if needs_nlf else std_row(cam, iso)
         if r is not None:
             return r
         key = (cam, iso, n0, n1) if needs_nlf else (cam, iso, 0.0, 1.0)
+        n_slots = MAX_ROWS - N_STD_ROWS
         with self._lock:
-            if key not in self._extra_rows:
-                if N_STD_ROWS + len(self._extra_rows) >= MAX_ROWS:
-                    self._extra_rows.pop(0)          # recycle the oldest non-standard conditioning row
-                self._extra_rows.append(key)
-                self._engine.update_scale_tables(self._extra_rows)
-            return N_STD_ROWS + self._extra_rows.index(key)
+            slots = self._extra_rows
+            if key in slots:
+                idx = slots.index(key)
+            else:
+                if len(slots) < n_slots:
+                    slots.append(key)
+                    idx = len(slots) - 1
+                else:
+                    free = [k for k in sorted(range(n_slots), key=lambda k: self._extra_used.get(k, 0)) if k not in pinned]
+                    if not free:
+                        raise ValueError("more than %d distinct non-standard (cam, iso[, nlf]) keys in one batch" % n_slots)
+                    idx = free[0]
+                    slots[idx] = key                 # in place: the other slots keep their row ids
+                self._engine.update_scale_tables(slots)
+            self._extra_tick += 1
+            self._extra_used[idx] = self._extra_tick
+            pinned.add(idx)
+            return N_STD_ROWS + idx
 
     # ------------------------------------------------------------------ reference API
+    @_iso_guarded
     def inverse(self, x, objective, yy=None, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None):
         """noise_flow_model.py:394-428 -> ``(z, objective + sum of log-dets)``."""
         training = self._check_training(is_training)
@@ -378,6 +452,7 @@ class NoiseFlow(object):
         obj = objective if isinstance(objective, torch.Tensor) else torch.as_tensor(np.asarray(objective))
         return z, obj.to(self.device, torch.float32) + ld
 
+    @_iso_guarded
     def forward(self, z, eps_std=None, yy=None, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None):
         """noise_flow_model.py:430-447 (``eps_std`` only matters for multi-level models, as in the reference)."""
         training = self._check_training(is_training)
@@ -396,6 +471,7 @@ class NoiseFlow(object):
                                         x.data_ptr(), None, _stream_ptr(self.device)), "nf_forward")
         return x
 
+    @_iso_guarded
     def sample(self, y, eps_std=None, yy=None, nlf0=None, nlf1=None, iso=None, cam=None, is_training=None,
                eps=None, seed=None, offset=None, patch_base: int = 0):
         """noise_flow_model.py:449-456: ``z = eps * eps_std``, ``x = forward(z)``.
@@ -430,6 +506,7 @@ class NoiseFlow(object):
                                        x.data_ptr(), _stream_ptr(self.device)), "nf_sample")
         return x
 
+    @_iso_guarded
     def _loss(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, reuse=False, is_training=None, return_z=False):
         """noise_flow_model.py:458-480 -> ``(nll[N], sd_z)``."""
         training = self._check_training(is_training)
@@ -491,6 +568,7 @@ class NoiseFlow(object):
         return logp, sample
 
     # ------------------------------------------------------------------ per-bijector access (tests, config 1)
+    @_iso_guarded
     def run_layers(self, first: int, last: int, direction: str, x, yy=None, nlf0=None, nlf1=None, iso=None, cam=None):
         """``_inverse_and_log_det_jacobian`` / ``_forward_and_log_det_jacobian`` of bijectors first..last-1."""
         self.build("inverse")

@@ -4,6 +4,8 @@ needed, so everything here is covered by the CPU test-suite.
 
 Reference being mirrored (paths relative to the reference repo):
   * ``borealisflows/noise_flow_model.py:71-235``  arch string -> bijector list, scopes and names
+  * ``borealisflows/noise_flow_model.py:237-392`` legacy ``revnet2d`` models (``hps.arch`` unset): clean-image-conditioned
+    couplings, ISO-conditioned templates (``layers.py:501-547,616-648``), ISO-polynomial scale layers (``cond_utils.py:11-38``)
   * ``borealisflows/matrix_param.py:31-140``       LU parameterisation of the 1x1 conv
   * ``borealisflows/noise_flow_layers/cond_utils.py``  scale functions of the sdn*/gain* layers
   * ``borealisflows/layers.py:271-273,598-599,662-673,382-387``  initialisers
@@ -24,7 +26,8 @@ MAX_ROWS = 32                                              # NF_MAX_ROWS in csrc
 BN_EPS = 1e-4                                              # layers.py:378
 
 SCALE_SDN, SCALE_GAIN = 1, 2                               # include/noiseflow_b200.h
-SDN_TOKENS = ("sdn", "sdn1", "sdn2", "sdn3", "sdn4", "sdn5", "sdn6", "camsdn")
+SDN_TOKENS = ("sdn", "sdn1", "sdn2", "sdn3", "sdn4", "sdn5", "sdn6", "camsdn", "sdngain", "fitsdngain2")
+COUPLING_X, COUPLING_XY, COUPLING_Y = 0, 1, 2              # include/noiseflow_b200.h NF_COUPLING_*
 GAIN_TOKENS = ("gain", "gain1", "gain2", "gain3", "gain4")
 # Gain, GainEx1, GainEx3 return log(scale) without the sum over the 4096 dims (AffineCouplingGain.py:86,96,111,125)
 NO_FULL_SUM = ("gain", "gain1", "gain3")
@@ -154,7 +157,11 @@ class ModelSpec:
         self.width = int(hps.width)
         self.layers: List[LayerSpec] = []
         self._template_scopes_assigned = False
-        self._parse_arch(hps.arch, hps.flow_permutation)
+        if getattr(hps, "arch", None):                                       # noise_flow_model.py:63-68
+            self._parse_arch(hps.arch, hps.flow_permutation)
+        else:
+            self._parse_revnet2d(hps.flow_permutation)
+        self.has_iso_templates = any(l.kind == "coupling" and l.data.get("iso") for l in self.layers)
 
     # ---- noise_flow_model.py:71-235 ---------------------------------------------------------------
     def _parse_arch(self, arch: str, flow_permutation: int):
@@ -178,6 +185,55 @@ class ModelSpec:
                 pre = "gain" if lyr in GAIN_TOKENS else "sdn"
                 self.layers.append(LayerSpec("scale", "%s_%d" % (pre, i), scope, token=lyr))
             # any other token falls through the reference's if/elif chain and adds nothing
+
+    # ---- noise_flow_model.py:237-392 ---------------------------------------------------------------
+    def _parse_revnet2d(self, flow_permutation: int):
+        """Legacy models: ``depth`` x ([permutation] + a bijector chosen by ``hps.sidd_cond``) plus the ``append_*`` layers."""
+        st, h = self.store, self.hps
+        ic = self.x_shape[-1]
+        depth = int(h.depth)
+        name = "level0"
+
+        def scale(token, scope, lname):
+            st.get(scope + "/rescaling_scale0", (), 1e-4)
+            self.layers.append(LayerSpec("scale", lname, scope, token=token))
+
+        def coupling(mode, iso, scope, lname):
+            st.get(scope + "/rescaling_scale0", (), 1e-4)
+            self.layers.append(LayerSpec("coupling", lname, scope, data={"template": None, "mode": mode, "iso": iso}))
+
+        if getattr(h, "append_sdn2", False):                                                         # :243-253
+            scale("fitsdngain2", name + "/bijector_sdn2", "ac_fitSdnGain2_%d" % depth)
+        if getattr(h, "append_sdn_first", False):                                                    # :255-265
+            scale("sdngain", name + "/bijector_sdn", "ac_fitSdnGain_%d" % depth)
+        if getattr(h, "append_cY", False):                                                           # :267-279
+            coupling(COUPLING_Y, False, name + "/bijector_cy", "ac_cY_first")
+        for i in range(depth):                                                                       # :280-378
+            scope = "%s/bijector%d" % (name, i)
+            if flow_permutation == 0:
+                self.layers.append(LayerSpec("permute", "permute", scope, data={"perm": list(range(ic))[::-1]}))
+            elif flow_permutation == 1:
+                lname = "Conv2d_1x1_%d" % i
+                self._create_conv1x1(scope + "/" + lname, "conv2d_1x1_%d_0" % i, ic)
+                self.layers.append(LayerSpec("conv1x1", lname, scope,
+                                             data={"vscope": scope + "/" + lname, "pname": "conv2d_1x1_%d_0" % i}))
+            cond = getattr(h, "sidd_cond", "uncond")
+            if cond == "condY":
+                coupling(COUPLING_Y, False, scope, "ac_cY_%d" % i)
+            elif cond == "condYG":
+                coupling(COUPLING_Y, True, scope, "ac_cYG_%d" % i)
+            elif cond == "condXY":
+                coupling(COUPLING_XY, False, scope, "ac_cXY_%d" % i)
+            elif cond == "condXYG":
+                coupling(COUPLING_XY, True, scope, "ac_cXYG_%d" % i)
+            elif cond == "condSDN":
+                scale("camsdn", scope, "ac_cSDN_%d" % i)
+            elif cond == "fitSDN":
+                scale("sdngain", scope, "ac_fitSDN_%d" % i)
+            else:                                                                                    # uncond | unc_sdn
+                coupling(COUPLING_X, False, scope, "ac_unc_%d" % i)
+        if getattr(h, "append_sdn", False):                                                          # :379-390
+            scale("sdngain", "%s/bijector%d" % (name, depth), "ac_fitSDN_%d" % depth)
 
     def _create_conv1x1(self, vscope: str, pname: str, n: int):
         """Conv2d1x1._init_weights (layers.py:92-100) + matrix_param_lu initialisers (matrix_param.py:100-126)."""
@@ -214,24 +270,36 @@ class ModelSpec:
         cps = [l for l in self.layers if l.kind == "coupling"]
         order = cps if first_call == "inverse" else list(reversed(cps))
         for l in order:
-            l.data["template"] = self.store.unique_scope("model", "real_nvp_conv_template")
-            self._create_template(l.data["template"])
+            iso = bool(l.data.get("iso"))
+            l.data["template"] = self.store.unique_scope("model", "real_nvp_conv_template_iso" if iso else "real_nvp_conv_template")
+            mode = l.data.get("mode", COUPLING_X)
+            self._create_template(l.data["template"], cin={COUPLING_X: 2, COUPLING_XY: 6, COUPLING_Y: 4}[mode],
+                                  cout=8 if mode == COUPLING_Y else 4, iso=iso)
         self._template_scopes_assigned = True
 
-    def _create_template(self, s: str):
+    def _create_template(self, s: str, cin: int = 2, cout: int = 4, iso: bool = False):
+        """real_nvp_conv_template (layers.py:452-498) / real_nvp_conv_template_iso (:501-547, conv2d_iso :616-648)."""
         st, w = self.store, self.width
         std = w / 512 * 0.05                                                                     # layers.py:598-599
-        st.get(s + "/l_1/W", (3, 3, 2, w), lambda: st.rng.randn(3, 3, 2, w) * std)
-        st.get(s + "/l_1/b", (1, 1, 1, w), 0.0)
+        def conv(nm, shp):           # variables in the reference's creation order: conv (W, b | B1, B2, C1, C2), then its BatchNorm
+            if iso:                                                                              # :631-647, init_sd = 0.05
+                for v in ("B1", "B2"):
+                    st.get("%s/%s/%s" % (s, nm, v), shp, lambda: st.rng.randn(*shp) * 0.05)
+                for v in ("C1", "C2"):
+                    st.get("%s/%s/%s" % (s, nm, v), (1, 1, 1, w), lambda: st.rng.randn(1, 1, 1, w) * 0.05)
+            else:
+                st.get("%s/%s/W" % (s, nm), shp, lambda: st.rng.randn(*shp) * std)
+                st.get("%s/%s/b" % (s, nm), (1, 1, 1, w), 0.0)
+
+        conv("l_1", (3, 3, cin, w))
         st.get(s + "/bn_nvp_conv_1/mean", (w,), 0.0, trainable=False)                            # layers.py:382-387
         st.get(s + "/bn_nvp_conv_1/var", (w,), 1.0, trainable=False)
-        st.get(s + "/l_2/W", (1, 1, w, w), lambda: st.rng.randn(1, 1, w, w) * std)
-        st.get(s + "/l_2/b", (1, 1, 1, w), 0.0)
+        conv("l_2", (1, 1, w, w))
         st.get(s + "/bn_nvp_conv_2/mean", (w,), 0.0, trainable=False)
         st.get(s + "/bn_nvp_conv_2/var", (w,), 1.0, trainable=False)
-        st.get(s + "/l_last/W", (3, 3, w + 1, 4), 0.0)                                           # layers.py:662-663
-        st.get(s + "/l_last/b", (1, 1, 1, 4), 0.0)
-        st.get(s + "/l_last/logs", (1, 4), 0.0)
+        st.get(s + "/l_last/W", (3, 3, w + 1, cout), 0.0)                                        # layers.py:662-663
+        st.get(s + "/l_last/b", (1, 1, 1, cout), 0.0)
+        st.get(s + "/l_last/logs", (1, cout), 0.0)
 
     def create_scale_variables(self):
         """Scale-layer variables are created when the bijector is first called under scope 'model'."""
@@ -249,13 +317,21 @@ class ModelSpec:
                             v["%s/U_vec_matpar_lu_%s" % (s, p)], v["%s/log_S_matpar_lu_%s" % (s, p)],
                             v["%s/sign_S_matpar_lu_%s" % (s, p)])
 
-    def coupling_weights(self, l: LayerSpec) -> Dict[str, np.ndarray]:
+    def coupling_weights(self, l: LayerSpec, iso: float = 100.0) -> Dict[str, np.ndarray]:
+        """Reference-shaped tensors of a coupling's net.  ISO-conditioned templates (conv2d_iso, layers.py:616-648):
+        ``w = B1 * iso[0] + B2``, ``b = C1 * iso[0] + C2`` -- the effective weights for the call's ISO (fp32 arithmetic as TF)."""
         v, s = self.store.vars, l.data["template"]
         if s is None:
             raise RuntimeError("template scopes not assigned yet (call assign_template_scopes)")
         c = lambda a: np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
-        return dict(l1_w=c(v[s + "/l_1/W"]), l1_b=c(v[s + "/l_1/b"]), bn1_mean=c(v[s + "/bn_nvp_conv_1/mean"]),
-                    bn1_var=c(v[s + "/bn_nvp_conv_1/var"]), l2_w=c(v[s + "/l_2/W"]), l2_b=c(v[s + "/l_2/b"]),
+        if l.data.get("iso"):
+            i0 = np.float32(iso)
+            l1w, l1b = v[s + "/l_1/B1"] * i0 + v[s + "/l_1/B2"], v[s + "/l_1/C1"] * i0 + v[s + "/l_1/C2"]
+            l2w, l2b = v[s + "/l_2/B1"] * i0 + v[s + "/l_2/B2"], v[s + "/l_2/C1"] * i0 + v[s + "/l_2/C2"]
+        else:
+            l1w, l1b, l2w, l2b = v[s + "/l_1/W"], v[s + "/l_1/b"], v[s + "/l_2/W"], v[s + "/l_2/b"]
+        return dict(l1_w=c(l1w), l1_b=c(l1b), bn1_mean=c(v[s + "/bn_nvp_conv_1/mean"]),
+                    bn1_var=c(v[s + "/bn_nvp_conv_1/var"]), l2_w=c(l2w), l2_b=c(l2b),
                     bn2_mean=c(v[s + "/bn_nvp_conv_2/mean"]), bn2_var=c(v[s + "/bn_nvp_conv_2/var"]),
                     last_w=c(v[s + "/l_last/W"]), last_b=c(v[s + "/l_last/b"]), last_logs=c(v[s + "/l_last/logs"]),
                     rescaling_scale=float(v[l.scope + "/rescaling_scale0"]))
@@ -292,6 +368,12 @@ def scale_row(token: str, store: VariableStore, hps, cam: float, iso: float, nlf
     """(a, b) for sdn tokens, (g, 0) for gain tokens, for one (cam, iso[, nlf0, nlf1]) conditioning class."""
     g = store.get
     gain_init = float(getattr(hps, "gain_init", 0.0))
+    if token in ("sdngain", "fitsdngain2"):                                                     # cond_utils.py:11-38 (ISO polynomials)
+        e = lambda n: math.exp(float(g("model/" + n, (1,), -6.0)[0]))
+        i0 = float(iso)
+        if token == "sdngain":                                                                   # sdn_iso_model_params_3
+            return e("p1") * i0 ** 2 + e("p2") * i0 + e("p3"), e("q1") * i0 ** 3 + e("q2") * i0 ** 2 + e("q3") * i0 + e("q4")
+        return e("p2") * i0 + e("p3"), e("q2") * i0 ** 2 + e("q3") * i0 + e("q4")               # sdn_iso_model_params_2
     if token == "sdn":                                                                           # cond_utils.py:41-52
         return _sigmoid(g("model/b1", (1,), -3.0)[0]), _sigmoid(g("model/b2", (1,), 3.0)[0])
     if token == "sdn1":                                                                          # :55-97

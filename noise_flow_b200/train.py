@@ -153,7 +153,7 @@ def _tick(name):
         _t_last[0] = now
 
 
-def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_training=True, refold=True):
+def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_training=True, refold=True, bn_update=True):
     """``(loss, sd_z, grads)``: ``loss = mean_n nll_n`` (``NoiseFlow.loss``) and ``grads[tf_variable_name]`` (float64
     numpy, same shapes as the variables) for every trainable variable.  With ``is_training`` (the reference's train
     thread, ``train_noise_flow.py:64-71``) BatchNorm runs on batch statistics and the moving statistics are updated."""
@@ -217,8 +217,10 @@ def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_trainin
         if trainable and name not in grads:
             grads[name] = np.zeros(v[name].shape, dtype=np.float64)
     _tick("chain_rules")
-    if is_training:
+    if is_training and bn_update:
         nf._apply_bn_moving_update(bstats, refold=refold)    # refold=False: the caller re-folds after its optimizer step
+    elif is_training:
+        nf.last_batch_stats = bstats                         # bn_update=False: the caller averages them over ranks first
     _tick("bn_update_refold")
     loss = sums[0] / n
     sd_z = sums[1] / n
@@ -253,14 +255,18 @@ def train_step(nf, optimizer: AdamOptimizer, x, y, nlf0=None, nlf1=None, iso=Non
     """One ``sess.run([train_op, loss, sd_z], is_training=True)`` (train_noise_flow.py:50-77) on this rank's shard.
     With ``torch.distributed`` initialised, gradients and ``[sum nll, sum sd_z, n]`` are summed over ranks with ONE
     all-reduce (gradients are then divided by the world size: every rank's loss is the mean over ITS shard, and
-    BatchNorm statistics stay per rank, which is the reference's per-``sess.run`` semantics)."""
+    BatchNorm NORMALISES with per-rank statistics, which is the reference's per-``sess.run`` semantics).  The batch
+    statistics ride in the same buffer: the moving averages move towards their rank average, exactly as
+    ``DeviceTrainer.step`` does, so replicas -- and checkpoints written by any rank -- stay identical."""
     import torch.distributed as dist
-    loss, sd_z, grads = loss_and_grad(nf, x, y, nlf0, nlf1, iso, cam, is_training=True, refold=False)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    loss, sd_z, grads = loss_and_grad(nf, x, y, nlf0, nlf1, iso, cam, is_training=True, refold=False, bn_update=not multi)
     names = sorted(grads)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if multi:
         world = dist.get_world_size(group)
         n = int(np.asarray(x).shape[0]) if not isinstance(x, torch.Tensor) else x.shape[0]
-        flat = np.concatenate([grads[k].reshape(-1) for k in names] + [np.array([loss * n, sd_z * n, float(n)])])
+        bstats = np.asarray(nf.last_batch_stats, dtype=np.float64)
+        flat = np.concatenate([grads[k].reshape(-1) for k in names] + [np.array([loss * n, sd_z * n, float(n)]), bstats.reshape(-1)])
         t = torch.as_tensor(flat, dtype=torch.float64, device=nf.device if dist.get_backend(group) == "nccl" else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         flat = t.cpu().numpy()
@@ -270,6 +276,7 @@ def train_step(nf, optimizer: AdamOptimizer, x, y, nlf0=None, nlf1=None, iso=Non
             grads[k] = flat[o:o + sz].reshape(grads[k].shape) / world
             o += sz
         loss, sd_z = flat[o] / flat[o + 2], flat[o + 1] / flat[o + 2]
+        nf._apply_bn_moving_update((flat[o + 3:o + 3 + bstats.size].reshape(bstats.shape) / world).astype(np.float32), refold=False)
     trainable = {k: g for k, g in grads.items() if nf.spec.store.trainable.get(k, False)}
     _tick("allreduce")
     optimizer.apply_gradients(nf.spec.store.vars, trainable)

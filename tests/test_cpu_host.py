@@ -163,7 +163,7 @@ def test_c_abi_argument_validation_without_gpu():
     lib = _lib.load()
     h = C.c_void_p()
     assert lib.nf_model_create(16, 16, 16, 4, C.byref(h)) == -2 and b"32x32x4" in lib.nf_last_error()
-    assert lib.nf_model_create(32, 32, 4, 512, C.byref(h)) == -2
+    assert lib.nf_model_create(32, 32, 4, 48, C.byref(h)) == -2       # widths: 4, 8, 16, 32, 64, 128, 256, 512
     assert lib.nf_model_create(32, 32, 4, 12, C.byref(h)) == -2              # wide kernel: widths 8 / 16 / 32
     hw = C.c_void_p()
     assert lib.nf_model_create(32, 32, 4, 32, C.byref(hw)) == 0 and hw.value and lib.nf_model_destroy(hw) == 0

@@ -236,6 +236,25 @@ def test_metrics_match_reference_numpy_code():
     assert np.array_equal(g["unpacked"], g["bayer"]) and g["packed"].shape == (4, 6, 4)
 
 
+def test_host_model_spec_reproduces_reference_legacy_graphs():
+    """The product's host-side assembly (noise_flow_b200.params.ModelSpec) of the legacy revnet2d models: bijector names,
+    exactly the reference graph's variables (nothing created, nothing unused), trainable-parameter count."""
+    from noise_flow_b200 import make_hps
+    from noise_flow_b200.params import ModelSpec
+    lc = _load("ref_legacy_cases.npz")
+    for tag in sorted({k.split("::")[0] for k in lc.files}):
+        g = {k.split("::", 1)[1]: lc[k] for k in lc.files if k.startswith(tag + "::")}
+        flags = {str(f): True for f in g["flags"]}
+        hps = make_hps(arch=None, depth=int(g["depth"]), sidd_cond=str(g["sidd_cond"]), flow_permutation=int(g["flow_permutation"]), **flags)
+        variables = {k[len("var/"):]: v for k, v in g.items() if k.startswith("var/")}
+        spec = ModelSpec(hps, variables)
+        spec.assign_template_scopes("inverse")
+        spec.create_scale_variables()
+        assert spec.get_layer_names() == list(g["layer_names"]), tag
+        assert not spec.store.created and set(spec.store.vars) == set(variables), tag
+        assert spec.store.num_trainable() == int(g["num_params"]), tag
+
+
 def _legacy_tags():
     lc = _load("ref_legacy_cases.npz")
     return sorted({k.split("::")[0] for k in lc.files})
@@ -245,8 +264,8 @@ def _legacy_tags():
 def test_oracle_reproduces_reference_legacy_revnet2d_cases(tag):
     """`hps.arch` unset -> `revnet2d` (noise_flow_model.py:237-392): the clean-image-conditioned couplings CondY / CondYG /
     CondXY / CondXYG (the G variants with ISO-conditioned convolutions), CamSdn, the ISO-polynomial SdnGain / FitSdnGain2
-    layers and the append_* options.  Oracle only (the CUDA engine implements the `hps.arch` path); the goldens are the
-    reference's own classes executed over the TF stand-in."""
+    layers and the append_* options; the goldens are the reference's own classes executed over the TF stand-in (the CUDA
+    path runs the same cases in tests/test_gpu_reference_goldens.py)."""
     from types import SimpleNamespace
     lc = _load("ref_legacy_cases.npz")
     g = {k.split("::", 1)[1]: lc[k] for k in lc.files if k.startswith(tag + "::")}
