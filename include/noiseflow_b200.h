@@ -174,9 +174,11 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
                          int32_t default_row, int64_t n, float temp, uint64_t seed, uint64_t offset,
                          uint64_t patch_base, float* out, float* logdet, float* nll, float* sdz, double* stats_ws,
                          float* batch_stats_host, void* stream);
-/* 1 (default): nf_chain_batch_stats runs batches of up to one co-resident CTA per patch (296 patches on a B200; width-4
- * chains of [1x1 conv / permutation +] coupling groups and scale layers) as ONE cooperative kernel -- the reference
- * sampling script's call pattern is one patch per sess.run (sample_noise_flow.py:44,71); 0: always layer by layer. */
+/* 1 (default): nf_chain_batch_stats runs batches of up to 4096 patches (width-4 chains of [1x1 conv / permutation +] coupling
+ * groups and scale layers) as ONE cooperative kernel with no host round trip -- one co-resident CTA per patch up to 296
+ * patches on a B200 (the reference sampling script's call pattern is one patch per sess.run, sample_noise_flow.py:44,71),
+ * the same kernel walking its patches grid-stride beyond (train_noise_flow.py:165-167 samples whole test minibatches in
+ * this mode); 0: always layer by layer (two probe launches + a stream synchronisation each, per coupling). */
 int nf_model_set_bs_small(nf_model* m, int enable);
 
 /* ---- training step support: loss and its gradient (train_noise_flow.py:187-198, 50-77) -------------------- */

@@ -91,19 +91,26 @@ struct nf_model {
     int sm_count = 0;
     NfModelParams full = {};     // fused program of the whole chain
     float full_ldj_const = 0.f;
-    std::mutex pool_mu;          // guards the _host staging pool
-    mutable std::mutex prog_mu;  // guards `layers` / `full` against a concurrent nf_model_set_* (launches snapshot)
+    // _host entry points: every call borrows a HostPipe (staging slots + streams) from this free list and gives it back at
+    // the end, so concurrent host callers (the reference's 16-32 sampler threads, train_dncnn_noiseflow.py:195-198) each
+    // run their own copy/compute pipeline; a pipe's slots are sized by the largest call it has served (<= kChunk patches)
+    std::mutex pool_mu;          // guards pipes_free only
     struct Staging {
         float *x = nullptr, *y = nullptr, *z = nullptr, *nll = nullptr, *sdz = nullptr;
         int32_t* rows = nullptr;
+        int64_t cap = 0;         // patches this slot's buffers hold
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-    } st[4];                     // staging slots of the _host pipeline (kSlots)
+    };
     static constexpr int kSlots = 4;
-    double* d_sums = nullptr;
-    int64_t chunk = 0;
-    float* h_tmp = nullptr;      // pinned scratch for per-patch results the caller did not ask for (sums only)
-    size_t h_tmp_floats = 0;
+    struct HostPipe {
+        Staging st[kSlots];
+        float* h_tmp = nullptr;      // pinned scratch for per-patch results the caller did not ask for (sums only)
+        size_t h_tmp_floats = 0;
+    };
+    std::vector<HostPipe*> pipes_free;
+    int pipes_total = 0;
+    mutable std::mutex prog_mu;  // guards `layers` / `full` against a concurrent nf_model_set_* (launches snapshot)
     // wide coupling nets (width 8 / 16 / 32, nf_wide.cu): the folded program of the whole chain lives in a device
     // blob owned by the handle (re-uploaded by nf_model_finalize / nf_model_set_*)
     int width = 4;
@@ -636,18 +643,20 @@ int nf_model_create(int height, int width, int channels, int net_width, nf_model
 
 int nf_model_destroy(nf_model* m) {
     if (!m) return NF_OK;
-    for (auto& s : m->st) {
-        if (s.x) cudaFree(s.x);
-        if (s.y) cudaFree(s.y);
-        if (s.z) cudaFree(s.z);
-        if (s.nll) cudaFree(s.nll);
-        if (s.sdz) cudaFree(s.sdz);
-        if (s.rows) cudaFree(s.rows);
-        if (s.done) cudaEventDestroy(s.done);
-        if (s.stream) cudaStreamDestroy(s.stream);
+    for (nf_model::HostPipe* hp : m->pipes_free) {
+        for (auto& s : hp->st) {
+            if (s.x) cudaFree(s.x);
+            if (s.y) cudaFree(s.y);
+            if (s.z) cudaFree(s.z);
+            if (s.nll) cudaFree(s.nll);
+            if (s.sdz) cudaFree(s.sdz);
+            if (s.rows) cudaFree(s.rows);
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+        if (hp->h_tmp) cudaFreeHost(hp->h_tmp);
+        delete hp;
     }
-    if (m->d_sums) cudaFree(m->d_sums);
-    if (m->h_tmp) cudaFreeHost(m->h_tmp);
     if (m->d_wide_full) cudaFree(m->d_wide_full);
     if (m->d_wide_tc) cudaFree(m->d_wide_tc);
     for (auto& b : m->bs_free) cudaFree(b.first);
@@ -1024,23 +1033,51 @@ int nf_histogram(const float* data, int64_t count, const double* edges, int n_bi
 // ---- host-buffer pipeline ---------------------------------------------------------------------------
 static const int64_t kChunk = 4096;   // patches per staged chunk: 64 MiB per tensor
 
-static int ensure_staging(nf_model* m) {
-    if (m->chunk) return NF_OK;
-    const size_t pb = (size_t)NF_DIMS * sizeof(float);
-    for (auto& s : m->st) {
-        NF_CUDA(cudaMalloc(&s.x, kChunk * pb));
-        NF_CUDA(cudaMalloc(&s.y, kChunk * pb));
-        NF_CUDA(cudaMalloc(&s.z, kChunk * pb));
-        NF_CUDA(cudaMalloc(&s.nll, kChunk * sizeof(float)));
-        NF_CUDA(cudaMalloc(&s.sdz, kChunk * sizeof(float)));
-        NF_CUDA(cudaMalloc(&s.rows, kChunk * sizeof(int32_t)));
+namespace {
+struct PipeLease {          // borrows a HostPipe for the duration of one _host call
+    nf_model* m;
+    nf_model::HostPipe* hp = nullptr;
+    explicit PipeLease(nf_model* m_) : m(m_) {
+        std::lock_guard<std::mutex> lock(m->pool_mu);
+        if (!m->pipes_free.empty()) { hp = m->pipes_free.back(); m->pipes_free.pop_back(); }
+        else { hp = new (std::nothrow) nf_model::HostPipe(); if (hp) ++m->pipes_total; }
+    }
+    ~PipeLease() {
+        if (!hp) return;
+        std::lock_guard<std::mutex> lock(m->pool_mu);
+        m->pipes_free.push_back(hp);
+    }
+};
+
+// slot k of the pipe, with buffers for `c` patches (grown on demand; streams / events created on first use)
+int ensure_slot(nf_model::Staging& s, int64_t c, bool want_x, bool want_y, bool want_z, bool want_rows) {
+    if (!s.stream) {
         NF_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         NF_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
-    NF_CUDA(cudaMalloc(&m->d_sums, 3 * sizeof(double)));
-    m->chunk = kChunk;
+    const size_t pb = (size_t)NF_DIMS * sizeof(float);
+    if (c > s.cap) {       // grow: everything the slot already holds is re-allocated at the new capacity
+        NF_CUDA(cudaStreamSynchronize(s.stream));
+        int64_t cap = 64;
+        while (cap < c) cap *= 2;
+        if (cap > kChunk) cap = kChunk;
+        float** bufs[3] = {&s.x, &s.y, &s.z};
+        for (auto b : bufs)
+            if (*b) { cudaFree(*b); *b = nullptr; }
+        if (s.nll) { cudaFree(s.nll); s.nll = nullptr; }
+        if (s.sdz) { cudaFree(s.sdz); s.sdz = nullptr; }
+        if (s.rows) { cudaFree(s.rows); s.rows = nullptr; }
+        s.cap = cap;
+    }
+    if (want_x && !s.x) NF_CUDA(cudaMalloc(&s.x, s.cap * pb));
+    if (want_y && !s.y) NF_CUDA(cudaMalloc(&s.y, s.cap * pb));
+    if (want_z && !s.z) NF_CUDA(cudaMalloc(&s.z, s.cap * pb));
+    if (!s.nll) NF_CUDA(cudaMalloc(&s.nll, s.cap * sizeof(float)));
+    if (!s.sdz) NF_CUDA(cudaMalloc(&s.sdz, s.cap * sizeof(float)));
+    if (want_rows && !s.rows) NF_CUDA(cudaMalloc(&s.rows, s.cap * sizeof(int32_t)));
     return NF_OK;
 }
+}  // namespace
 
 int nf_log_prob_host(const nf_model* cm, const float* x_host, const float* y_host, const int32_t* rows_host,
                      int32_t default_row, int64_t n, float* nll_host, float* sdz_host, float* z_host, double* sums_host) {
@@ -1049,29 +1086,31 @@ int nf_log_prob_host(const nf_model* cm, const float* x_host, const float* y_hos
     if (!x_host || n < 0) return fail(NF_ERR_INVALID, "x_host is required");
     if (!nll_host && !sums_host) return fail(NF_ERR_INVALID, "nll_host or sums_host is required");
     nf_model* m = const_cast<nf_model*>(cm);
-    std::lock_guard<std::mutex> lock(m->pool_mu);   // one host pipeline per handle at a time
-    rc = ensure_staging(m);
-    if (rc) return rc;
+    PipeLease lease(m);            // this caller's own pipeline: concurrent callers do not serialise
+    if (!lease.hp) return fail(NF_ERR_INVALID, "out of host memory");
+    nf_model::HostPipe& hp = *lease.hp;
     const size_t pb = (size_t)NF_DIMS * sizeof(float);
     double tot[3] = {0.0, 0.0, 0.0};
     // Results the caller did not ask for but the sums need go to PINNED scratch: a device->host copy into pageable
     // memory blocks the host until the chunk's kernel has finished, which would serialise copies and compute.
     const size_t need = ((sums_host && !nll_host) ? (size_t)n : 0) + ((sums_host && !sdz_host) ? (size_t)n : 0);
-    if (need > m->h_tmp_floats) {
-        if (m->h_tmp) cudaFreeHost(m->h_tmp);
-        m->h_tmp = nullptr;
-        m->h_tmp_floats = 0;
-        NF_CUDA(cudaHostAlloc((void**)&m->h_tmp, need * sizeof(float), cudaHostAllocDefault));
-        m->h_tmp_floats = need;
+    if (need > hp.h_tmp_floats) {
+        if (hp.h_tmp) cudaFreeHost(hp.h_tmp);
+        hp.h_tmp = nullptr;
+        hp.h_tmp_floats = 0;
+        NF_CUDA(cudaHostAlloc((void**)&hp.h_tmp, need * sizeof(float), cudaHostAllocDefault));
+        hp.h_tmp_floats = need;
     }
-    float* tmp_nll = (sums_host && !nll_host) ? m->h_tmp : nullptr;
-    float* tmp_sdz = (sums_host && !sdz_host) ? m->h_tmp + (tmp_nll ? (size_t)n : 0) : nullptr;
+    float* tmp_nll = (sums_host && !nll_host) ? hp.h_tmp : nullptr;
+    float* tmp_sdz = (sums_host && !sdz_host) ? hp.h_tmp + (tmp_nll ? (size_t)n : 0) : nullptr;
     float* nll_dst = nll_host ? nll_host : tmp_nll;
     float* sdz_dst = sdz_host ? sdz_host : tmp_sdz;
     int64_t k = 0;
-    for (int64_t off = 0; off < n; off += m->chunk, ++k) {
-        nf_model::Staging& s = m->st[k % nf_model::kSlots];
-        const int64_t c = (n - off < m->chunk) ? n - off : m->chunk;
+    for (int64_t off = 0; off < n; off += kChunk, ++k) {
+        nf_model::Staging& s = hp.st[k % nf_model::kSlots];
+        const int64_t c = (n - off < kChunk) ? n - off : kChunk;
+        rc = ensure_slot(s, c, true, y_host != nullptr, z_host != nullptr, rows_host != nullptr);
+        if (rc) return rc;
         NF_CUDA(cudaEventSynchronize(s.done));   // previous use of this slot has drained
         NF_CUDA(cudaMemcpyAsync(s.x, x_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));
         if (y_host) NF_CUDA(cudaMemcpyAsync(s.y, y_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));
@@ -1084,7 +1123,8 @@ int nf_log_prob_host(const nf_model* cm, const float* x_host, const float* y_hos
         if (z_host) NF_CUDA(cudaMemcpyAsync(z_host + off * NF_DIMS, s.z, c * pb, cudaMemcpyDeviceToHost, s.stream));
         NF_CUDA(cudaEventRecord(s.done, s.stream));
     }
-    for (auto& s : m->st) NF_CUDA(cudaStreamSynchronize(s.stream));
+    for (auto& s : hp.st)
+        if (s.stream) NF_CUDA(cudaStreamSynchronize(s.stream));
     if (sums_host) {   // fixed-order fp64 accumulation on the host: identical for any chunking
         for (int64_t i = 0; i < n; ++i) {
             tot[0] += (double)nll_dst[i];
@@ -1102,14 +1142,16 @@ int nf_sample_host(const nf_model* cm, const float* y_host, const int32_t* rows_
     if (rc) return rc;
     if (!x_host || n < 0) return fail(NF_ERR_INVALID, "x_host is required");
     nf_model* m = const_cast<nf_model*>(cm);
-    std::lock_guard<std::mutex> lock(m->pool_mu);
-    rc = ensure_staging(m);
-    if (rc) return rc;
+    PipeLease lease(m);
+    if (!lease.hp) return fail(NF_ERR_INVALID, "out of host memory");
+    nf_model::HostPipe& hp = *lease.hp;
     const size_t pb = (size_t)NF_DIMS * sizeof(float);
     int64_t k = 0;
-    for (int64_t off = 0; off < n; off += m->chunk, ++k) {
-        nf_model::Staging& s = m->st[k % nf_model::kSlots];
-        const int64_t c = (n - off < m->chunk) ? n - off : m->chunk;
+    for (int64_t off = 0; off < n; off += kChunk, ++k) {
+        nf_model::Staging& s = hp.st[k % nf_model::kSlots];
+        const int64_t c = (n - off < kChunk) ? n - off : kChunk;
+        rc = ensure_slot(s, c, eps_host != nullptr, y_host != nullptr, true, rows_host != nullptr);
+        if (rc) return rc;
         NF_CUDA(cudaEventSynchronize(s.done));
         if (y_host) NF_CUDA(cudaMemcpyAsync(s.y, y_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));
         if (eps_host) NF_CUDA(cudaMemcpyAsync(s.x, eps_host + off * NF_DIMS, c * pb, cudaMemcpyHostToDevice, s.stream));
@@ -1120,7 +1162,8 @@ int nf_sample_host(const nf_model* cm, const float* y_host, const int32_t* rows_
         NF_CUDA(cudaMemcpyAsync(x_host + off * NF_DIMS, s.z, c * pb, cudaMemcpyDeviceToHost, s.stream));
         NF_CUDA(cudaEventRecord(s.done, s.stream));
     }
-    for (auto& s : m->st) NF_CUDA(cudaStreamSynchronize(s.stream));
+    for (auto& s : hp.st)
+        if (s.stream) NF_CUDA(cudaStreamSynchronize(s.stream));
     return NF_OK;
 }
 
@@ -1218,7 +1261,7 @@ static int chain_batch_stats_small(const nf_model* m, const std::vector<std::pai
         a.ld = inverse ? (logdet ? logdet : nll) : nullptr;      // running log-det (nll doubles as scratch), zeroed below
         a.temp = temp; a.seed = seed; a.offset = offset; a.patch_base = patch_base;
         if (a.ld && (e = cudaMemsetAsync(a.ld, 0, (size_t)n * sizeof(float), stream)) != cudaSuccess) { rc = fail(NF_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); break; }
-        if ((e = nf::launch_bs_small(a, stream)) != cudaSuccess) {
+        if ((e = nf::launch_bs_small(a, nf::bs_small_capacity(cached_sm_count()), stream)) != cudaSuccess) {
             if (e == cudaErrorCooperativeLaunchTooLarge) { cudaGetLastError(); rc = 1; break; }   // e.g. SMs partitioned by MPS: layer by layer
             rc = fail(NF_ERR_CUDA, "small-batch chain launch: %s", cudaGetErrorString(e));
             break;
@@ -1275,7 +1318,11 @@ int nf_chain_batch_stats(const nf_model* m, int direction, const float* in, cons
         else { groups.push_back({l, l + 1}); l += 1; }
     }
     if (!inverse) std::reverse(groups.begin(), groups.end());
-    if (W == 4 && !m->has_cond && m->bs_small && !(direction == 1 && logdet) && n <= (int64_t)nf::bs_small_capacity(cached_sm_count())) {
+    // one cooperative kernel, no host round trip: one co-resident CTA per patch up to 296 patches (B200), the same kernel
+    // walking its patches grid-stride up to kBsCoopMax; beyond that the probes of the warp-per-patch kernel win by more than the
+    // 16 stream synchronisations cost (< 1 % of the call at that size)
+    const int64_t kBsCoopMax = 4096;
+    if (W == 4 && !m->has_cond && m->bs_small && !(direction == 1 && logdet) && nf::bs_small_capacity(cached_sm_count()) > 0 && n <= kBsCoopMax) {
         bool ok = true;       // [mix +] coupling groups and scale layers only
         for (const auto& g : groups) {
             const int k = m->layers[g.second - 1].kind;

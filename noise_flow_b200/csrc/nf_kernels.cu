@@ -383,6 +383,15 @@ __global__ void nf_squeeze_kernel(const float* __restrict__ in, float* __restric
 cudaError_t launch_chain(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, int warps_per_cta,
                          cudaStream_t stream) {
     if (args.n <= 0) return cudaSuccess;
+    // CTA shape against wave quantisation: every SM takes part and the CTA is sized so that its rounds are full --
+    // ceil(n / SMs) patches per SM in ceil(per_sm / warps_per_cta) rounds of equal size.  4 096 patches: two rounds of 14
+    // warps on all 148 SMs (16-warp CTAs: a full round + a round with 40 SMs idle); 1 024 patches: one round of 7 warps on
+    // every SM (16-warp CTAs: 64 SMs).  The kernel itself is untouched: blockDim decides how many patches a CTA keeps resident.
+    {
+        const long long g = args.n < (long long)num_sms ? args.n : (long long)num_sms;
+        const long long per_sm = (args.n + g - 1) / g, rounds = (per_sm + warps_per_cta - 1) / warps_per_cta;
+        warps_per_cta = (int)((per_sm + rounds - 1) / rounds);
+    }
     const size_t smem = (size_t)warps_per_cta * sizeof(WarpSmem);
     static bool attr_done[NF_MAX_DEVICES][2] = {};   // per device; idempotent: a benign race sets the same value twice
     const int dev = device_slot();

@@ -90,5 +90,5 @@ struct BsArgs {
 };
 
 int bs_small_capacity(int sm_count);                       // patches that can own a co-resident CTA (0: unavailable)
-cudaError_t launch_bs_small(const BsArgs& a, cudaStream_t s);
+cudaError_t launch_bs_small(const BsArgs& a, int capacity, cudaStream_t s);   // grid = min(n, capacity); beyond: grid-stride
 }  // namespace nf

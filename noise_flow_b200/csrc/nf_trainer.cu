@@ -1135,9 +1135,11 @@ td_step_kernel(const TdStepArgs a) {
 // last stage of a coupling in the sampling direction: y1 -> (y1 - shift) * exp(-ls), then the mix with the inverse matrix
 template <int NW>
 __device__ __forceinline__ void td_sample3_body(TdSmem& S, const TdCoupling& d, const float* __restrict__ vars, const float* Ainv,
-                                                int has_mix, const double* stats, float4* zout, float* ld, long long n, double inv_cnt) {
+                                                int has_mix, const double* stats, const float4* zin, float4* zout, float* ld, long long n,
+                                                double inv_cnt, bool resident) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    td_load_params(S, d, vars, nullptr, stats, inv_cnt, 2, true);      // weights and the (un-mixed) patch are resident
+    // resident (one patch per CTA): weights, the (un-mixed) patch and its conv-1 output are still in shared memory from F2
+    td_load_params(S, d, vars, nullptr, stats, inv_cnt, 2, resident);
     __shared__ float Ai[16];
     if (threadIdx.x < 16) Ai[threadIdx.x] = has_mix ? __ldcg(Ainv + threadIdx.x) : ((threadIdx.x >> 2) == (threadIdx.x & 3) ? 1.f : 0.f);
     __syncthreads();
@@ -1145,9 +1147,11 @@ __device__ __forceinline__ void td_sample3_body(TdSmem& S, const TdCoupling& d, 
 #pragma unroll
     for (int o = 0; o < 4; ++o) e3[o] = expf(3.f * S.P.logs[o]);
     for (long long p = blockIdx.x; p < n; p += gridDim.x) {
+        if (!resident) td_load_mixed<NW>(S, zin + p * NF_PIXELS, warp, lane);      // d.has_mix == 0 here: a plain copy
         for (int k = threadIdx.x; k < 34 * 34; k += blockDim.x)
             if (on_ring(k)) S.h2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
+        if (!resident) td_conv1_rows<NW>(S, warp, lane);
         for (int r = warp; r < 32; r += NW) {
             float c1hat[4], h1[4], c2hat[4];
             td_net_to_c2hat(S, r, lane, c1hat, h1, c2hat);
@@ -1216,6 +1220,9 @@ td_bs_chain_kernel(const BsArgs a) {
     const double inv_cnt = 1.0 / ((double)n * NF_PIXELS);
     const float4* cur = (const float4*)a.in;
     float4* out = (float4*)a.out;
+    // one patch per CTA: the patch, the weights and the conv-1 output stay in shared memory between the passes of a coupling;
+    // more patches than co-resident CTAs: every pass walks its patches grid-stride and re-loads (still one launch, no host)
+    const bool resident = n <= (long long)gridDim.x;
     if (a.direction == 1) {     // z = eps * temp (noise_flow_model.py:499-504); eps given or Philox4x32-10 as nf_sample
         for (long long p = blockIdx.x; p < n; p += gridDim.x)
             for (int k = threadIdx.x; k < NF_PIXELS; k += blockDim.x) {
@@ -1236,10 +1243,10 @@ td_bs_chain_kernel(const BsArgs a) {
             if (a.direction == 1) d.has_mix = 0;          // the net sees the un-mixed input; the mix comes last
             td_fwd_body<1, NW>(S, d, a.vars, A, st, cur, out, a.ld, n, inv_cnt);
             grid.sync();
-            td_fwd_body<2, NW>(S, d, a.vars, A, st, cur, out, a.ld, n, inv_cnt, true);
+            td_fwd_body<2, NW>(S, d, a.vars, A, st, cur, out, a.ld, n, inv_cnt, resident);
             grid.sync();
-            if (a.direction == 0) td_fwd_body<3, NW>(S, d, a.vars, A, st, cur, out, a.ld, n, inv_cnt, true);
-            else td_sample3_body<NW>(S, d, a.vars, A, has_mix, st, out, a.ld, n, inv_cnt);
+            if (a.direction == 0) td_fwd_body<3, NW>(S, d, a.vars, A, st, cur, out, a.ld, n, inv_cnt, resident);
+            else td_sample3_body<NW>(S, d, a.vars, A, has_mix, st, cur, out, a.ld, n, inv_cnt, resident);
         } else if (a.direction == 0) {
             td_scale_fwd_body(sh, a.tables + op.sidx * NF_MAX_ROWS * 2, op.is_sdn, op.full_sum, cur, (const float4*)a.y, out, a.ld, a.rows,
                               a.default_row, n);
@@ -1293,9 +1300,10 @@ int bs_small_capacity(int sm_count) {
     return per_sm * sm_count;
 }
 
-cudaError_t launch_bs_small(const BsArgs& a, cudaStream_t s) {
+cudaError_t launch_bs_small(const BsArgs& a, int capacity, cudaStream_t s) {
     void* kargs[] = {(void*)&a};
-    return cudaLaunchCooperativeKernel((const void*)td_bs_chain_kernel<8>, dim3((unsigned)a.n), dim3(256), kargs, sizeof(TdSmem), s);
+    const long long grid = a.n < (long long)capacity ? a.n : (long long)capacity;      // beyond: grid-stride over the patches
+    return cudaLaunchCooperativeKernel((const void*)td_bs_chain_kernel<8>, dim3((unsigned)grid), dim3(256), kargs, sizeof(TdSmem), s);
 }
 
 }  // namespace nf

@@ -284,6 +284,52 @@ def test_host_buffer_entry_points(shipped):
     assert np.array_equal(out, dev)
 
 
+def test_host_entry_points_from_16_threads(shipped):
+    """The reference drives ONE model from 16-32 Python threads (train_dncnn_noiseflow.py:195-198: 32 sampler threads, 128
+    patches each).  Every `_host` call borrows its own staging pipeline, so concurrent callers overlap instead of queueing on
+    one: same bits as a lone caller, and 16 threads finish a fixed amount of work faster than one."""
+    import ctypes as C
+    import threading
+    import time
+    from noise_flow_b200 import _lib
+    hps, ck = shipped
+    nf = _nf(hps, ck, first_call="inverse")
+    lib, h = _lib.load(), nf._engine.handle
+    n_threads, n, reps = 16, 128, 12
+    ys = [np.random.RandomState(100 + k).rand(n, 32, 32, 4).astype(np.float32) for k in range(n_threads)]
+    eps = [np.random.RandomState(200 + k).randn(n, 32, 32, 4).astype(np.float32) for k in range(n_threads)]
+    outs = [np.empty((n, 32, 32, 4), np.float32) for _ in range(n_threads)]
+    errs = []
+
+    def worker(k, r):
+        try:
+            for _ in range(r):
+                _lib.check(lib.nf_sample_host(h, ys[k].ctypes.data, None, 10, n, 0.6, eps[k].ctypes.data, 0, 0, outs[k].ctypes.data))
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+
+    worker(0, 2)                                                      # warm-up: first pipe, kernel attributes
+    t0 = time.perf_counter()
+    for k in range(n_threads):
+        worker(k, reps)
+    t_serial = time.perf_counter() - t0
+    serial = [o.copy() for o in outs]
+    for o in outs:
+        o.fill(0)
+    ths = [threading.Thread(target=worker, args=(k, reps)) for k in range(n_threads)]
+    t0 = time.perf_counter()
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    t_par = time.perf_counter() - t0
+    assert not errs, errs
+    for k in range(n_threads):
+        assert np.array_equal(outs[k], serial[k]), k                  # thread-safe: bit-identical to the serial calls
+        dev = nf.sample(ys[k], 0.6, ys[k], iso=[100.0], cam=[2.0], eps=eps[k]).cpu().numpy()
+        assert np.array_equal(outs[k], dev)
+    print("16 threads x %d calls of %d patches: serial %.1f ms, concurrent %.1f ms" % (reps, n, 1e3 * t_serial, 1e3 * t_par))
+    assert t_par < 0.8 * t_serial, (t_par, t_serial)                  # the callers overlap (one shared pipeline: ~1.0)
+
+
 def test_error_paths_fail_loudly(shipped):
     from noise_flow_b200 import NoiseFlow, make_hps
     hps, ck = shipped
@@ -424,12 +470,13 @@ def test_training_mode_batch_stat_bn_matches_oracle(shipped, n):
     assert np.abs(nll2.cpu().numpy() - nll2_o.numpy()).max() / 4096 < NLL_TOL_PER_DIM
 
 
-@pytest.mark.parametrize("n", [1, 5, 37, 300])
+@pytest.mark.parametrize("n", [1, 5, 37, 300, 1000])
 def test_batch_stat_chain_cooperative_kernel_equals_layer_by_layer(shipped, n):
-    """Small batches run the batch-statistics chain as ONE cooperative kernel (nf_trainer.cu: td_bs_chain_kernel); larger
-    ones (300 > 296 co-resident CTAs) and `set_batch_stats_fused(False)` go layer by layer.  Both directions, injected and
-    Philox noise, per-patch (camera, ISO) rows: same results, same moving-statistics side effect, both within the oracle
-    tolerance."""
+    """Batches up to 4096 patches run the batch-statistics chain as ONE cooperative kernel with no host round trip
+    (nf_trainer.cu: td_bs_chain_kernel; one co-resident CTA per patch up to 296, grid-stride beyond: n = 300, 1000);
+    `set_batch_stats_fused(False)` goes layer by layer (probe launches + a stream synchronisation each).  Both directions,
+    injected and Philox noise, per-patch (camera, ISO) rows: same results, same moving-statistics side effect, both within
+    the oracle tolerance."""
     hps, ck = shipped
     x, y = synth_batch(n, seed=71)
     eps = np.random.RandomState(72).randn(n, 32, 32, 4).astype(np.float32)
