@@ -222,6 +222,19 @@ def test_sharded_mean_nll_world_size_2_gloo():
         assert abs(r[3] - r[5]) < 1e-12 and abs(r[4] - r[6]) < 1e-12      # every rank holds the global means
 
 
+def test_shipped_checkpoint_shows_the_bias_random_walk_of_the_reference(shipped):
+    """`l_1/b` and `l_2/b` sit in front of a batch-statistics BatchNorm (layers.py:469-489): their exact gradient is zero
+    and they are initialised to zero (layers.py:602), yet the reference's own trained checkpoint holds values of 0.01 - 0.5.
+    TensorFlow's fp32 gradient is summation noise there and Adam normalises noise to steps of about +-lr: a random walk of
+    1e-4 * sqrt(2000 epochs x 112 iterations) ~ 0.05 per thread.  The device trainer does the same (it does NOT zero these
+    gradients structurally); tests/test_gpu_reference_goldens.py::test_two_adam_steps_match_reference_train_op bounds the
+    walk by lr per step."""
+    _, ck = shipped
+    b = np.concatenate([v.reshape(-1) for k, v in ck.items() if k.endswith("/l_1/b") or k.endswith("/l_2/b")])
+    assert b.size == 64 and np.all(b != 0.0)
+    assert 0.05 < float(np.sqrt(np.mean(b * b))) < 0.5
+
+
 def test_lu_chain_rule_closed_form_equals_autograd(shipped):
     """train.lu_chain (closed form of d loss / d (L_vec, U_vec, log_S) for A = P L U, matrix_param.py:117-130)
     against torch autograd through the same parameterisation, on the shipped LU variables."""

@@ -30,18 +30,18 @@ def test_device_gradients_match_oracle_autograd(shipped, is_training):
         zero_g, grads_nz = _split_zero_grad(grads)
         for k in zero_g:
             assert np.abs(grads[k]).max() < 2e-2 and np.abs(grads_o[k]).max() < 1e-6, k
-        worst = _check(grads_nz, _split_zero_grad(grads_o)[1], rel=5e-3)
+        worst = _check(grads_nz, _split_zero_grad(grads_o)[1], rel=5e-4)
     else:
-        worst = _check(grads, grads_o, rel=5e-3)
+        worst = _check(grads, grads_o, rel=5e-4)
     print("device trainer vs oracle: max relative gradient error %.2e" % worst)
     # and against the independently written host-synchronous path (same math, other kernels)
     nf2 = NoiseFlow([32, 32, 4], is_training, copy.copy(hps), variables=ck, device="cuda:0", first_call="inverse")
     loss_h, sd_h, grads_h = loss_and_grad(nf2, x, y, iso=[100.0], cam=[2.0], is_training=is_training)
     assert abs(loss - loss_h) / 4096 < 2e-6 and abs(sd_z - sd_h) < 1e-5
     if is_training:
-        _check(_split_zero_grad(grads)[1], _split_zero_grad(grads_h)[1], rel=2e-3)
+        _check(_split_zero_grad(grads)[1], _split_zero_grad(grads_h)[1], rel=5e-4)
     else:
-        _check(grads, grads_h, rel=2e-3)
+        _check(grads, grads_h, rel=5e-4)
     if is_training:     # batch statistics that drive the moving averages
         assert np.allclose(tr.batch_stats(), nf2.last_batch_stats, rtol=2e-4, atol=1e-6)
 
@@ -74,7 +74,7 @@ def test_device_gradients_other_archs(arch, perm, cam, iso):
     loss, _ = tr.loss()
     loss_o, _, grads_o, _ = _oracle_loss_and_grads(hps, vs, x, y, iso, cam, True)
     assert abs(loss - loss_o) / 4096 < 1e-4
-    _check(tr.gradients(), grads_o, rel=5e-3)
+    _check(tr.gradients(), grads_o, rel=5e-4)
 
 
 def _split_zero_grad(grads):
@@ -120,7 +120,7 @@ def test_device_gradients_per_patch_rows(shipped):
         for k in zero_g:
             assert np.abs(res[name][1][k]).max() < 2e-2, (name, k)
         try:
-            _check(g, _split_zero_grad(grads_h)[1], rel=2e-3)
+            _check(g, _split_zero_grad(grads_h)[1], rel=5e-4)
         except AssertionError as e:
             raise AssertionError("\n".join(report) + "\n" + str(e)[:600])
 
@@ -139,7 +139,7 @@ def test_device_cta_shapes_agree(shipped, warps, fused):
     tr.loss_and_grad(x, y, iso=[100.0], cam=[2.0])
     loss_o, sd_o, grads_o, _ = _oracle_loss_and_grads(hps, ck, x, y, 100.0, 2.0, True)
     assert abs(tr.loss()[0] - loss_o) / 4096 < 1e-4
-    _check(tr.gradients(), grads_o, rel=5e-3)
+    _check(tr.gradients(), grads_o, rel=5e-4)
     assert tr.launches_per_step(True) == (4 if fused else 57)
 
 
