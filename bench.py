@@ -216,6 +216,43 @@ def _traffic(key):
         return None
 
 
+def h2d_ceiling(dev, world, mib=256, reps=4):
+    """What bounds `e2e`: pinned host -> device copy bandwidth with EVERY rank copying at the same time (the ranks of one box
+    share the host's memory system and PCIe root complexes).  Returns (aggregate GB/s over all ranks, this rank's GB/s)."""
+    nbytes = mib << 20
+    hs = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    ds = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    ss = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    for h in hs:
+        h.fill_(1)
+
+    def run():
+        for _ in range(reps):
+            for h, d, st in zip(hs, ds, ss):
+                with torch.cuda.stream(st):
+                    d.copy_(h, non_blocking=True)
+    run()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    run()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    mine = 2 * reps * nbytes / dt / 1e9
+    if world > 1:
+        torch.distributed.barrier()
+    t = torch.tensor([dt, mine], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone()
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        agg = world * 2 * reps * nbytes / float(tmax[0]) / 1e9
+    else:
+        agg = mine
+    del hs, ds
+    return agg, mine
+
+
 def wide_model(hps, ck, width, dev):
     """A net of the shipped arch at another coupling width: no shipped checkpoint exists, so reference initialisers for the
     structure and O(1)-activation random weights for the coupling nets."""
@@ -444,8 +481,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (ONE JSON line)
+        # ONE JSON line on stdout: NCCL prints its version banner there at NCCL_DEBUG >= VERSION (WARN and INFO included);
+        # whatever level the environment asks for goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from noise_flow_b200 import NoiseFlow, _lib
     from noise_flow_b200.distributed import allreduce_sums
@@ -604,10 +642,16 @@ def main():
         edt = float(tt[0])
         h2d = 2 * nb if args.mode == "log_prob" else nb
         d2h = B * 4 if args.mode == "log_prob" else nb
+        del hx_t, hy_t, hn_t
+        ceil_agg, ceil_mine = h2d_ceiling(dev, world)
+        moved = world * (h2d + d2h) * e_steps / edt / 1e9          # both directions share nothing on PCIe, but the host side does
         e2e = {"value": world * B * e_steps / edt, "unit": "patches/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e_steps,
-               "path": "nf_%s_host: pinned host buffers, 4096-patch chunks in flight on 4 streams" % args.mode}
-        del hx_t, hy_t, hn_t
+               "path": "nf_%s_host: pinned host buffers, 4096-patch chunks in flight on 4 streams" % args.mode,
+               "achieved_gbs": moved, "h2d_gbs": world * h2d * e_steps / edt / 1e9, "ceiling_gbs": ceil_agg,
+               "ceiling_gbs_rank0": ceil_mine, "frac_of_ceiling": world * h2d * e_steps / edt / 1e9 / ceil_agg,
+               "ceiling_note": "ceiling = pinned host -> device copies of 256 MiB on 2 streams per rank, all %d ranks at once, "
+                               "measured in this run; frac = this run's H2D rate / that" % world}
 
     # ---- the other BASELINE configs (every rank takes part), sharding check
     also = shard = None

@@ -12,7 +12,7 @@ from noise_flow_b200.train import DeviceTrainer
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-os.environ.setdefault("NCCL_DEBUG", "WARN")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 dist.init_process_group("nccl", device_id=dev)
 g = os.path.join(ROOT, "tests", "golden", "NoiseFlow")
 hps = hps_loader(os.path.join(g, "hps.txt")); ck = load_checkpoint(os.path.join(g, "ckpt", "model.ckpt.best"))
@@ -40,4 +40,19 @@ same = bool(torch.equal(lo, hi))
 if rank == 0:
     print("replicas bit-identical after 3 steps:", same, "| loss = global mean:", ok)
     print("DP_TRAIN_CHECK", "OK" if (same and ok) else "FAILED")
+# the host-synchronous path (train.train_step): gradients AND batch statistics ride in one all-reduce, so the BatchNorm
+# moving averages -- and therefore a checkpoint written by any rank -- stay identical across ranks
+from noise_flow_b200.train import AdamOptimizer, train_step
+nf2 = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables={k: v.copy() for k, v in ck.items()}, device=dev, first_call="inverse")
+opt = AdamOptimizer(learning_rate=1e-4)
+for s in range(2):
+    x, y = synth_batch(8 * world, seed=600 + s)
+    train_step(nf2, opt, x[rank * 8:(rank + 1) * 8], y[rank * 8:(rank + 1) * 8], iso=[100.0], cam=[2.0])
+flat2 = np.concatenate([v.reshape(-1) for k, v in sorted(nf2.variables.items())])
+t2 = torch.as_tensor(flat2, device=dev)
+lo2, hi2 = t2.clone(), t2.clone()
+dist.all_reduce(lo2, op=dist.ReduceOp.MIN); dist.all_reduce(hi2, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("host path: variables incl. BatchNorm moving statistics identical on all ranks after 2 steps:", bool(torch.equal(lo2, hi2)))
+    print("DP_HOST_TRAIN_CHECK", "OK" if bool(torch.equal(lo2, hi2)) else "FAILED")
 dist.destroy_process_group()
