@@ -457,6 +457,7 @@ int build_wide_program(const nf_model* m, int first, int last, NfWideProgram* wp
     for (int l = first; l < last; ++l) {
         const Layer& L = m->layers[l];
         if (n_ops >= NF_MAX_LAYERS) return fail(NF_ERR_UNSUPPORTED, "more than %d kernel ops", NF_MAX_LAYERS);
+        if (tc && L.kind == L_COUPLING) blob->resize((blob->size() + NF_TMA_ROW_FLOATS - 1) / NF_TMA_ROW_FLOATS * NF_TMA_ROW_FLOATS, 0.f);   // TMA rows
         const size_t off = blob->size();
         if (L.kind == L_CONV1X1 || L.kind == L_PERMUTE) {
             ldj += L.log_abs_det * (double)NF_PIXELS;
@@ -482,6 +483,8 @@ int build_wide_program(const nf_model* m, int first, int last, NfWideProgram* wp
         wp->off[n_ops++] = (int32_t)off;
     }
     wp->n_layers = n_ops;
+    if (tc) blob->resize((blob->size() + NF_TMA_ROW_FLOATS - 1) / NF_TMA_ROW_FLOATS * NF_TMA_ROW_FLOATS, 0.f);
+    wp->blob_floats = (int32_t)blob->size();
     *ldj_const = (float)ldj;
     return NF_OK;
 }

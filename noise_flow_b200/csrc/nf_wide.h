@@ -48,7 +48,7 @@ struct NfWideProgram {           // by-value kernel argument; the parameters the
     int32_t width;
     int32_t n_layers;
     int32_t flags;
-    int32_t pad_;
+    int32_t blob_floats;         // size of the blob (tensor-core kernels: a multiple of NF_TMA_ROW_FLOATS, coupling blocks row-aligned)
     int32_t op[NF_MAX_LAYERS];   // NfKernelOp, data -> latent order
     int32_t off[NF_MAX_LAYERS];  // float offset of the op's block in the blob
 };
@@ -74,7 +74,11 @@ struct NfWideTcLayout {
 };
 inline int nf_wide_tc_coupling_floats(int W) { return NfWideTcLayout::block_bytes(W) / 4; }
 
+// The tensor-core kernels fetch their weight blocks with TMA tensor copies (cp.async.bulk.tensor.2d): the blob is described
+// to the TMA engine as a 2-D tensor of rows of 64 floats (256 B), one box = NF_TMA_ROW_FLOATS x box_rows.
+#define NF_TMA_ROW_FLOATS 64
 namespace nf {
+inline int wide_tc_box_rows(int width) { return width == 32 ? 62 : (width == 64 ? 77 : (width == 128 ? 217 : 32)); }
 bool wide_width_supported(int width);
 cudaError_t launch_wide_cond(const NfWideProgram& prog, const float* blob, const NfChainArgs& args, bool inverse, unsigned grid,
                              cudaStream_t stream);

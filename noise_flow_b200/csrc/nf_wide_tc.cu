@@ -284,7 +284,7 @@ __device__ __forceinline__ void tc_coupling(const unsigned char* wb, GroupSmem& 
 
 template <int W, bool INV>
 __global__ void __launch_bounds__(THREADS, 1)
-nf_wide_tc_kernel(const NfWideProgram prog, const float* __restrict__ blob, const NfChainArgs a) {
+nf_wide_tc_kernel(const __grid_constant__ CUtensorMap tmap, const NfWideProgram prog, const float* __restrict__ blob, const NfChainArgs a) {
     using C = Cfg<W>;
     constexpr int G = C::G, GT = C::GT, NBUF = C::NBUF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -322,11 +322,12 @@ nf_wide_tc_kernel(const NfWideProgram prog, const float* __restrict__ blob, cons
                     if (use > 0) mbar_wait(smem_u32(&S.empty[b]), (use - 1u) & 1u);
                     const uint32_t fb = smem_u32(&S.full[b]);
                     mbar_arrive_expect_tx(fb, (uint32_t)C::BLOCK_BYTES);
-                    const unsigned char* src = reinterpret_cast<const unsigned char*>(blob + prog.off[l]);
-                    for (uint32_t off = 0; off < (uint32_t)C::BLOCK_BYTES; off += 16384u) {
-                        const uint32_t bytes = (uint32_t)C::BLOCK_BYTES - off < 16384u ? (uint32_t)C::BLOCK_BYTES - off : 16384u;
-                        bulk_g2s(smem_u32(&S.wbuf[b][off]), src + off, bytes, fb);
-                    }
+                    // TMA tensor copies: the block is BLOCK_ROWS rows of the blob's 2-D view, fetched in boxes of BOX_ROWS
+                    constexpr int BLOCK_ROWS = C::BLOCK_BYTES / (NF_TMA_ROW_FLOATS * 4), BOX_ROWS = W == 32 ? 62 : (W == 64 ? 77 : 217);
+                    static_assert(BLOCK_ROWS % BOX_ROWS == 0, "box rows");
+                    const int row0 = prog.off[l] / NF_TMA_ROW_FLOATS;
+                    for (int r = 0; r < BLOCK_ROWS; r += BOX_ROWS)
+                        tma_load_rows(smem_u32(&S.wbuf[b][(size_t)r * NF_TMA_ROW_FLOATS * 4]), &tmap, row0 + r, fb);
                 }
                 __syncwarp();
                 ++item;
@@ -453,10 +454,13 @@ static cudaError_t launch_w(const NfWideProgram& prog, const float* blob, const 
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(nf_wide_tc_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    CUtensorMap tmap;
+    e = make_blob_tensor_map(blob, prog.blob_floats, wide_tc_box_rows(W), &tmap);
+    if (e != cudaSuccess) return e;
     long long grid = (a.n + Cfg<W>::G - 1) / Cfg<W>::G;
     if (grid > num_sms) grid = num_sms;
-    if (inverse) nf_wide_tc_kernel<W, true><<<(unsigned)grid, THREADS, smem, stream>>>(prog, blob, a);
-    else nf_wide_tc_kernel<W, false><<<(unsigned)grid, THREADS, smem, stream>>>(prog, blob, a);
+    if (inverse) nf_wide_tc_kernel<W, true><<<(unsigned)grid, THREADS, smem, stream>>>(tmap, prog, blob, a);
+    else nf_wide_tc_kernel<W, false><<<(unsigned)grid, THREADS, smem, stream>>>(tmap, prog, blob, a);
     return cudaGetLastError();
 }
 

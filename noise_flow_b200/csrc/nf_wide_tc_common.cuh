@@ -2,10 +2,12 @@
 // widths 32 / 64 / 128; nf_wide_tcs.cu: weights streamed through a ring, widths 256 / 512): PTX wrappers for tcgen05 /
 // TMEM / mbarrier / the TMA engine, the bf16 (hi, lo) split, and the TMEM -> TMEM epilogues.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "nf_params.h"
+#include "nf_wide.h"
 
 namespace nf {
 namespace wtc {
@@ -61,6 +63,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t by
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+// TMA engine, 2-D tensor copy global -> shared: box (NF_TMA_ROW_FLOATS x box_rows of the tensor map) at row `row`
+__device__ __forceinline__ void tma_load_rows(uint32_t dst, const CUtensorMap* tmap, int row, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(row), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void group_barrier(int g, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(g + 1), "r"(threads) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -170,6 +177,29 @@ __device__ __forceinline__ void probe_accumulate(uint32_t d0, uint32_t d1, int l
     for (int k = 0; k < 32; ++k) q[k] = v[k] * v[k];
     acc_s += warp_sum_to_lanes(v, lane);
     acc_q += warp_sum_to_lanes(q, lane);
+}
+
+
+// Host: describe the weight blob to the TMA engine (driver entry point fetched through the runtime: no libcuda link).
+inline cudaError_t make_blob_tensor_map(const float* blob, long long blob_floats, int box_rows, CUtensorMap* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (!p || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+        fn = (EncodeFn)p;
+    }
+    const cuuint64_t gdim[2] = {NF_TMA_ROW_FLOATS, (cuuint64_t)(blob_floats / NF_TMA_ROW_FLOATS)};
+    const cuuint64_t gstride[1] = {NF_TMA_ROW_FLOATS * sizeof(float)};
+    const cuuint32_t box[2] = {NF_TMA_ROW_FLOATS, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(blob), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 }  // namespace wtc

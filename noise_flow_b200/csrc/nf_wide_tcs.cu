@@ -94,7 +94,7 @@ __device__ __forceinline__ void probe16(uint32_t d, int lane, float* s_sum, floa
 //   STAGE 0: per tile, per pass: NK blocks A (B1 chunk + B2 chunk), one block B (bias + B3 of the pass)
 //   STAGE 1: per tile: NK blocks A' (B1 chunk only)              STAGE 2: per tile, per pass: NK blocks A, one block B' (bias)
 template <int W>
-__device__ __forceinline__ void produce_coupling(SSmem& S, const unsigned char* cb, int stage, uint32_t& blk) {
+__device__ __forceinline__ void produce_coupling(SSmem& S, const CUtensorMap* tmap, int row0, int stage, uint32_t& blk) {
     using C = SCfg<W>;
     using L = NfWideTcLayout;
     const int passes = stage == 1 ? 1 : C::P;
@@ -108,18 +108,19 @@ __device__ __forceinline__ void produce_coupling(SSmem& S, const unsigned char* 
                 if (kc < C::NK) {
                     const bool with_b2 = stage != 1;
                     mbar_arrive_expect_tx(fb, C::B1C + (with_b2 ? C::B2C : 0u));
-                    bulk_g2s(dst, cb + L::off_b1() + (size_t)kc * C::B1C, C::B1C, fb);
+                    // TMA tensor copies in boxes of 32 rows x 256 B of the blob's 2-D view
+                    tma_load_rows(dst, tmap, row0 + (int)((L::off_b1() + kc * C::B1C) / 256u), fb);
                     if (with_b2) {
-                        const unsigned char* src = cb + L::off_b2(W) + ((size_t)p * C::NK + kc) * C::B2C;
-                        for (uint32_t o = 0; o < C::B2C; o += 16384u) bulk_g2s(dst + C::B1C + o, src + o, 16384u, fb);
+                        const int r2 = row0 + (int)((L::off_b2(W) + ((size_t)p * C::NK + kc) * C::B2C) / 256u);
+                        for (uint32_t o = 0; o < C::B2C; o += 8192u) tma_load_rows(dst + C::B1C + o, tmap, r2 + (int)(o / 256u), fb);
                     }
                 } else {
                     const bool with_b3 = stage == 0;
                     mbar_arrive_expect_tx(fb, C::BB2 + (with_b3 ? C::B3P : 0u));
-                    bulk_g2s(dst, cb + L::off_bb2(W) + (size_t)p * C::BB2, C::BB2, fb);
+                    tma_load_rows(dst, tmap, row0 + (int)((L::off_bb2(W) + (size_t)p * C::BB2) / 256u), fb);
                     if (with_b3) {
-                        const unsigned char* src = cb + L::off_b3(W) + (size_t)p * C::B3P;
-                        for (uint32_t o = 0; o < C::B3P; o += 16384u) bulk_g2s(dst + C::BB2 + o, src + o, 16384u, fb);
+                        const int r3 = row0 + (int)((L::off_b3(W) + (size_t)p * C::B3P) / 256u);
+                        for (uint32_t o = 0; o < C::B3P; o += 8192u) tma_load_rows(dst + C::BB2 + o, tmap, r3 + (int)(o / 256u), fb);
                     }
                 }
                 ++blk;
@@ -336,7 +337,7 @@ __device__ __forceinline__ void tcs_coupling(const float* __restrict__ cblob, SS
 
 template <int W, bool INV>
 __global__ void __launch_bounds__(THREADS, 1)
-nf_wide_tcs_kernel(const NfWideProgram prog, const float* __restrict__ blob, const NfChainArgs a) {
+nf_wide_tcs_kernel(const __grid_constant__ CUtensorMap tmap, const NfWideProgram prog, const float* __restrict__ blob, const NfChainArgs a) {
     using C = SCfg<W>;
     constexpr int GT = C::GT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -367,7 +368,7 @@ nf_wide_tcs_kernel(const NfWideProgram prog, const float* __restrict__ blob, con
                 const int l = INV ? a.first_layer + step : a.last_layer - 1 - step;
                 if (prog.op[l] != NF_KOP_COUPLING) continue;
                 const int stage = (a.bn_stage != 0 && step == n_l - 1) ? a.bn_stage : 0;
-                if (lane == 0) produce_coupling<W>(S, reinterpret_cast<const unsigned char*>(blob + prog.off[l]), stage, blk);
+                if (lane == 0) produce_coupling<W>(S, &tmap, prog.off[l] / NF_TMA_ROW_FLOATS, stage, blk);
                 blk = __shfl_sync(0xffffffffu, blk, 0);
             }
     } else {
@@ -470,9 +471,12 @@ static cudaError_t launch_s(const NfWideProgram& prog, const float* blob, const 
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(nf_wide_tcs_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    CUtensorMap tmap;
+    e = make_blob_tensor_map(blob, prog.blob_floats, wide_tc_box_rows(W), &tmap);
+    if (e != cudaSuccess) return e;
     const long long grid = a.n < (long long)num_sms ? a.n : (long long)num_sms;
-    if (inverse) nf_wide_tcs_kernel<W, true><<<(unsigned)grid, THREADS, smem, stream>>>(prog, blob, a);
-    else nf_wide_tcs_kernel<W, false><<<(unsigned)grid, THREADS, smem, stream>>>(prog, blob, a);
+    if (inverse) nf_wide_tcs_kernel<W, true><<<(unsigned)grid, THREADS, smem, stream>>>(tmap, prog, blob, a);
+    else nf_wide_tcs_kernel<W, false><<<(unsigned)grid, THREADS, smem, stream>>>(tmap, prog, blob, a);
     return cudaGetLastError();
 }
 
