@@ -153,8 +153,7 @@ __device__ __forceinline__ void tc_coupling(const unsigned char* wb, GroupSmem& 
                 mma_ts(tD, tA0 + 8u * j, make_desc(wb_addr + L::off_b1() + (uint32_t)j * 2u * W * 16u, W * 16u, 128u), idesc(W), j > 0 ? 1u : 0u);
             mma_commit(mbar);
         }
-        mbar_wait(mbar, mphase);
-        mphase ^= 1u;
+        group_wait_mma(mbar, mphase, g, i, GT);
         tc_fence_after();
         if (STAGE == 1) { probe_accumulate<false>(tD + lane_sel + 32u * h, 0u, lane, acc_s, acc_q); continue; }
         // ---------------- epilogue 1: ReLU, split, A2 (this thread: channels [32 h, 32 h + 32))
@@ -179,8 +178,7 @@ __device__ __forceinline__ void tc_coupling(const unsigned char* wb, GroupSmem& 
             mma_ts(tD, tA0 + 24u, make_desc(wb_addr + L::off_bb2(W), W * 16u, 128u), idesc(W), 1u);
             mma_commit(mbar);
         }
-        mbar_wait(mbar, mphase);
-        mphase ^= 1u;
+        group_wait_mma(mbar, mphase, g, i, GT);
         tc_fence_after();
         if (STAGE == 2) { probe_accumulate<C::NB>(tD + lane_sel + 32u * h, tD + lane_sel + W + 32u * h, lane, acc_s, acc_q); continue; }
         // ---------------- epilogue 2: ReLU, split, A3 (over A1)
@@ -205,8 +203,7 @@ __device__ __forceinline__ void tc_coupling(const unsigned char* wb, GroupSmem& 
             }
             mma_commit(mbar);
         }
-        mbar_wait(mbar, mphase);
-        mphase ^= 1u;
+        group_wait_mma(mbar, mphase, g, i, GT);
         tc_fence_after();
         // ---------------- epilogue 3: shifted sum.  Pixel (r, c), tap (dy, dx) contributes to output (r - dy + 1, c - dx + 1):
         // horizontal neighbours by warp shuffle (s_dy = the three dx taps of row r gathered at their output column), vertical

@@ -62,7 +62,7 @@ __device__ __forceinline__ void relu_split_store16(uint32_t d, uint32_t a_hi, ui
     tmem_wait_ld();
     uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) split2(fmaxf(__uint_as_float(r[2 * k]), 0.f), fmaxf(__uint_as_float(r[2 * k + 1]), 0.f), hi[k], lo[k]);
+    for (int k = 0; k < 8; ++k) relu_split2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]), hi[k], lo[k]);
     tmem_st8(a_hi, hi);
     tmem_st8(a_lo, lo);
     tmem_wait_st();
@@ -200,8 +200,7 @@ __device__ __forceinline__ void tcs_coupling(const float* __restrict__ cblob, SS
                     mma_commit(mbar);
                     if (STAGE == 1) mma_commit(smem_u32(&S.empty[s]));
                 }
-                mbar_wait(mbar, mphase);
-                mphase ^= 1u;
+                group_wait_mma(mbar, mphase, 0, i, GT);
                 tc_fence_after();
                 if (STAGE == 1) {
                     probe16(tD1 + lane_sel + 16u * h, lane, &S.sacc[64 * kc + 16 * h], &S.sacc[W + 64 * kc + 16 * h]);
@@ -227,8 +226,7 @@ __device__ __forceinline__ void tcs_coupling(const float* __restrict__ cblob, SS
                     mma_commit(smem_u32(&S.empty[s]));      // slot free when these have retired
                     mma_commit(mbar);
                 }
-                mbar_wait(mbar, mphase);                     // A2c / D1c are reused by the next chunk
-                mphase ^= 1u;
+                group_wait_mma(mbar, mphase, 0, i, GT);          // A2c / D1c are reused by the next chunk
                 tc_fence_after();
                 ++blk;
             }
@@ -243,8 +241,7 @@ __device__ __forceinline__ void tcs_coupling(const float* __restrict__ cblob, SS
                 mma_commit(mbar);
                 if (STAGE == 2) mma_commit(smem_u32(&S.empty[s]));
             }
-            mbar_wait(mbar, mphase);
-            mphase ^= 1u;
+            group_wait_mma(mbar, mphase, 0, i, GT);
             tc_fence_after();
 #pragma unroll 1
             for (int nc = 0; nc < 4; ++nc) {
@@ -266,8 +263,7 @@ __device__ __forceinline__ void tcs_coupling(const float* __restrict__ cblob, SS
                     if (nc == 3) mma_commit(smem_u32(&S.empty[s]));
                     mma_commit(mbar);
                 }
-                mbar_wait(mbar, mphase);
-                mphase ^= 1u;
+                group_wait_mma(mbar, mphase, 0, i, GT);
                 tc_fence_after();
             }
             if (STAGE == 2) { tc_fence_before(); group_barrier(0, GT); }
