@@ -29,6 +29,7 @@ UNITS = [
     ("nf_wide_tc.cu", ["-use_fast_math"]),
     ("nf_wide_tcs.cu", ["-use_fast_math"]),
     ("nf_train.cu", []),
+    ("nf_train_wide.cu", []),
     ("nf_trainer.cu", []),
     ("nf_api.cu", []),
 ]

@@ -501,9 +501,12 @@ int num_ctas_for(const nf_model* m) { return m->num_ctas > 0 ? m->num_ctas : m->
 // blob; partial ranges and batch-statistics re-folds upload their own blob, stream-ordered (cudaMallocAsync).
 // Tensor-core kernel (nf_wide_tc.cu) where the width has one (probes of the batch-statistics mode included).
 int launch_wide_range(const nf_model* m, int first, int last, bool inverse, NfChainArgs& a, int bn_layer, const float* bn,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool prefer_fp32 = false) {
     cudaError_t e;
-    const bool tc = !m->has_cond && nf::wide_tc_width_supported(m->width) && (m->use_tc_wide || !nf::wide_width_supported(m->width));
+    // prefer_fp32 (the train step): the backward kernels recompute activations in fp32, so the forward that stores every op's
+    // input runs on the fp32 CUDA-core kernel where the width has one
+    const bool tc = !m->has_cond && nf::wide_tc_width_supported(m->width) && (m->use_tc_wide || !nf::wide_width_supported(m->width)) &&
+                    !(prefer_fp32 && nf::wide_width_supported(m->width));
     if (!tc && !nf::wide_width_supported(m->width))
         return fail(NF_ERR_UNSUPPORTED, "clean-image-conditioned couplings are built for coupling-net widths 4 / 8 / 16 / 32, got %d", m->width);
     if (first == 0 && last == (int)m->layers.size() && bn_layer < 0) {
@@ -585,8 +588,9 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
 }
 
 // bijectors [lo, hi) with the BatchNorm of coupling `bn_layer` re-folded on explicit statistics (batch-statistics mode)
-int launch_custom(const nf_model* m, int lo, int hi, bool inverse, NfChainArgs& a, int bn_layer, const float* bn, cudaStream_t stream) {
-    if (m->width != 4 || m->has_cond) return launch_wide_range(m, lo, hi, inverse, a, bn_layer, bn, stream);
+int launch_custom(const nf_model* m, int lo, int hi, bool inverse, NfChainArgs& a, int bn_layer, const float* bn, cudaStream_t stream,
+                  bool prefer_fp32 = false) {
+    if (m->width != 4 || m->has_cond) return launch_wide_range(m, lo, hi, inverse, a, bn_layer, bn, stream, prefer_fp32);
     NfModelParams mp;
     float ldjc = 0.f;
     int rc;
@@ -1423,10 +1427,10 @@ void fill_train_coupling(const nf_model* m, const Group& g, const float* bn, NfT
     P->scale = L.raw.rescaling_scale;
 }
 
-int64_t layer_grad_size(const Layer& L) {
+int64_t layer_grad_size(const Layer& L, int W = 4) {
     switch (L.kind) {
         case L_CONV1X1: return 16;
-        case L_COUPLING: return NF_G_HOST_COUPLING;
+        case L_COUPLING: return W == 4 ? NF_G_HOST_COUPLING : nf_train_wide_host_coupling(W);
         case L_SCALE: return 2 * (int64_t)L.n_rows;
         default: return 0;
     }
@@ -1436,7 +1440,7 @@ int64_t layer_grad_size(const Layer& L) {
 int nf_grad_layout(const nf_model* m, int64_t* offsets) {
     if (!m || !offsets) return fail(NF_ERR_INVALID, "null argument");
     int64_t off = 0;
-    for (size_t l = 0; l < m->layers.size(); ++l) { offsets[l] = off; off += layer_grad_size(m->layers[l]); }
+    for (size_t l = 0; l < m->layers.size(); ++l) { offsets[l] = off; off += layer_grad_size(m->layers[l], m->width); }
     offsets[m->layers.size()] = off;
     return NF_OK;
 }
@@ -1444,7 +1448,179 @@ int nf_grad_layout(const nf_model* m, int64_t* offsets) {
 int nf_train_workspace_floats(const nf_model* m, int64_t n, int64_t* n_floats) {
     if (!m || !n_floats || n < 0) return fail(NF_ERR_INVALID, "bad argument");
     const int64_t G = (int64_t)make_groups(m).size();
-    *n_floats = (G + 4) * n * NF_DIMS + 2 * n;
+    // width 4: G op inputs + two gradient buffers + scratch + g_z'; wider nets: the scratch holds one float per hidden channel
+    *n_floats = (G + 3 + (m->width == 4 ? 1 : m->width / 4)) * n * NF_DIMS + 2 * n;
+    return NF_OK;
+}
+
+// Coupling nets wider than 4 (nf_train_wide.cu): same orchestration as below -- forward with batch-statistics BatchNorm keeping
+// every op's input (probe + apply launches of the wide chain kernels), backward sweep with three passes per coupling and the
+// BatchNorm sums read back in between.
+static int loss_and_grad_wide(const nf_model* m, const float* x, const float* y, const int32_t* rows, int32_t default_row, int64_t n,
+                              int batch_stats, float* workspace, double* dscratch, double* grads_host, float* batch_stats_host,
+                              double* sums_host, cudaStream_t stream) {
+    const int W = m->width;
+    if (!nf::train_wide_width_supported(W)) return fail(NF_ERR_UNSUPPORTED, "the train-step kernels are built for coupling-net widths 4 / 8 / 16 / 32, got %d", W);
+    int rc;
+    const std::vector<Group> groups = make_groups(m);
+    const int G = (int)groups.size();
+    const int64_t S = n * NF_DIMS;
+    auto slot = [&](int k) { return workspace + (int64_t)k * S; };
+    float *gA = slot(G), *gB = slot(G + 1), *gzp = slot(G + 2), *scratch = slot(G + 3);
+    float *d_nll = scratch + (int64_t)(W / 4) * S, *d_sdz = d_nll + n;
+    double *d_stats = dscratch, *d_sums = dscratch + 128, *d_sg = dscratch + 136, *d_mix = dscratch + 256;
+    const double cnt = (double)n * NF_PIXELS;
+    const int sms = num_ctas_for(m);
+    std::vector<int64_t> goff(m->layers.size() + 1);
+    nf_grad_layout(m, goff.data());
+    memset(grads_host, 0, sizeof(double) * (size_t)goff.back());
+    std::vector<float> bn_all((size_t)G * 4 * W, 0.f);
+    const int n_gd = nf_train_wide_grad_doubles(W), n_pf = nf_train_wide_param_floats(W);
+    double* d_cg = nullptr;
+    float* d_par = nullptr;
+    NF_CUDA(cudaMallocAsync((void**)&d_cg, (size_t)n_gd * sizeof(double), stream));
+    NF_CUDA(cudaMallocAsync((void**)&d_par, (size_t)n_pf * sizeof(float), stream));
+    struct Free { double* a; float* b; cudaStream_t s; ~Free() { cudaFreeAsync(a, s); cudaFreeAsync(b, s); } } guard{d_cg, d_par, stream};
+    // ------------------------------------------------------------ forward, keeping every op's input
+    for (int g = 0; g < G; ++g) {
+        const Group& gr = groups[g];
+        const float* in = g == 0 ? x : slot(g - 1);
+        float* bn = &bn_all[(size_t)g * 4 * W];
+        if (!y && range_has_sdn(m, gr.lo, gr.hi)) return fail(NF_ERR_INVALID, "clean patch y is required by an sdn layer");
+        if (gr.cl >= 0) {
+            const Layer& L = m->layers[gr.cl];
+            const WideRawView r(L.wraw.data(), W);
+            if (batch_stats) {
+                const float ident = 1.0f - L.raw.bn_eps;
+                for (int k = 0; k < W; ++k) { bn[k] = 0.f; bn[2 * W + k] = 0.f; bn[W + k] = ident; bn[3 * W + k] = ident; }
+                for (int stage = 1; stage <= 2; ++stage) {
+                    NF_CUDA(cudaMemsetAsync(d_stats, 0, 2 * (size_t)W * sizeof(double), stream));
+                    NfChainArgs a = {};
+                    a.in = in; a.y = y; a.rows = rows; a.n = n; a.default_row = default_row; a.temp = 1.f;
+                    a.bn_stats = d_stats; a.bn_stage = stage;
+                    rc = launch_custom(m, gr.lo, gr.hi, true, a, gr.cl, bn, stream, true);
+                    if (rc) return rc;
+                    std::vector<double> h(2 * (size_t)W);
+                    NF_CUDA(cudaMemcpyAsync(h.data(), d_stats, 2 * (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                    NF_CUDA(cudaStreamSynchronize(stream));
+                    for (int k = 0; k < W; ++k) {
+                        const double mean = h[k] / cnt;
+                        double var = h[W + k] / cnt - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        bn[(stage - 1) * 2 * W + k] = (float)mean;
+                        bn[(stage - 1) * 2 * W + W + k] = (float)var;
+                    }
+                }
+            } else {
+                memcpy(bn, r.bn1_mean, W * sizeof(float)); memcpy(bn + W, r.bn1_var, W * sizeof(float));
+                memcpy(bn + 2 * W, r.bn2_mean, W * sizeof(float)); memcpy(bn + 3 * W, r.bn2_var, W * sizeof(float));
+            }
+            if (batch_stats_host) {
+                int idx = 0;
+                for (int l = 0; l < gr.cl; ++l) idx += m->layers[l].kind == L_COUPLING;
+                memcpy(batch_stats_host + (size_t)4 * W * idx, bn, (size_t)4 * W * sizeof(float));
+            }
+        }
+        NfChainArgs a = {};
+        a.in = in; a.y = y; a.rows = rows; a.out = slot(g); a.n = n; a.default_row = default_row; a.temp = 1.f;
+        a.logdet_in = g > 0 ? d_nll : nullptr;
+        if (g + 1 == G) { a.nll = d_nll; a.sdz = d_sdz; } else a.logdet = d_nll;
+        rc = launch_custom(m, gr.lo, gr.hi, true, a, gr.cl, gr.cl >= 0 ? bn : nullptr, stream, true);
+        if (rc) return rc;
+    }
+    if (sums_host) {
+        cudaError_t e = nf::launch_reduce(d_nll, d_sdz, n, d_sums, stream);
+        if (e != cudaSuccess) return fail(NF_ERR_CUDA, "reduce launch: %s", cudaGetErrorString(e));
+        NF_CUDA(cudaMemcpyAsync(sums_host, d_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    // ------------------------------------------------------------ backward
+    {
+        cudaError_t e = nf::launch_train_prior(slot(G - 1), gA, n, sms, stream);
+        if (e != cudaSuccess) return fail(NF_ERR_CUDA, "prior launch: %s", cudaGetErrorString(e));
+    }
+    std::vector<float> par((size_t)n_pf);
+    std::vector<double> hg((size_t)n_gd);
+    for (int g = G - 1; g >= 0; --g) {
+        const Group& gr = groups[g];
+        const float* zin = g == 0 ? x : slot(g - 1);
+        const float* zout = slot(g);
+        cudaError_t e = cudaSuccess;
+        if (gr.cl >= 0) {
+            const Layer& L = m->layers[gr.cl];
+            const WideRawView r(L.wraw.data(), W);
+            const float* bn = &bn_all[(size_t)g * 4 * W];
+            const bool fused = gr.hi - gr.lo == 2;
+            std::fill(par.begin(), par.end(), 0.f);
+            for (int i = 0; i < 4; ++i)
+                for (int o = 0; o < 4; ++o) par[i * 4 + o] = fused ? m->layers[gr.lo].a[o][i] : (i == o ? 1.f : 0.f);   // a[o][i] = A[i][o]
+            par[16] = fused ? 1.f : 0.f;
+            par[17] = L.raw.rescaling_scale;
+            memcpy(&par[20], r.last_b, 16); memcpy(&par[24], r.last_logs, 16);
+            float* q = &par[32];
+            memcpy(q, r.l1_b, W * 4); q += W;
+            memcpy(q, bn, W * 4); q += W;
+            for (int k = 0; k < W; ++k) q[k] = (float)(1.0 / sqrt((double)bn[W + k] + (double)L.raw.bn_eps));
+            q += W;
+            memcpy(q, r.l2_b, W * 4); q += W;
+            memcpy(q, bn + 2 * W, W * 4); q += W;
+            for (int k = 0; k < W; ++k) q[k] = (float)(1.0 / sqrt((double)bn[3 * W + k] + (double)L.raw.bn_eps));
+            q += W;
+            memcpy(q, r.l1_w, (size_t)18 * W * 4); q += 18 * W;
+            memcpy(q, r.l2_w, (size_t)W * W * 4); q += W * W;
+            memcpy(q, r.last_w, (size_t)36 * (W + 1) * 4);
+            NF_CUDA(cudaMemcpyAsync(d_par, par.data(), (size_t)n_pf * sizeof(float), cudaMemcpyHostToDevice, stream));
+            NF_CUDA(cudaMemsetAsync(d_cg, 0, (size_t)n_gd * sizeof(double), stream));
+            e = nf::launch_train_wide(W, 1, d_par, zin, gA, gzp, scratch, nullptr, n, nullptr, d_cg, sms, stream);
+            if (e != cudaSuccess) return fail(NF_ERR_CUDA, "wide B1 launch: %s", cudaGetErrorString(e));
+            const int oBN2 = n_gd - 4 * W, oBN1 = n_gd - 2 * W;
+            NfBnTermsWide t2 = {}, t1 = {};
+            std::vector<double> h(2 * (size_t)W);
+            if (batch_stats) {
+                NF_CUDA(cudaMemcpyAsync(h.data(), d_cg + oBN2, 2 * (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                NF_CUDA(cudaStreamSynchronize(stream));
+                for (int k = 0; k < 2 * W; ++k) t2.v[k] = (float)(h[k] / cnt);
+            }
+            e = nf::launch_train_wide(W, 2, d_par, zin, nullptr, nullptr, scratch, nullptr, n, &t2, d_cg, sms, stream);
+            if (e != cudaSuccess) return fail(NF_ERR_CUDA, "wide B2 launch: %s", cudaGetErrorString(e));
+            if (batch_stats) {
+                NF_CUDA(cudaMemcpyAsync(h.data(), d_cg + oBN1, 2 * (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                NF_CUDA(cudaStreamSynchronize(stream));
+                for (int k = 0; k < 2 * W; ++k) t1.v[k] = (float)(h[k] / cnt);
+            }
+            e = nf::launch_train_wide(W, 3, d_par, zin, nullptr, gzp, scratch, gB, n, &t1, d_cg, sms, stream);
+            if (e != cudaSuccess) return fail(NF_ERR_CUDA, "wide B3 launch: %s", cudaGetErrorString(e));
+            NF_CUDA(cudaMemcpyAsync(hg.data(), d_cg, (size_t)n_gd * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            NF_CUDA(cudaStreamSynchronize(stream));
+            // device block: A 16 | W1 | b1 | W2 | b2 | W3 | b3 | logs | scale ...  ->  host block: W1 .. scale (contiguous)
+            memcpy(grads_host + goff[gr.cl], hg.data() + 16, (size_t)nf_train_wide_host_coupling(W) * sizeof(double));
+            if (fused && m->layers[gr.lo].kind == L_CONV1X1) memcpy(grads_host + goff[gr.lo], hg.data(), 16 * sizeof(double));
+        } else {
+            const Layer& L = m->layers[gr.lo];
+            if (L.kind == L_SCALE) {
+                NfTrainScale T = {};
+                for (int r = 0; r < NF_MAX_ROWS; ++r) { T.t[r][0] = L.table[r][0]; T.t[r][1] = L.table[r][1]; }
+                T.is_sdn = L.scale_kind == NF_SCALE_SDN; T.full_sum = L.full_sum;
+                NF_CUDA(cudaMemsetAsync(d_sg, 0, 2 * NF_MAX_ROWS * sizeof(double), stream));
+                e = nf::launch_train_scale(zout, y, gA, gB, rows, default_row, n, T, d_sg, sms, stream);
+                if (e != cudaSuccess) return fail(NF_ERR_CUDA, "scale backward launch: %s", cudaGetErrorString(e));
+                NF_CUDA(cudaMemcpyAsync(grads_host + goff[gr.lo], d_sg, 2 * (size_t)L.n_rows * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                NF_CUDA(cudaStreamSynchronize(stream));
+            } else {
+                NfTrainMix M;
+                for (int i = 0; i < 4; ++i)
+                    for (int o = 0; o < 4; ++o) M.A[i][o] = L.a[o][i];
+                NF_CUDA(cudaMemsetAsync(d_mix, 0, 16 * sizeof(double), stream));
+                e = nf::launch_train_mix(zin, gA, gB, n, M, d_mix, sms, stream);
+                if (e != cudaSuccess) return fail(NF_ERR_CUDA, "mix backward launch: %s", cudaGetErrorString(e));
+                if (L.kind == L_CONV1X1) {
+                    NF_CUDA(cudaMemcpyAsync(grads_host + goff[gr.lo], d_mix, 16 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+                    NF_CUDA(cudaStreamSynchronize(stream));
+                }
+            }
+        }
+        float* t = gA; gA = gB; gB = t;
+    }
+    NF_CUDA(cudaStreamSynchronize(stream));
     return NF_OK;
 }
 
@@ -1453,8 +1629,13 @@ int nf_loss_and_grad(const nf_model* m, const float* x, const float* y, const in
                      double* sums_host, void* stream_) {
     int rc = check_ready(m);
     if (rc) return rc;
-    if (m->width != 4) return fail(NF_ERR_UNSUPPORTED, "the train-step kernels are built for coupling-net width 4, got %d", m->width);
     if (m->has_cond) return fail(NF_ERR_UNSUPPORTED, "the train-step kernels do not cover clean-image-conditioned couplings (legacy revnet2d models)");
+    if (m->width != 4) {
+        if (n <= 0 || !x || !workspace || !dscratch || !grads_host) return fail(NF_ERR_INVALID, "x, workspace, dscratch, grads_host are required and n > 0");
+        if (default_row < 0 || default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
+        return loss_and_grad_wide(m, x, y, rows, default_row, n, batch_stats, workspace, dscratch, grads_host, batch_stats_host, sums_host,
+                                  (cudaStream_t)stream_);
+    }
     if (n <= 0 || !x || !workspace || !dscratch || !grads_host) return fail(NF_ERR_INVALID, "x, workspace, dscratch, grads_host are required and n > 0");
     if (default_row < 0 || default_row >= NF_MAX_ROWS) return fail(NF_ERR_INVALID, "default_row out of range");
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -43,7 +43,23 @@ struct NfTrainMix { float A[4][4]; };   // [in][out]
 // host gradient block of one coupling: [W1 72][b1 4][W2 16][b2 4][W3 180][b3 4][logs 4][scale 1]
 #define NF_G_HOST_COUPLING 285
 
+// ---- coupling nets wider than 4 (nf_train_wide.cu, widths 8 / 16 / 32): one CTA per patch
+// device parameter block of one coupling (floats), raw TF layouts:
+//   A [4][4] ([in][out]) | META has_mix, rescaling_scale, 0, 0 | b3 [4] | logs [4] | pad to 32
+//   b1 [W] | m1 [W] | is1 [W] | b2 [W] | m2 [W] | is2 [W] | w1 [9][2][W] | w2 [W][W] ([in][out]) | w3 [9][W+1][4]
+// device gradient block (doubles):
+//   A 16 | W1 18W | b1 W | W2 W*W | b2 W | W3 36(W+1) | b3 4 | logs 4 | scale 1 (+3 pad) | BN2 sums 2W | BN1 sums 2W
+// host gradient block of one coupling: [W1][b1][W2][b2][W3][b3][logs][scale] contiguous from W1, as for width 4
+constexpr int nf_train_wide_param_floats(int W) { return 32 + 6 * W + 18 * W + W * W + 36 * (W + 1); }
+constexpr int nf_train_wide_grad_doubles(int W) { return 16 + 18 * W + W + W * W + W + 36 * (W + 1) + 4 + 4 + 4 + 4 * W; }
+constexpr int nf_train_wide_host_coupling(int W) { return 18 * W + W + W * W + W + 36 * (W + 1) + 4 + 4 + 1; }
+struct NfBnTermsWide { float v[64]; };   // [0..W) = mean(g_hat), [W..2W) = mean(g_hat * x_hat); zeros for moving statistics
+
 namespace nf {
+bool train_wide_width_supported(int W);
+// pass 1 / 2 / 3 = B1 / B2 / B3 (see nf_train_wide.cu); scratch: n * 1024 * W floats
+cudaError_t launch_train_wide(int W, int pass, const float* params, const float* zin, const float* gout, float* gzp, float* scratch, float* gin,
+                              long long n, const NfBnTermsWide* bn, double* grads, int num_sms, cudaStream_t s);
 cudaError_t launch_train_b1(const NfTrainCoupling& P, const float* zin, const float* gout, float* gzp, float* scratch, long long n,
                             double* grads, int num_sms, cudaStream_t s);
 cudaError_t launch_train_b2(const NfTrainCoupling& P, const float* zin, float* scratch, long long n, const NfBnTerms& bn2,

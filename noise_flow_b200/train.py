@@ -178,7 +178,8 @@ def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_trainin
     dscr = torch.zeros(512, device=nf.device, dtype=torch.float64)
     flat = np.zeros(max(int(offs[n_layers]), 1), dtype=np.float64)
     cps = [l for l in spec.layers if l.kind == "coupling"]
-    bstats = np.zeros((max(len(cps), 1), 16), dtype=np.float32)
+    wd = int(spec.width)
+    bstats = np.zeros((max(len(cps), 1), 4 * wd), dtype=np.float32)       # per coupling: mean1, var1, mean2, var2 ([W] each)
     sums = (C.c_double * 3)()
     p = lambda t: t.data_ptr() if t is not None else None
     _tick("setup")
@@ -205,8 +206,8 @@ def loss_and_grad(nf, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_trainin
         elif l.kind == "coupling":
             s = l.data["template"]
             o = 0
-            for name, size in (("/l_1/W", 72), ("/l_1/b", 4), ("/l_2/W", 16), ("/l_2/b", 4), ("/l_last/W", 180),
-                               ("/l_last/b", 4), ("/l_last/logs", 4)):
+            for name, size in (("/l_1/W", 18 * wd), ("/l_1/b", wd), ("/l_2/W", wd * wd), ("/l_2/b", wd),
+                               ("/l_last/W", 36 * (wd + 1)), ("/l_last/b", 4), ("/l_last/logs", 4)):
                 add(s + name, blk[o:o + size])
                 o += size
             add(l.scope + "/rescaling_scale0", blk[o])
@@ -371,7 +372,10 @@ def build_train_program(spec):
 
 
 class DeviceTrainer:
-    """The same train step with NOTHING on the host: every TF variable, the Adam slots and the step counter live in
+    """(Coupling-net widths 8 / 16 / 32: the constructor returns a :class:`WideTrainer` -- same interface on the
+    host-synchronous kernels.)
+
+    The same train step with NOTHING on the host: every TF variable, the Adam slots and the step counter live in
     device memory inside an ``nf_trainer`` (include/noiseflow_b200.h); LU assembly, scale tables, batch-statistics
     BatchNorm, backward, chain rules, Adam and the BatchNorm moving averages are kernels on one stream, with no
     stream synchronisation inside a step.  ``step`` is one ``sess.run([train_op, loss, sd_z])``
@@ -384,6 +388,11 @@ class DeviceTrainer:
 
     ``sync_to_model()`` copies the trained variables back into ``nf.variables`` and re-folds the inference engine.
     """
+
+    def __new__(cls, nf, *args, **kw):
+        if cls is DeviceTrainer and int(nf.spec.width) != 4:
+            return object.__new__(WideTrainer)
+        return object.__new__(cls)
 
     def __init__(self, nf, learning_rate=1e-4, beta1=0.9, beta2=0.999, epsilon=1e-8, max_batch=256, group=None,
                  cuda_graph=True, cta_warps=0, fused=True):
@@ -507,3 +516,59 @@ class DeviceTrainer:
                 self.handle = C.c_void_p()
         except Exception:
             pass
+
+
+class WideTrainer(DeviceTrainer):
+    """``DeviceTrainer`` for coupling nets wider than 4 (``--width`` 8 / 16 / 32; the reference trains any width,
+    train_noise_flow.py:187-198).  Same methods, built on the host-synchronous step: forward with batch-statistics BatchNorm
+    through the wide chain kernels, backward through ``csrc/nf_train_wide.cu`` (one CTA per patch, three passes per
+    coupling), chain rules to the LU / scale variables and TF-rule Adam on the host.  Data parallel: one all-reduce of
+    [gradients | sums | batch statistics], replicas stay identical (:func:`train_step`)."""
+
+    def __init__(self, nf, learning_rate=1e-4, beta1=0.9, beta2=0.999, epsilon=1e-8, max_batch=256, group=None, **_unused):
+        nf.build("inverse")
+        if int(nf.spec.width) not in (8, 16, 32):
+            raise NotImplementedError("the train-step kernels are built for coupling-net widths 4 / 8 / 16 / 32, got %d" % int(nf.spec.width))
+        self.nf, self.group = nf, group
+        self.opt = AdamOptimizer(learning_rate, beta1, beta2, epsilon)
+        self.max_batch = int(max_batch)
+        self.steps = 0
+        self.handle = None
+        self._last = None
+
+    def loss_and_grad(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, is_training=True):
+        loss, sd_z, grads = loss_and_grad(self.nf, x, y, nlf0, nlf1, iso, cam, is_training=is_training, refold=False, bn_update=False)
+        self._last = (float(loss), float(sd_z), grads)
+        return int(np.asarray(x).shape[0]) if not isinstance(x, torch.Tensor) else int(x.shape[0])
+
+    def step(self, x, y, nlf0=None, nlf1=None, iso=None, cam=None, sync=True):
+        loss, sd_z = train_step(self.nf, self.opt, x, y, nlf0, nlf1, iso, cam, group=self.group)
+        self.steps += 1
+        self._last = (float(loss), float(sd_z), None)
+        return float(loss), float(sd_z)
+
+    def gradients(self) -> Dict[str, np.ndarray]:
+        tr = self.nf.spec.store.trainable
+        return {k: np.asarray(g) for k, g in (self._last[2] or {}).items() if tr.get(k, False)}
+
+    def loss(self):
+        return self._last[0], self._last[1]
+
+    def batch_stats(self) -> np.ndarray:
+        return np.asarray(self.nf.last_batch_stats)
+
+    def launches_per_step(self, is_training=True) -> int:
+        n_cp = sum(l.kind == "coupling" for l in self.nf.spec.layers)
+        return n_cp * ((3 if is_training else 1) + 3) + (len(self.nf.spec.layers) - n_cp) * 2 + 2
+
+    def variables(self) -> Dict[str, np.ndarray]:
+        return {k: v.copy() for k, v in self.nf.spec.store.vars.items()}
+
+    def sync_to_model(self):
+        self.nf.refresh_parameters()
+
+    def sync_from_model(self):
+        pass
+
+    def __del__(self):
+        pass

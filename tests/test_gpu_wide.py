@@ -162,14 +162,68 @@ def test_wide_unsupported_widths_and_switches_raise():
         nf.set_tensor_cores(False)            # width 64 has no CUDA-core kernel
 
 
-def test_wide_training_is_refused_loudly():
+@pytest.mark.parametrize("width,is_training", [(8, True), (8, False), (16, True), (32, True), (32, False)])
+def test_wide_gradients_match_oracle_autograd(width, is_training):
+    """The train step at coupling-net widths 8 / 16 / 32 (the reference trains any `--width`, train_noise_flow.py:187-198):
+    d(mean NLL) / d(every trainable variable) from the CTA-per-patch backward kernels (csrc/nf_train_wide.cu) against torch
+    autograd through the fp64 oracle, both BatchNorm modes; `DeviceTrainer` hands out the wide trainer."""
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import DeviceTrainer, WideTrainer
+    from test_gpu_train import _check, _oracle_loss_and_grads
+    hps, vs = _perturbed_model(width, arch="sdn5|unc|gain4|unc")
+    nf = NoiseFlow([32, 32, 4], is_training, copy.copy(hps), variables={k: v.copy() for k, v in vs.items()}, device="cuda:0",
+                   first_call="inverse")
+    x, y = synth_batch(5, cam=2, iso=100, seed=95)
+    x = (x * 20).astype(np.float32)
+    tr = DeviceTrainer(nf, max_batch=8)
+    assert isinstance(tr, WideTrainer)
+    tr.loss_and_grad(x, y, iso=[100.0], cam=[2.0], is_training=is_training)
+    loss, sd_z = tr.loss()
+    loss_o, sd_o, grads_o, _ = _oracle_loss_and_grads(hps, vs, x, y, 100.0, 2.0, is_training)
+    assert abs(loss - loss_o) / 4096 < 1e-4 and abs(sd_z - sd_o) < 1e-4
+    worst = _check(tr.gradients(), grads_o, rel=5e-4)
+    print("width %d, is_training %s: max relative gradient error %.2e" % (width, is_training, worst))
+
+
+def test_wide_adam_steps_follow_the_oracle():
+    """Two Adam steps at width 16 (batch-statistics BatchNorm, TF update rule, moving averages) against the same steps taken
+    with the oracle's autograd gradients."""
+    from noise_flow_b200 import NoiseFlow
+    from noise_flow_b200.train import AdamOptimizer, DeviceTrainer
+    from test_gpu_train import _oracle_loss_and_grads
+    hps, vs = _perturbed_model(16, arch="sdn5|unc|gain4|unc")
+    nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables={k: v.copy() for k, v in vs.items()}, device="cuda:0",
+                   first_call="inverse")
+    tr = DeviceTrainer(nf, learning_rate=1e-3, max_batch=8)
+    x, y = synth_batch(4, cam=2, iso=100, seed=97)
+    x = (x * 20).astype(np.float32)
+    ref_vars = {k: v.copy() for k, v in vs.items()}
+    opt = AdamOptimizer(learning_rate=1e-3)
+    for step in range(2):
+        loss, _ = tr.step(x, y, iso=[100.0], cam=[2.0])
+        loss_o, _, grads_o, orc = _oracle_loss_and_grads(hps, ref_vars, x, y, 100.0, 2.0, True)
+        assert abs(loss - loss_o) / 4096 < 1e-4
+        opt.apply_gradients(ref_vars, grads_o)
+        for k, v in orc.store.vars.items():          # the oracle moved its BatchNorm statistics during the training-mode pass
+            if k.endswith("/mean") or k.endswith("/var"):
+                ref_vars[k] = v.detach().numpy().astype(np.float32)
+        got = tr.variables()
+        for k, want in ref_vars.items():
+            d = np.abs(got[k].astype(np.float64) - want).max()
+            if k.endswith("/l_1/b") or k.endswith("/l_2/b"):
+                assert d <= (step + 1) * 1e-3 * 2.01 + 1e-7, (step, k, d)     # exact-zero gradients: +-lr random walk on both sides
+            else:
+                assert d < 2e-4 * max(1.0, np.abs(want).max()) + 2e-5, (step, k, d)
+
+
+def test_unsupported_training_is_refused_loudly():
     from noise_flow_b200 import NoiseFlow
     from noise_flow_b200.train import DeviceTrainer, loss_and_grad
-    hps, vs = _perturbed_model(8)
+    hps, vs = _perturbed_model(64, arch="unc")
     nf = NoiseFlow([32, 32, 4], True, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
     x, y = synth_batch(2)
     with pytest.raises(NotImplementedError):
-        DeviceTrainer(nf)
+        DeviceTrainer(nf)                               # widths 4 / 8 / 16 / 32
     with pytest.raises(RuntimeError):
         loss_and_grad(nf, x, y, iso=[100.0], cam=[2.0])
 
