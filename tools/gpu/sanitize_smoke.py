@@ -68,6 +68,29 @@ if os.environ.get("NF_SANITIZE_WIDE", "1") == "1":        # CTA-per-patch kernel
         zl, _ = nfw.run_layers(1, 3, "inverse", x[:nw], yy=y[:nw], iso=[100.0], cam=[2.0])
         print("wide %d: nll/dim %.4f round trip %.2e batch-stat nll/dim %.4f" % (wd, float(nl.mean()) / 4096,
               float(np.abs(xw.cpu().numpy() - x[:nw]).max()), float(nb.mean()) / 4096))
+if os.environ.get("NF_SANITIZE_WIDE_TC", "1") == "1":     # round 4: tensor-core wide kernels (resident 64, streamed 256), legacy
+    nw = min(n, 5)                                         # couplings, wide backward kernels
+    for wd in (64, 256):
+        nfw = NoiseFlow([32, 32, 4], False, make_hps(arch="sdn5|unc|gain4|unc", width=wd), device="cuda:0", first_call="inverse", seed=1)
+        for k, v in nfw.variables.items():
+            if k.endswith("/l_last/W"):
+                v[...] = (np.random.RandomState(2).randn(*v.shape) * 0.05).astype(np.float32)
+        nfw.refresh_parameters()
+        nl, _, zw = nfw._loss(x[:nw], y[:nw], iso=[100.0], cam=[2.0], return_z=True)
+        xw = nfw.forward(zw, None, yy=y[:nw], iso=[100.0], cam=[2.0])
+        nb, _ = nfw._loss(x[:nw], y[:nw], iso=[100.0], cam=[2.0], is_training=True)
+        print("tensor-core wide %d: nll/dim %.4f round trip %.2e batch-stat nll/dim %.4f" % (wd, float(nl.mean()) / 4096,
+              float(np.abs(xw.cpu().numpy() - x[:nw]).max()), float(nb.mean()) / 4096))
+    nfl = NoiseFlow([32, 32, 4], False, make_hps(arch=None, depth=2, sidd_cond="condXY", append_cY=True), device="cuda:0",
+                    first_call="inverse", seed=1)
+    nl, _ = nfl._loss(x[:nw], y[:nw], iso=[100.0], cam=[2.0])
+    nb, _ = nfl._loss(x[:nw], y[:nw], iso=[100.0], cam=[2.0], is_training=True)
+    print("legacy condXY + cY: nll/dim %.4f batch-stat %.4f" % (float(nl.mean()) / 4096, float(nb.mean()) / 4096))
+    from noise_flow_b200.train import DeviceTrainer
+    nft = NoiseFlow([32, 32, 4], True, make_hps(arch="sdn5|unc|gain4|unc", width=16), device="cuda:0", first_call="inverse", seed=1)
+    trw = DeviceTrainer(nft, max_batch=8)
+    lw, _ = trw.step(x[:nw], y[:nw], iso=[100.0], cam=[2.0])
+    print("wide trainer (16): loss/dim %.4f" % (lw / 4096))
 if os.environ.get("NF_SANITIZE_TC", "0") == "1":
     nf.set_tensor_cores(True)
     nll_t, _ = nf._loss(x, y, iso=[100.0], cam=[2.0])
