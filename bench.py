@@ -97,26 +97,33 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_rate(hps, ck, seconds_target=12.0, threads=None):
-    """patches/s of the oracle port (torch-CPU fp32, all host threads) on a bounded sample."""
+def cpu_oracle_rate(hps, ck, seconds_target=12.0, threads=None, per_step=1024):
+    """patches/s of the oracle port (torch-CPU fp32, all host threads) on a bounded sample: steps of `per_step` patches -- the SAME
+    step size as `--impl reference` (--ref-patches), so the two CPU numbers of a round agree (larger steps run slower on the
+    host: 16 384-patch steps measured 5.1 k patches/s against 10 k at 1024, round 1)."""
     from common import make_oracle, synth_batch
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     orc = make_oracle(hps, ck, dtype=torch.float32)
-    x, y = synth_batch(256, seed=3)
+    x, y = synth_batch(per_step, seed=4)
     orc._loss(x, y, iso=[100.0], cam=[2.0])                      # warm-up
     t0 = time.perf_counter()
     orc._loss(x, y, iso=[100.0], cam=[2.0])
-    dt = time.perf_counter() - t0
-    n = int(min(16384, max(256, 256 * seconds_target / max(dt, 1e-3))))          # 16384 patches: ~6 GB of activations on the host
-    reps = int(max(1, min(8, round(seconds_target * 256 / max(dt, 1e-3) / n))))   # bounded sample: ~seconds_target of CPU work
-    x, y = synth_batch(n, seed=4)
+    dt1 = time.perf_counter() - t0
+    reps = int(max(2, min(200, round(seconds_target / max(dt1, 1e-3)))))
     t0 = time.perf_counter()
     for _ in range(reps):
         orc._loss(x, y, iso=[100.0], cam=[2.0])
     dt = time.perf_counter() - t0
-    return reps * n / dt, threads, ("log_prob of %d x %d synthetic S6/ISO-100 patches, oracle port torch-CPU fp32, %.1f s"
-                                    % (reps, n, dt))
+    return reps * per_step / dt, threads, ("log_prob, %d steps x %d synthetic S6/ISO-100 patches, oracle port torch-CPU fp32, %.1f s"
+                                           % (reps, per_step, dt))
+
+
+def workload_config(mode, arch, B, world, width, clean):
+    """`config` of the JSON line -- the SAME dict for this engine's arm and for `--impl reference` (the driver compares them)."""
+    return {"workload": "%s Noise Flow (shipped weights, arch %s), batch %d 32x32x4 patches per GPU, cam S6 / ISO 100" % (mode, arch, B),
+            "per_gpu_batch": B, "global_batch": world * B, "parallelism": "dp%d" % world, "width": width, "clean": clean,
+            "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (2 * B * 16384 / 2 ** 30)}
 
 
 def run_reference(args):
@@ -154,11 +161,9 @@ def run_reference(args):
            "value": val, "unit": "patches/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "%s Noise Flow (shipped weights, arch %s), batch %d 32x32x4 patches per GPU, "
-                                  "cam S6 / ISO 100" % (mode, hps.arch, args.batch),
-                      "per_gpu_batch": args.batch, "global_batch": args.gpus * args.batch, "parallelism": "dp%d" % args.gpus,
-                      "width": 4, "reference_sample": sample,
-                      "note": "TF 1.12/TFP 0.5 reference cannot run here; timed arm = oracle port (torch-CPU fp32)"},
+           "config": workload_config(mode, hps.arch, args.batch, args.gpus, 4, args.clean),
+           "reference_note": "TF 1.12/TFP 0.5 reference cannot run here; timed arm = oracle port (torch-CPU fp32); every step is a "
+                             "bounded sample of the workload: " + sample,
            "cpu_baseline": {"value": val, "unit": "patches/s", "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -690,12 +695,7 @@ def main():
            "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "%s Noise Flow (shipped weights, arch %s), batch %d 32x32x4 patches per GPU, "
-                                  "cam S6 / ISO 100" % (args.mode, hps.arch, B),
-                      "per_gpu_batch": B, "global_batch": world * B, "parallelism": "dp%d" % world,
-                      "width": args.width, "clean": args.clean,
-                      "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (2 * B * 16384 / 2 ** 30),
-                      "mean_nll_per_dim": mean_nll},
+           "config": workload_config(args.mode, hps.arch, B, world, args.width, args.clean), "mean_nll_per_dim": mean_nll,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else ("nf_chain_kernel" if args.width == 4 else "nf_wide_chain_kernel"),
                         "kernel_ms": kms, "alg_bytes_per_patch": alg,
@@ -737,7 +737,7 @@ def main():
             out["config"]["note"] = ("one sess.run([train_op, loss, sd_z]) equivalent: batch-stat BN forward (2 probes + apply per "
                                      "coupling), backward (3 passes per coupling), host LU/scale chain rules, Adam, re-fold")
     if world == 1 and not args.no_cpu_baseline and args.mode != "train":
-        v, cores, sample = cpu_oracle_rate(hps, ck)
+        v, cores, sample = cpu_oracle_rate(hps, ck, per_step=args.ref_patches)
         out["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(out), flush=True)
     if world > 1:
