@@ -456,7 +456,7 @@ def main():
     ap.add_argument("--warps", type=int, default=0, help="resident patches per CTA (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--tc", type=int, default=0, help="1: tensor-core (tcgen05) coupling convolutions")
+    ap.add_argument("--tc", type=int, default=0, help="width 4: 2 = hybrid kernel (conv-3 on tcgen05), 1 = older all-TC experiment, 0 = all-fp32 kernel")
     ap.add_argument("--cta-warps", type=int, default=0, help="train mode: warps per patch-CTA (0 = automatic, 8, 16)")
     ap.add_argument("--fused", type=int, default=1, help="train mode: 1 = one cooperative kernel per loss+gradient, 0 = one launch per pass")
     ap.add_argument("--trainer", default="device", choices=["device", "host"],
@@ -501,7 +501,7 @@ def main():
     if args.warps:
         nf.set_launch(args.warps, 0)
     if args.tc:
-        nf.set_tensor_cores(True)
+        nf.set_tensor_cores(args.tc)
     lib, eng = _lib.load(), nf._engine
     B = args.batch
     g = torch.Generator(device=dev).manual_seed(1234 + rank)

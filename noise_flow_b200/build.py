@@ -24,6 +24,7 @@ UNITS = [
     ("nf_kernels.cu", ["-use_fast_math"]),
     ("nf_stream.cu", ["-use_fast_math"]),
     ("nf_tc.cu", ["-use_fast_math"]),
+    ("nf_hybrid.cu", ["-use_fast_math"]),
     ("nf_wide.cu", ["-use_fast_math"]),
     ("nf_wide_cond.cu", ["-use_fast_math"]),
     ("nf_wide_tc.cu", ["-use_fast_math"]),

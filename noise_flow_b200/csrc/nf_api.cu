@@ -560,7 +560,9 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
         a.last_layer = mp.n_layers;
         if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
             e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);   // HBM-bound streaming path
-        else if (m->use_tc && nf::tc_program_supported(mp, a))
+        else if (m->use_tc == 2 && nf::hybrid_program_supported(mp, a))
+            e = nf::launch_chain_hybrid(mp, a, inverse, num_ctas_for(m), stream);   // conv-3 on tcgen05, the rest fp32
+        else if (m->use_tc == 1 && nf::tc_program_supported(mp, a))
             e = nf::launch_chain_tc(mp, a, inverse, num_ctas_for(m), stream);   // tcgen05 path
         else
             e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
@@ -578,7 +580,9 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
         a.ldj_const = ldj;
         if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
             e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);
-        else if (m->use_tc && nf::tc_program_supported(mp, a))
+        else if (m->use_tc == 2 && nf::hybrid_program_supported(mp, a))
+            e = nf::launch_chain_hybrid(mp, a, inverse, num_ctas_for(m), stream);
+        else if (m->use_tc == 1 && nf::tc_program_supported(mp, a))
             e = nf::launch_chain_tc(mp, a, inverse, num_ctas_for(m), stream);
         else
             e = nf::launch_chain(mp, a, inverse, num_ctas_for(m), m->warps_per_cta, stream);
@@ -910,7 +914,7 @@ int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas) {
 
 int nf_model_set_tensor_cores(nf_model* m, int enable) {
     if (!m) return fail(NF_ERR_INVALID, "null model");
-    if (m->width == 4) m->use_tc = enable ? 1 : 0;
+    if (m->width == 4) m->use_tc = enable == 2 ? 2 : (enable ? 1 : 0);
     else {
         if (!enable && !nf::wide_width_supported(m->width))
             return fail(NF_ERR_UNSUPPORTED, "width %d has no CUDA-core kernel: the tensor-core kernel cannot be switched off", m->width);

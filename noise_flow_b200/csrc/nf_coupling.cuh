@@ -18,8 +18,6 @@
 
 namespace nf {
 
-struct Acc4 { float2 v[4]; };   // one pending output row: 4 outputs x (even, odd) input-channel partial sums
-
 struct B3 { float top[4], mid[4], bot[4]; };   // conv2d_zeros bias incl. edge indicator, for this lane's column
 
 template <class CP>
@@ -32,34 +30,6 @@ __device__ __forceinline__ B3 load_b3(const CP& P, int lane) {
         b.bot[o] = lane == 0 ? P.b3[2][0][o] : (lane == 31 ? P.b3[2][2][o] : P.b3[2][1][o]);
     }
     return b;
-}
-
-// The 4x4 mix matrix as PER-THREAD registers.  Left to itself ptxas hoists these 16 uniform loads (and a dozen conv-1
-// weights) out of the row loop, runs out of uniform registers, parks the values in vector registers and pays an R2UR per
-// value and row step (31 of 293 instructions).  Adding a 0.0f that is only known at run time (the zero halo of the row
-// ring, read from shared memory) makes the values genuinely per-thread for ptxas -- it sees through empty inline asm and
-// even through shuffles of warp-uniform values -- so the mix runs as FFMA2 with vector-register operands: 261
-// instructions per step, no R2UR (data -> latent kernel; the latent -> data kernel keeps its 34 R2UR either way).
-template <bool INV, class CP>
-__device__ __forceinline__ void load_mix_regs(const CP& P, float2 (&am)[4][2], const float rt_zero) {
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        am[o][0] = INV ? ld2(&P.a[o][0]) : ld2(&P.ainv[o][0]);
-        am[o][1] = INV ? ld2(&P.a[o][2]) : ld2(&P.ainv[o][2]);
-        am[o][0] = make_float2(am[o][0].x + rt_zero, am[o][0].y + rt_zero);
-        am[o][1] = make_float2(am[o][1].x + rt_zero, am[o][1].y + rt_zero);
-    }
-}
-__device__ __forceinline__ float4 mix4r(float4 v, const float2 (&m)[4][2]) {
-    const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
-    float r[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        float2 t = ffma2(lo, m[o][0], make_float2(0.f, 0.f));
-        t = ffma2(hi, m[o][1], t);
-        r[o] = t.x + t.y;
-    }
-    return make_float4(r[0], r[1], r[2], r[3]);
 }
 
 // STATS: 0 = normal step.  1 / 2 = batch-statistics probe (reference batch_norm(training=True),

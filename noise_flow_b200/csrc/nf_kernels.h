@@ -45,4 +45,7 @@ cudaError_t launch_histogram(const float* data, long long count, const double* e
                              int num_sms, cudaStream_t stream);
 bool tc_program_supported(const NfModelParams& mp, const NfChainArgs& a);
 cudaError_t launch_chain_tc(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, cudaStream_t stream);
+// hybrid chain kernel (nf_hybrid.cu): conv-3 of every coupling on tcgen05, everything else as in launch_chain
+bool hybrid_program_supported(const NfModelParams& mp, const NfChainArgs& a);
+cudaError_t launch_chain_hybrid(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, cudaStream_t stream);
 }  // namespace nf

@@ -250,13 +250,14 @@ class NoiseFlow(object):
         self.build()
         _lib.check(self._engine.lib.nf_model_set_launch(self._engine.handle, warps_per_cta, num_ctas), "nf_model_set_launch")
 
-    def set_tensor_cores(self, enable: bool = True):
-        """Width 4: run the coupling-net 3x3 convolutions on the tensor cores (tcgen05, bf16 hi/lo split operands;
-        experimental, default off).  Widths 32 / 64 / 128: the tensor-core kernel is the default; ``False`` selects the
-        CUDA-core kernel (width 32 only)."""
+    def set_tensor_cores(self, enable=True):
+        """Width 4: ``"hybrid"`` (or 2) runs conv-3 of every coupling net on the tensor cores (tcgen05, fp16 hi/lo split
+        operands, csrc/nf_hybrid.cu) and everything else as the fp32 kernel does; ``True`` (1) selects the older
+        experimental kernel with both 3x3 convolutions as bf16 hi/lo implicit GEMMs; ``False`` the all-fp32 kernel.
+        Widths 32 / 64 / 128: the tensor-core kernel is the default; ``False`` selects the CUDA-core kernel (width 32 only)."""
         self.build()
-        _lib.check(self._engine.lib.nf_model_set_tensor_cores(self._engine.handle, 1 if enable else 0),
-                   "nf_model_set_tensor_cores")
+        mode = 2 if enable in ("hybrid", 2) else (1 if enable else 0)
+        _lib.check(self._engine.lib.nf_model_set_tensor_cores(self._engine.handle, mode), "nf_model_set_tensor_cores")
         return self
 
     def set_batch_stats_fused(self, enable: bool = True):
