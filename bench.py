@@ -353,10 +353,27 @@ def run_also(args, nf, hps, ck, x, y, dev, rank, world, sm_mhz, row):
         "metric": "patches_per_sec_sample", "value": world * B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 20,
         "config": {"workload": "sample (temperature 0.6, in-kernel Philox) Noise Flow, batch %d per GPU, cam S6 / ISO 100" % B,
                    "baseline_config": 3, "per_gpu_batch": B},
-        "roofline": _hbm_roofline(B, ALG_BYTES_SAMPLE, ms, "nf_chain_kernel<false>", _traffic("sample_%d" % B),
-                                  "binding roof is the FP32 FMA pipe (roofline_fp32)"),
+        "roofline": _hbm_roofline(B, ALG_BYTES_SAMPLE, ms, "nf_chain_kernel<false>",
+                                  _traffic("sample_%d" % B), "binding roof is the FP32 FMA pipe (roofline_fp32)"),
+        "roofline_fp32": _fp32_roofline(B, conv_flop, ms, sm_mhz), "gpu_launches": world * 20}
+    # the same sampler and log_prob on the hybrid kernel (conv-3 on tcgen05; opt-in: nf_model_set_tensor_cores 2)
+    nf.set_tensor_cores(2)
+    ms = _timed(lambda i: _lib.check(lib.nf_sample(eng.handle, y.data_ptr(), None, row, B, 0.6, None, 7, i, rank * B, xs.data_ptr(), stream)),
+                20, 3, dev, world)
+    out["sample_%d_hybrid_kernel" % B] = {
+        "metric": "patches_per_sec_sample", "value": world * B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 20,
+        "config": {"workload": "sample, hybrid kernel (conv-3 on tcgen05; nf_model_set_tensor_cores 2), batch %d per GPU" % B, "per_gpu_batch": B},
+        "roofline": _hbm_roofline(B, ALG_BYTES_SAMPLE, ms, "nf_chain_hyb_kernel<false>", None, "binding roof is the FP32 FMA pipe (roofline_fp32)"),
         "roofline_fp32": _fp32_roofline(B, conv_flop, ms, sm_mhz), "gpu_launches": world * 20}
     del xs
+    nf.set_tensor_cores(2)
+    ms = _timed(lambda i: log_prob_step(eng.handle, x, y, B), 20, 3, dev, world)
+    out["log_prob_%d_hybrid_kernel" % B] = {
+        "metric": "patches_per_sec_nll", "value": world * B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 20,
+        "config": {"workload": "log_prob, hybrid kernel (conv-3 on tcgen05; nf_model_set_tensor_cores 2), batch %d per GPU" % B, "per_gpu_batch": B},
+        "roofline": _hbm_roofline(B, ALG_BYTES_LOG_PROB, ms, "nf_chain_hyb_kernel<true>", None, "binding roof is the FP32 FMA pipe (roofline_fp32)"),
+        "roofline_fp32": _fp32_roofline(B, conv_flop, ms, sm_mhz), "gpu_launches": world * 20 * 2}
+    nf.set_tensor_cores(0 if args.tc < 0 else args.tc)
     # ---- configs 2 and 4: log_prob at 4096 (config 2) and the batch sweep 1k / 16k / 64k / 256k per GPU (config 4); batches
     # smaller than the resident one walk through it slice by slice, so consecutive launches never re-read L2-resident inputs
     for n in (1024, 4096, 16384, 262144):
@@ -456,7 +473,8 @@ def main():
     ap.add_argument("--warps", type=int, default=0, help="resident patches per CTA (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--tc", type=int, default=0, help="width 4: 2 = hybrid kernel (conv-3 on tcgen05), 1 = older all-TC experiment, 0 = all-fp32 kernel")
+    ap.add_argument("--tc", type=int, default=-1, help="width 4: -1 = library default (hybrid kernel for sampling, all-fp32 for log_prob), "
+                    "0 = all-fp32 kernel, 2 = hybrid kernel (conv-3 on tcgen05) in both directions, 1 = older all-TC experiment")
     ap.add_argument("--cta-warps", type=int, default=0, help="train mode: warps per patch-CTA (0 = automatic, 8, 16)")
     ap.add_argument("--fused", type=int, default=1, help="train mode: 1 = one cooperative kernel per loss+gradient, 0 = one launch per pass")
     ap.add_argument("--trainer", default="device", choices=["device", "host"],
@@ -500,7 +518,7 @@ def main():
     nf = NoiseFlow([32, 32, 4], False, hps, variables=ck, first_call="inverse", device=dev)
     if args.warps:
         nf.set_launch(args.warps, 0)
-    if args.tc:
+    if args.tc >= 0:
         nf.set_tensor_cores(args.tc)
     lib, eng = _lib.load(), nf._engine
     B = args.batch
@@ -660,7 +678,7 @@ def main():
 
     # ---- the other BASELINE configs (every rank takes part), sharding check
     also = shard = None
-    default_workload = args.mode == "log_prob" and args.width == 4 and not args.arch and not args.tc and args.clean == "uniform"
+    default_workload = args.mode == "log_prob" and args.width == 4 and not args.arch and args.tc < 0 and args.clean == "uniform"
     sm_mhz_now = 1965.0
     if rank == 0 and clocks and clocks.get("sm_mhz"):
         sm_mhz_now = float(clocks["sm_mhz"])
@@ -697,7 +715,7 @@ def main():
            "dtype": "f32", "data": "synthetic",
            "config": workload_config(args.mode, hps.arch, B, world, args.width, args.clean), "mean_nll_per_dim": mean_nll,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else ("nf_chain_kernel" if args.width == 4 else "nf_wide_chain_kernel"),
+                        "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else (("nf_chain_hyb_kernel" if (args.tc == 2 or (args.tc == 3 and args.mode == "sample")) else "nf_chain_kernel") if args.width == 4 else "nf_wide_chain_kernel"),
                         "kernel_ms": kms, "alg_bytes_per_patch": alg,
                         "note": ("binding roof is the FP32 FMA pipe (see roofline_fp32), not HBM" if n_couplings else
                                  "scale-layer-only chain: streaming kernel, HBM-bound")},

@@ -120,10 +120,16 @@ int nf_model_begin_update(nf_model* m);
 int nf_model_end_update(nf_model* m);
 /* Launch tuning: resident patches (warps) per CTA in [1, 16] and CTA count (0 = one per SM). */
 int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas);
-/* Width 4 -- enable != 0: run the two 3x3 convolutions of every coupling net on the tensor cores (tcgen05.mma with bf16
- * hi/lo-split operands, fp32 accumulation in TMEM; csrc/nf_tc.cu) for full-chain calls with explicit inputs;
- * other calls (partial ranges, in-kernel Philox, batch-statistics probes) keep the fp32 CUDA-core kernel (default 0:
- * at 4 output channels the tensor pipe does not pay).
+/* Width 4 -- which kernel runs full-chain / range calls (batch-statistics probes always use the all-fp32 kernel):
+ *   0 (default): the all-fp32 CUDA-core kernel (csrc/nf_kernels.cu) everywhere;
+ *   2: the hybrid kernel (csrc/nf_hybrid.cu): conv-3 of every coupling net on the tensor cores (tcgen05.mma, fp16 hi/lo-split
+ *      operands, fp32 accumulation in TMEM), everything else fp32 -- |dNLL| vs the fp32 kernel < 1e-6 nats/dim on the shipped
+ *      model; 22 instead of 24 mantissa bits inside conv-3, which a stress model with O(1) random weights shows as 2e-5
+ *      instead of 1e-5 relative error of a sampled patch -- hence opt-in;
+ *   3: the hybrid kernel for the latent -> data direction only (nf_sample / nf_forward, where it is 7 % faster), the
+ *      all-fp32 kernel for data -> latent (nf_log_prob / nf_inverse, where the two are equally fast);
+ *   1: older experiment -- both 3x3 convolutions as bf16 hi/lo implicit GEMMs (csrc/nf_tc.cu), full-chain calls with explicit
+ *      inputs only; slower than 0.
  * Widths 32 ... 512 -- the tensor-core kernels (csrc/nf_wide_tc.cu, nf_wide_tcs.cu: all three convolutions as tcgen05.mma
  * GEMMs, activations and accumulators in tensor memory) are the default; enable == 0 selects the CUDA-core kernel at
  * width 32 and is refused (NF_ERR_UNSUPPORTED) at 64 ... 512, which have no other kernel. */

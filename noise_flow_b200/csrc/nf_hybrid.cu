@@ -1,30 +1,31 @@
 // Fused Noise Flow chain for sm_100a with the coupling net's last convolution on the tensor cores
 // ("hybrid" chain kernel).  Same organisation as nf_kernels.cu -- one warp owns one 32x32x4 patch, the patch is
-// resident in tensor memory for the whole chain, a coupling is one software-pipelined pass over the 32 rows --
-// but conv-3 (3x3, 4 -> 4, 58 % of the multiply-adds of a coupling) leaves the FP32 pipe:
+// resident on the SM for the whole chain, a coupling is one software-pipelined pass over the 32 rows -- but conv-3
+// (3x3, 4 -> 4, 58 % of the multiply-adds of a coupling) leaves the FP32 pipe:
 //
-//   * FOUR worker warps form a group (their 4 x 32 lanes are the 128 TMEM lanes an M = 128 MMA writes).  For image
-//     row r every lane writes its pixel's h2 activation, split into fp16 (hi, lo) halves, into the group's A tile
-//     in shared memory: once as its own pixel's centre tap and once each as the left / right neighbour's tap, so
-//     the three horizontal taps of a pixel sit side by side in K and the SAME padding is simply never written.
-//   * one elected thread (an issuer warp per group) runs  D[128 x 16] = A[128 x 48] . B[48 x 16]  as three
-//     tcgen05.mma (kind::f16, fp32 accumulate in TMEM).  K = 3 taps x (hi, lo) x 4 channels against W_hi, plus the
-//     hi halves again against W_lo, plus three one-hot "column class" slots that carry the conv2d_zeros bias incl. its
-//     edge-indicator taps; N = 3 vertical taps x 4 outputs.  fp16 (hi, lo) keeps 22 mantissa bits of every
-//     activation and weight; the dropped lo x lo term is 2^-22 relative.
-//   * the worker reads its 12 accumulator columns back one step later (tcgen05.ld) and adds the three vertical taps
+//   * FOUR warps form a group (their 4 x 32 lanes are the 128 TMEM lanes an M = 128 MMA writes); a CTA holds four
+//     groups = 16 resident patches.  For image row r every lane writes its pixel's h2 activation, split into fp16
+//     (hi, lo) halves, into the group's A tile in shared memory: once as its own pixel's centre tap and once each as the
+//     left / right neighbour's tap, so the three horizontal taps of a pixel sit side by side in K and the SAME padding
+//     is simply never written.
+//   * D[128 x 16] = A[128 x 48] . B[48 x 16]  runs as three tcgen05.mma (kind::f16, fp32 accumulate in TMEM).
+//     K = 3 taps x (hi, lo) x 4 channels against W_hi, plus the hi halves again against W_lo, plus three one-hot
+//     "column class" slots that carry the conv2d_zeros bias incl. its edge-indicator taps; N = 3 vertical taps x 4
+//     outputs.  fp16 (hi, lo) keeps 22 mantissa bits of every activation and weight; the dropped lo x lo term is
+//     2^-22 relative.  The four warps of a group take turns at issuing (no issuer warp: a fifth warp on a scheduler
+//     would cap everybody at 102 registers): the warp whose turn it is waits on the row's "A tile written" mbarrier.
+//   * every warp reads its 12 accumulator columns back two steps later (tcgen05.ld) and adds the three vertical taps
 //     into the two pending output rows it carries (8 FADD per pixel instead of 72 FFMA2 + 36 LDCU + 8 FADD).
 //
-// A tiles and accumulators are double-buffered per group, so the MMAs of row r run while the workers are busy with
-// row r + 1; per row a worker warp pays one mbarrier arrive and one (normally already satisfied) mbarrier wait.
-// TMEM: columns 0..383 hold the 12 resident patches (3 groups), columns 384..479 the 3 x 2 accumulator tiles.
+// A tiles and accumulators are double-buffered per group, so the MMAs of row r run while the warps are busy with rows
+// r + 1 and r + 2.  Tensor memory: columns 0..383 hold the resident patches of groups 0..2, columns 384..511 the 4 x 2
+// accumulator tiles; the patches of group 3 live in shared memory (ZDual).
 //
 // Reference semantics: identical to nf_kernels.cu / nf_coupling.cuh (layers.py:117-130, 333-375, 452-498, 555-583,
 // 651-674; noise_flow_model.py:394-480).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 #include "nf_params.h"
 #include "nf_kernels.h"
 #include "nf_rng.cuh"
@@ -37,21 +38,22 @@
 namespace nf {
 namespace hyb {
 
-constexpr int GROUPS = 3;                    // groups of four worker warps per CTA
+constexpr int GROUPS = 4;                    // groups of four worker warps per CTA
 constexpr int WORKERS = GROUPS * 4;          // resident patches per CTA
-constexpr int WARPS = WORKERS + GROUPS;      // + one MMA issuer warp per group
-constexpr int THREADS = WARPS * 32;
+constexpr int THREADS = WORKERS * 32;
+constexpr int TMEM_GROUPS = 3;               // groups whose patches live in tensor memory; the last group's live in shared memory
 constexpr int A_CHUNKS = 6;                  // K = 48 = 6 chunks of 8 fp16 (16 bytes)
 constexpr int A_STAGE = A_CHUNKS * 128;      // uint4 per A stage
-constexpr uint32_t D_COL0 = 128u * WORKERS / 4u;   // first accumulator column (384)
+constexpr uint32_t D_COL0 = 128u * TMEM_GROUPS;   // first accumulator column (384): 4 groups x 2 stages x 16 columns follow
 
 struct __align__(128) Smem {
     uint4 a[GROUPS + 1][2][A_CHUNKS][128];    // A tiles, K-major, no swizzle: [k chunk][row], LBO = 2048 B, SBO = 128 B;
                                               // tile [GROUPS] is a write-only dump for the taps that fall outside the image
     uint4 b[NF_MAX_COUPLINGS][A_CHUNKS][16];  // B tiles per coupling: [k chunk][n], LBO = 256 B, SBO = 128 B
+    uint4 z[4][NF_PIXELS];                    // resident patches of the last group: z[row * 32 + lane]
     float2 xr[WORKERS][2][34];                // x0 row ring per worker warp ([0] and [33] = zero halo)
-    uint64_t afull[GROUPS][2];                // A tile of row r written by the group's four warps
     uint64_t dfull[GROUPS][2];                // accumulators of row r complete (tcgen05.commit)
+    uint64_t afull[GROUPS][2];                // A tile of row r written by the group's four warps
     uint32_t tmem_base;
     uint32_t pad_[3];
 };
@@ -84,10 +86,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mbar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" :: "n"(WORKERS * 32) : "memory"); }
 __device__ __forceinline__ void tmem_issue_ld4(uint32_t taddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
 }
@@ -104,6 +110,32 @@ __device__ __forceinline__ void tmem_wait_ld20(uint32_t (&a)[8], uint32_t (&b)[1
                    "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
                    "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]) :: "memory");
 }
+
+// Where a worker keeps its resident patch z[32 rows][32 lanes] (float4 per pixel; lane = image column): groups 0..2 in
+// TENSOR MEMORY (384 columns, as in nf_kernels.cu), the last group in shared memory -- the accumulator tiles of the four
+// groups take the remaining 128 TMEM columns.  `sm` is warp-uniform.  Same interface as ZStore (nf_chain_dev.cuh).
+struct ZDual {
+    uint32_t taddr;   // (first TMEM lane of this warp << 16) | first column of this warp's patch
+    uint4* zsm;       // this lane's column of the shared-memory patch: zsm[r * 32]
+    bool sm;
+    __device__ __forceinline__ void issue_ld(int r, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) const {
+        if (sm) { const uint4 v = zsm[r * 32]; a = v.x; b = v.y; c = v.z; d = v.w; }
+        else tmem_issue_ld4(taddr + (uint32_t)(r * 4), a, b, c, d);
+    }
+    __device__ __forceinline__ float4 load(int r) const {
+        uint32_t a, b, c, d;
+        issue_ld(r, a, b, c, d);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d) :: "memory");
+        return make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+    }
+    __device__ __forceinline__ void store(int r, float4 z) const {
+        if (sm) zsm[r * 32] = make_uint4(__float_as_uint(z.x), __float_as_uint(z.y), __float_as_uint(z.z), __float_as_uint(z.w));
+        else asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                          :: "r"(taddr + (uint32_t)(r * 4)), "r"(__float_as_uint(z.x)), "r"(__float_as_uint(z.y)),
+                             "r"(__float_as_uint(z.z)), "r"(__float_as_uint(z.w)) : "memory");
+    }
+    __device__ __forceinline__ void commit() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
 
 // ReLU + fp16 (hi, lo) split of two floats, first value in the low half:  hi = rz(max(v, 0)) -- truncation keeps
 // hi <= v, so the remainder of a positive v is never negative -- and lo = rn(max(v - hi, 0)) (a negative v has
@@ -148,9 +180,12 @@ struct Worker {          // per worker-warp constants
     uint4* a_right;      // same entry of the pixel to my right (lane 31: of the dump tile -- the SAME padding stays zero)
     uint4* a_left;       // ... to my left (lane 0: dump tile)
     float2 (*xr)[34];    // this warp's x0 row ring
-    uint32_t afull;      // shared address of S.afull[group][0] (stage 1: + 8)
-    uint32_t dfull;      // shared address of S.dfull[group][0]
-    uint32_t d_taddr;    // TMEM address of this warp's quarter of the group's accumulator stage 0 (stage 1: + 16)
+    uint32_t a_tile;     // shared address of S.a[group][0] (stage 1: + A_STAGE * 16)            } warp-uniform:
+    uint32_t afull;      // shared address of S.afull[group][0] (stage 1: + 8)                   } operands of the
+    uint32_t dfull;      // shared address of S.dfull[group][0] (stage 1: + 8)                   } MMAs the group's
+    uint32_t d_mma;      // TMEM address of the group's accumulator stage 0 (stage 1: + 16)      } last warp issues
+    uint32_t d_taddr;    // ... of this warp's quarter of it
+    int quarter;         // this warp's index in its group: it issues the MMAs of the rows r with (r & 3) == quarter
 };
 
 // One row step of a coupling pass.  Schedule of coupling_step in nf_coupling.cuh with stage C one step later (t = 0..36):
@@ -160,8 +195,8 @@ struct Worker {          // per worker-warp constants
 //   stage C (j = t-4): accumulators of h2 row j (MMAs triggered TWO steps ago, so the wait below never stalls) -> the
 //                      three vertical taps go into the pending conv-3 rows; the finished row q = j-1 = t-5 gets the affine
 //                      update + log-det
-template <bool INV, bool GUARDED, int EXP, class CP>
-__device__ __forceinline__ void hyb_step(const CP& P, const Worker& wk, const ZStore& zs, const int lane, const int t,
+template <bool INV, bool GUARDED, class CP>
+__device__ __forceinline__ void hyb_step(const CP& P, const Worker& wk, const ZDual& zs, const uint32_t b_addr, const int lane, const int t,
                                          const bool has_mix, Acc4& b_old, Acc4& b_mid, float (&c_old)[4], float (&c_mid)[4],
                                          float& ldj, const float2 (&am)[4][2], const float2 (&w2c)[4][2]) {
     const float2 zero2 = make_float2(0.f, 0.f);
@@ -177,12 +212,12 @@ __device__ __forceinline__ void hyb_step(const CP& P, const Worker& wk, const ZS
     uint32_t lz[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, ld[12] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     if (c_fma) {
         const int j = t - 4;
-        if (!(EXP & 1)) mbar_wait(wk.dfull + (uint32_t)(j & 1) * 8u, (uint32_t)(j >> 1) & 1u);
+        mbar_wait(wk.dfull + (uint32_t)(j & 1) * 8u, (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
         tmem_issue_ld12(wk.d_taddr + (uint32_t)(j & 1) * 16u, ld);
     }
-    if (do_a) tmem_issue_ld4(zs.taddr + (uint32_t)(t * 4), lz[0], lz[1], lz[2], lz[3]);
-    if (c_emit) tmem_issue_ld4(zs.taddr + (uint32_t)((t - 5) * 4), lz[4], lz[5], lz[6], lz[7]);
+    if (do_a) zs.issue_ld(t, lz[0], lz[1], lz[2], lz[3]);
+    if (c_emit) zs.issue_ld(t - 5, lz[4], lz[5], lz[6], lz[7]);
     // ---------------- stage B
     Acc4 fin = b_old;
     if (b_fma) {
@@ -242,10 +277,28 @@ __device__ __forceinline__ void hyb_step(const CP& P, const Worker& wk, const ZS
     // arrive below: the MMAs that arrive releases overwrite the accumulator stage this step has just read.
     tmem_wait_ld20(lz, ld);
     if (b_emit) {
-        if (!(EXP & 2)) fence_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        tc_fence_before();       // orders the tcgen05.ld above before the MMAs of the thread the barrier releases
+        fence_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        tc_fence_before();       // orders the tcgen05.ld above before the MMAs of whichever thread issues them
         __syncwarp();
-        if (lane == 0) mbar_arrive(wk.afull + (uint32_t)((t - 2) & 1) * 8u);
+        // The four warps of a group take turns at issuing: the warp whose turn it is waits until all four have handed in
+        // the row's A tile, then runs K = 48 as three M128 N16 K16 MMAs into the row's accumulator stage and commits them
+        // to its "accumulators complete" barrier.  No issuer warp (a fifth warp on a scheduler would cap the workers at 102
+        // registers), no polling.
+        const int r = t - 2;
+        const uint32_t st = (uint32_t)r & 1u;
+        if (lane == 0) mbar_arrive(wk.afull + st * 8u);
+        if ((r & 3) == wk.quarter) {
+            mbar_wait(wk.afull + st * 8u, ((uint32_t)r >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t a_addr = wk.a_tile + st * (uint32_t)(A_STAGE * 16), d = wk.d_mma + st * 16u;
+            if (elect_one()) {
+                mma_ss(d, make_desc(a_addr, 2048u, 128u), make_desc(b_addr, 256u, 128u), 0u);
+                mma_ss(d, make_desc(a_addr + 4096u, 2048u, 128u), make_desc(b_addr + 512u, 256u, 128u), 1u);
+                mma_ss(d, make_desc(a_addr + 8192u, 2048u, 128u), make_desc(b_addr + 1024u, 256u, 128u), 1u);
+                mma_commit(wk.dfull + st * 8u);
+            }
+            __syncwarp();
+        }
     }
     // ---------------- stage A
     if (do_a) {
@@ -295,8 +348,8 @@ __device__ __forceinline__ void hyb_step(const CP& P, const Worker& wk, const ZS
     __syncwarp();
 }
 
-template <bool INV, int EXP, class CP>
-__device__ __forceinline__ void hyb_pass(const CP& P, const Worker& wk, const ZStore& zs, const int lane, float& ldj) {
+template <bool INV, class CP>
+__device__ __forceinline__ void hyb_pass(const CP& P, const Worker& wk, const ZDual& zs, const uint32_t b_addr, const int lane, float& ldj) {
     const bool has_mix = P.has_mix != 0;
     const float rz = wk.xr[0][0].x;   // a 0.0f only known at run time: keeps the values below per-thread (see load_mix_regs)
     float2 am[4][2];
@@ -316,70 +369,29 @@ __device__ __forceinline__ void hyb_pass(const CP& P, const Worker& wk, const ZS
     }
 #pragma unroll 1
     for (int t = 0; t < 37; ++t) {
-        if (t >= 6 && t < 32) hyb_step<INV, false, EXP>(P, wk, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, ldj, am, w2c);
-        else                  hyb_step<INV, true, EXP>(P, wk, zs, lane, t, has_mix, b_old, b_mid, c_old, c_mid, ldj, am, w2c);
+        if (t >= 6 && t < 32) hyb_step<INV, false>(P, wk, zs, b_addr, lane, t, has_mix, b_old, b_mid, c_old, c_mid, ldj, am, w2c);
+        else                  hyb_step<INV, true>(P, wk, zs, b_addr, lane, t, has_mix, b_old, b_mid, c_old, c_mid, ldj, am, w2c);
     }
 }
 
 #define NFH_FAST_SLOTS 8
-template <bool INV, int EXP>
-__device__ __forceinline__ void hyb_dispatch(const NfModelParams& mp, const Worker& wk, const ZStore& zs, int lane, float& ldj, int slot) {
+template <bool INV>
+__device__ __forceinline__ void hyb_dispatch(const NfModelParams& mp, const Worker& wk, const ZDual& zs, const uint32_t b0, int lane, float& ldj, int slot) {
     switch (slot) {
-#define NFH_CASE(K) case K: hyb_pass<INV, EXP>(mp.cp[K], wk, zs, lane, ldj); break;
+#define NFH_CASE(K) case K: hyb_pass<INV>(mp.cp[K], wk, zs, b0 + K * (uint32_t)(A_CHUNKS * 256), lane, ldj); break;
         NFH_CASE(0) NFH_CASE(1) NFH_CASE(2) NFH_CASE(3) NFH_CASE(4) NFH_CASE(5) NFH_CASE(6) NFH_CASE(7)
 #undef NFH_CASE
-        default: hyb_pass<INV, EXP>(mp.cp[slot], wk, zs, lane, ldj); break;   // run-time slot: per-thread LDC weight fetches
+        default: hyb_pass<INV>(mp.cp[slot], wk, zs, b0 + (uint32_t)slot * (uint32_t)(A_CHUNKS * 256), lane, ldj); break;   // run-time slot: per-thread LDC weight fetches
     }
 }
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t p;
-    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(p));
-    return p != 0;
-}
-
-// The MMA issuer warp of one group: follows the workers' layer program; per coupling and image row it waits for the group's
-// A tile, runs K = 48 as three MMAs into the row's accumulator stage and commits to the row's "accumulators complete"
-// barrier.  One issuer per group keeps the groups independent of each other (a shared issuer serving them in a fixed order
-// row-lock-steps all twelve worker warps; one that polls them burns issue slots: 10.3 / 9.6 M patches/s).  The whole warp
-// runs the loop converged -- every operand of the MMAs is warp-uniform by construction and goes straight to uniform
-// registers -- and one elected lane issues.
 template <bool INV>
-__device__ __forceinline__ void issuer_loop(const NfModelParams& mp, const NfChainArgs& a, Smem& S, const int g) {
-    const uint32_t d_base = S.tmem_base + D_COL0 + (uint32_t)g * 32u;
-    const uint32_t a_base = smem_u32(&S.a[g][0][0][0]);
-    const uint32_t afull = smem_u32(&S.afull[g][0]), dfull = smem_u32(&S.dfull[g][0]);
-    const long long stride = (long long)gridDim.x * WORKERS;
-    for (long long base = (long long)blockIdx.x * WORKERS; base < a.n; base += stride) {
-        const int l0 = INV ? a.first_layer : a.last_layer - 1, l1 = INV ? a.last_layer : a.first_layer - 1, dl = INV ? 1 : -1;
-        for (int l = l0; l != l1; l += dl) {
-            if (mp.op[l] != NF_KOP_COUPLING) continue;
-            const uint32_t b_addr = smem_u32(&S.b[mp.slot[l]][0][0]);
-            const uint64_t bd0 = make_desc(b_addr, 256u, 128u), bd1 = make_desc(b_addr + 512u, 256u, 128u), bd2 = make_desc(b_addr + 1024u, 256u, 128u);
-#pragma unroll 1
-            for (int r = 0; r < 32; ++r) {
-                const uint32_t s = (uint32_t)r & 1u;
-                mbar_wait(afull + s * 8u, ((uint32_t)r >> 1) & 1u);
-                tc_fence_after();
-                const uint32_t a_addr = a_base + s * (uint32_t)(A_STAGE * 16);
-                if (elect_one()) {
-                    mma_ss(d_base + s * 16u, make_desc(a_addr, 2048u, 128u), bd0, 0u);
-                    mma_ss(d_base + s * 16u, make_desc(a_addr + 4096u, 2048u, 128u), bd1, 1u);
-                    mma_ss(d_base + s * 16u, make_desc(a_addr + 8192u, 2048u, 128u), bd2, 1u);
-                    mma_commit(dfull + s * 8u);
-                }
-                __syncwarp();
-            }
-        }
-    }
-}
-
-template <bool INV, int EXP>
 __global__ void __launch_bounds__(THREADS, 1)
 nf_chain_hyb_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too
 
     // ---- CTA prologue: B tiles of every coupling, A tiles zeroed + their constant one-hot chunk, barriers, tensor memory
     {
@@ -402,12 +414,9 @@ nf_chain_hyb_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs 
             a4[e] = v;
         }
         for (int e = tid; e < WORKERS * 2 * 34; e += THREADS) (&S.xr[0][0][0])[e] = make_float2(0.f, 0.f);
-        if (tid == 0) {
-            for (int g = 0; g < GROUPS; ++g)
-                for (int s = 0; s < 2; ++s) {
-                    mbar_init(smem_u32(&S.afull[g][s]), 4);
-                    mbar_init(smem_u32(&S.dfull[g][s]), 1);
-                }
+        if (tid < GROUPS * 2) {
+            mbar_init(smem_u32(&S.dfull[0][0] + tid), 1);
+            mbar_init(smem_u32(&S.afull[0][0] + tid), 4);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -421,91 +430,91 @@ nf_chain_hyb_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs 
         tc_fence_after();
     }
 
-    if (warp >= WORKERS) {
-        issuer_loop<INV>(mp, a, S, warp - WORKERS);
-    } else {
-        const int g = warp >> 2, q = warp & 3;
-        const ZStore zs = {S.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 128)};
-        Worker wk;
-        wk.a_row = &S.a[g][0][0][q * 32 + lane];
-        wk.a_right = lane < 31 ? wk.a_row + 1 : &S.a[GROUPS][0][0][q * 32 + lane];
-        wk.a_left = lane > 0 ? wk.a_row - 1 : &S.a[GROUPS][0][0][q * 32 + lane];
-        wk.xr = S.xr[warp];
-        wk.afull = smem_u32(&S.afull[g][0]);
-        wk.dfull = smem_u32(&S.dfull[g][0]);
-        wk.d_taddr = S.tmem_base + ((uint32_t)(q * 32) << 16) + D_COL0 + (uint32_t)g * 32u;
+    const int g = warp >> 2, q = warp & 3;
+    const ZDual zs = {S.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g < TMEM_GROUPS ? g : 0) * 128), &S.z[q][lane], g >= TMEM_GROUPS};
+    Worker wk;
+    wk.a_row = &S.a[g][0][0][q * 32 + lane];
+    wk.a_right = lane < 31 ? wk.a_row + 1 : &S.a[GROUPS][0][0][q * 32 + lane];
+    wk.a_left = lane > 0 ? wk.a_row - 1 : &S.a[GROUPS][0][0][q * 32 + lane];
+    wk.xr = S.xr[warp];
+    wk.a_tile = smem_u32(&S.a[g][0][0][0]);
+    wk.afull = smem_u32(&S.afull[g][0]);
+    wk.quarter = q;
+    wk.dfull = smem_u32(&S.dfull[g][0]);
+    wk.d_mma = S.tmem_base + D_COL0 + (uint32_t)g * 32u;
+    wk.d_taddr = wk.d_mma + ((uint32_t)(q * 32) << 16);
+    const uint32_t b0 = smem_u32(&S.b[0][0][0]);
 
-        // CTA-uniform patch loop (see nf_chain_kernel): trailing warps without a patch recompute the last one
-        const long long stride = (long long)gridDim.x * WORKERS;
-        for (long long base = (long long)blockIdx.x * WORKERS; base < a.n; base += stride) {
-            const bool active = base + warp < a.n;
-            const long long p = active ? base + warp : a.n - 1;
-            int row = a.rows ? a.rows[p] : a.default_row;
-            row = min(max(row, 0), NF_MAX_ROWS - 1);
-            if (a.in) {
-                const float4* src = reinterpret_cast<const float4*>(a.in) + p * NF_PIXELS;
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    float4 v = __ldcs(src + r * 32 + lane);
-                    if (!INV) { v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp; }   // noise_flow_model.py:501
-                    zs.store(r, v);
-                }
-            } else {
-#pragma unroll 2
-                for (int r = 0; r < 32; ++r) {
-                    float4 v = philox_normal4(a.seed, a.offset, a.patch_base + (unsigned long long)p, (unsigned int)(r * 32 + lane));
-                    v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp;
-                    zs.store(r, v);
-                }
-            }
-            zs.commit();
-            __syncwarp();
-
-            float ldj = 0.f;
-            const int l0 = INV ? a.first_layer : a.last_layer - 1, l1 = INV ? a.last_layer : a.first_layer - 1, dl = INV ? 1 : -1;
-            for (int l = l0; l != l1; l += dl) {
-                const int op = mp.op[l], slot = mp.slot[l];
-                switch (op) {
-                    case NF_KOP_COUPLING: hyb_dispatch<INV, EXP>(mp, wk, zs, lane, ldj, slot); break;
-                    case NF_KOP_MIX: mix_pass<INV>(mp.mix[slot], zs); break;
-                    case NF_KOP_SDN:
-                        sdn_pass<INV>(reinterpret_cast<const float4*>(a.y) + p * NF_PIXELS, mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], zs, lane, ldj);
-                        break;
-                    case NF_KOP_GAIN:
-                        gain_pass<INV>(mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], mp.sc[slot].t[row][2], zs, lane, ldj);
-                        break;
-                    default: break;
-                }
-                worker_barrier();   // layer boundary: keeps the workers in the same loop body (instruction cache)
-            }
-
-            // ---- epilogue: store the patch, reduce log-det / prior / latent statistics (same fixed tree as nf_chain_kernel)
-            zs.commit();
-            float s1 = 0.f, s2 = 0.f;
-            float4* dst = (a.out && active) ? reinterpret_cast<float4*>(a.out) + p * NF_PIXELS : nullptr;
+    // CTA-uniform patch loop (see nf_chain_kernel): trailing warps without a patch recompute the last one
+    const long long stride = (long long)gridDim.x * WORKERS;
+    for (long long base = (long long)blockIdx.x * WORKERS; base < a.n; base += stride) {
+        const bool active = base + warp < a.n;
+        const long long p = active ? base + warp : a.n - 1;
+        int row = a.rows ? a.rows[p] : a.default_row;
+        row = min(max(row, 0), NF_MAX_ROWS - 1);
+        if (a.in) {
+            const float4* src = reinterpret_cast<const float4*>(a.in) + p * NF_PIXELS;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-                const float4 z = zs.load(r);
-                if (dst) __stcs(dst + r * 32 + lane, z);
-                s1 += (z.x + z.y) + (z.z + z.w);
-                s2 = fmaf(z.x, z.x, fmaf(z.y, z.y, fmaf(z.z, z.z, fmaf(z.w, z.w, s2))));
+                float4 v = __ldcs(src + r * 32 + lane);
+                if (!INV) { v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp; }   // noise_flow_model.py:501
+                zs.store(r, v);
             }
-            ldj = warp_sum(ldj);
-            if (a.nll || a.sdz) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
-            if (lane == 0 && active) {
-                const float logdet = ldj + (INV ? a.ldj_const : -a.ldj_const) + (a.logdet_in ? a.logdet_in[p] : 0.f);
-                if (a.logdet) a.logdet[p] = logdet;
-                if (a.nll) {   // -(logdet + sum -0.5 (log 2pi + z^2))       noise_flow_model.py:474-475,537-539
-                    const float logp = -0.5f * (NF_DIMS * 1.8378770664093453f + s2);
-                    a.nll[p] = -(logdet + logp);
-                }
-                if (a.sdz) {   // population std-dev of z                     noise_flow_model.py:477-478
-                    const float mean = s1 * (1.f / NF_DIMS);
-                    a.sdz[p] = sqrtf(fmaxf(s2 * (1.f / NF_DIMS) - mean * mean, 0.f));
-                }
+        } else {
+#pragma unroll 2
+            for (int r = 0; r < 32; ++r) {
+                float4 v = philox_normal4(a.seed, a.offset, a.patch_base + (unsigned long long)p, (unsigned int)(r * 32 + lane));
+                v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp;
+                zs.store(r, v);
             }
-            __syncwarp();
         }
+        zs.commit();
+        __syncwarp();
+
+        float ldj = 0.f;
+        const int l0 = INV ? a.first_layer : a.last_layer - 1, l1 = INV ? a.last_layer : a.first_layer - 1, dl = INV ? 1 : -1;
+        for (int l = l0; l != l1; l += dl) {
+            const int op = mp.op[l], slot = mp.slot[l];
+            switch (op) {
+                case NF_KOP_COUPLING: hyb_dispatch<INV>(mp, wk, zs, b0, lane, ldj, slot); break;
+                case NF_KOP_MIX: mix_pass<INV>(mp.mix[slot], zs); break;
+                case NF_KOP_SDN:
+                    sdn_pass<INV>(reinterpret_cast<const float4*>(a.y) + p * NF_PIXELS, mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], zs, lane, ldj);
+                    break;
+                case NF_KOP_GAIN:
+                    gain_pass<INV>(mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], mp.sc[slot].t[row][2], zs, lane, ldj);
+                    break;
+                default: break;
+            }
+            __syncthreads();   // layer boundary: keeps the warps in the same loop body (instruction cache)
+        }
+
+        // ---- epilogue: store the patch, reduce log-det / prior / latent statistics (same fixed tree as nf_chain_kernel)
+        zs.commit();
+        float s1 = 0.f, s2 = 0.f;
+        float4* dst = (a.out && active) ? reinterpret_cast<float4*>(a.out) + p * NF_PIXELS : nullptr;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const float4 z = zs.load(r);
+            if (dst) __stcs(dst + r * 32 + lane, z);
+            s1 += (z.x + z.y) + (z.z + z.w);
+            s2 = fmaf(z.x, z.x, fmaf(z.y, z.y, fmaf(z.z, z.z, fmaf(z.w, z.w, s2))));
+        }
+        ldj = warp_sum(ldj);
+        if (a.nll || a.sdz) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
+        if (lane == 0 && active) {
+            const float logdet = ldj + (INV ? a.ldj_const : -a.ldj_const) + (a.logdet_in ? a.logdet_in[p] : 0.f);
+            if (a.logdet) a.logdet[p] = logdet;
+            if (a.nll) {   // -(logdet + sum -0.5 (log 2pi + z^2))       noise_flow_model.py:474-475,537-539
+                const float logp = -0.5f * (NF_DIMS * 1.8378770664093453f + s2);
+                a.nll[p] = -(logdet + logp);
+            }
+            if (a.sdz) {   // population std-dev of z                     noise_flow_model.py:477-478
+                const float mean = s1 * (1.f / NF_DIMS);
+                a.sdz[p] = sqrtf(fmaxf(s2 * (1.f / NF_DIMS) - mean * mean, 0.f));
+            }
+        }
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
@@ -521,30 +530,24 @@ bool hybrid_program_supported(const NfModelParams& mp, const NfChainArgs& a) {
     return false;
 }
 
-template <bool INV, int EXP>
+template <bool INV>
 static cudaError_t launch_hyb(const NfModelParams& mp, const NfChainArgs& args, int num_sms, cudaStream_t stream) {
     static bool attr_done[NF_MAX_DEVICES] = {};   // per device
     const int dev = device_slot();
     if (!attr_done[dev]) {
-        const cudaError_t e = cudaFuncSetAttribute(hyb::nf_chain_hyb_kernel<INV, EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(hyb::Smem));
+        const cudaError_t e = cudaFuncSetAttribute(hyb::nf_chain_hyb_kernel<INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(hyb::Smem));
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
     long long ctas = (args.n + hyb::WORKERS - 1) / hyb::WORKERS;
     if (ctas > num_sms) ctas = num_sms;
-    hyb::nf_chain_hyb_kernel<INV, EXP><<<(unsigned)ctas, hyb::THREADS, sizeof(hyb::Smem), stream>>>(mp, args);
+    hyb::nf_chain_hyb_kernel<INV><<<(unsigned)ctas, hyb::THREADS, sizeof(hyb::Smem), stream>>>(mp, args);
     return cudaGetLastError();
 }
 
 cudaError_t launch_chain_hybrid(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, cudaStream_t stream) {
     if (args.n <= 0) return cudaSuccess;
-#ifdef NFH_EXPERIMENTS
-    static const int exp = getenv("NF_HYB_EXP") ? atoi(getenv("NF_HYB_EXP")) : 0;   // timing experiments (results may be wrong)
-    if (inverse && exp == 1) return launch_hyb<true, 1>(mp, args, num_sms, stream);
-    if (inverse && exp == 2) return launch_hyb<true, 2>(mp, args, num_sms, stream);
-    if (inverse && exp == 3) return launch_hyb<true, 3>(mp, args, num_sms, stream);
-#endif
-    return inverse ? launch_hyb<true, 0>(mp, args, num_sms, stream) : launch_hyb<false, 0>(mp, args, num_sms, stream);
+    return inverse ? launch_hyb<true>(mp, args, num_sms, stream) : launch_hyb<false>(mp, args, num_sms, stream);
 }
 
 }  // namespace nf

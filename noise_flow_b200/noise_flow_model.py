@@ -251,13 +251,14 @@ class NoiseFlow(object):
         _lib.check(self._engine.lib.nf_model_set_launch(self._engine.handle, warps_per_cta, num_ctas), "nf_model_set_launch")
 
     def set_tensor_cores(self, enable=True):
-        """Width 4: ``"hybrid"`` (or 2) runs conv-3 of every coupling net on the tensor cores (tcgen05, fp16 hi/lo split
-        operands, csrc/nf_hybrid.cu) and everything else as the fp32 kernel does; ``True`` (1) selects the older
-        experimental kernel with both 3x3 convolutions as bf16 hi/lo implicit GEMMs; ``False`` the all-fp32 kernel.
+        """Width 4: ``"hybrid"`` (2) runs conv-3 of every coupling net on the tensor cores (tcgen05, fp16 hi/lo split
+        operands, csrc/nf_hybrid.cu) in both directions; ``"auto"`` (3) does so for sampling / forward only (where it is
+        faster); ``False`` (0, the default) selects the all-fp32 kernel everywhere; ``True`` (1) the older experimental kernel with both 3x3
+        convolutions as bf16 hi/lo implicit GEMMs.
         Widths 32 / 64 / 128: the tensor-core kernel is the default; ``False`` selects the CUDA-core kernel (width 32 only)."""
         self.build()
-        mode = 2 if enable in ("hybrid", 2) else (1 if enable else 0)
-        _lib.check(self._engine.lib.nf_model_set_tensor_cores(self._engine.handle, mode), "nf_model_set_tensor_cores")
+        mode = {"hybrid": 2, "auto": 3}.get(enable, enable) if isinstance(enable, (str, int)) and not isinstance(enable, bool) else (1 if enable else 0)
+        _lib.check(self._engine.lib.nf_model_set_tensor_cores(self._engine.handle, int(mode)), "nf_model_set_tensor_cores")
         return self
 
     def set_batch_stats_fused(self, enable: bool = True):

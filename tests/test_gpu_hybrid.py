@@ -85,3 +85,53 @@ def test_hybrid_is_deterministic(shipped):
     c, _ = nf._loss(x, y, iso=[100.0], cam=[2.0])
     assert torch.equal(a, c)
     assert torch.equal(a[:37], b)   # a patch's result does not depend on the batch around it
+
+
+def test_hybrid_stress_model_accuracy():
+    """A model with O(1) random coupling-net weights (the stress case of test_gpu_parity.py): activations of a few hundred
+    and log-scales up to 0.8 per coupling amplify conv-3's 22-bit operands (fp16 hi + lo) through the chain.  Stated bound:
+    5e-5 relative to the largest value, for z and for a sampled patch; the all-fp32 kernel is printed next to it."""
+    from noise_flow_b200 import NoiseFlow, make_hps
+    hps = make_hps(arch="sdn|unc|gain|unc", flow_permutation=0)
+    nf0 = NoiseFlow([32, 32, 4], False, copy.copy(hps), device="cuda:0", seed=4, first_call="inverse")
+    rng = np.random.RandomState(5)
+    vs = {k: v.copy() for k, v in nf0.variables.items()}
+    for k in vs:
+        if k.endswith("/l_1/W") or k.endswith("/l_2/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.5).astype(np.float32)
+        elif k.endswith("/l_last/W"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.1).astype(np.float32)
+        elif k.endswith("/b") or k.endswith("/logs") or k.endswith("/mean"):
+            vs[k] = (rng.randn(*vs[k].shape) * 0.2).astype(np.float32)
+        elif k.endswith("/var"):
+            vs[k] = (rng.rand(*vs[k].shape) + 0.05).astype(np.float32)
+        elif "rescaling_scale" in k:
+            vs[k] = np.float32(0.3 + 0.5 * rng.rand())
+    orc = make_oracle(hps, vs)
+    x, y = synth_batch(6, cam=2, iso=800, seed=19)
+    x = (x * 5).astype(np.float32)
+    kw = dict(nlf0=[0.003], nlf1=[0.00002], iso=[800.0], cam=[3.0])
+    eps = rng.randn(6, 32, 32, 4).astype(np.float32)
+    nll_o, _ = orc._loss(x, y, **kw)
+    zo = orc.last_z.numpy()
+    xo = orc.sample(eps, 0.8, y, **kw).numpy()
+    err = {}
+    for mode in ("hybrid", False):
+        nf = NoiseFlow([32, 32, 4], False, copy.copy(hps), variables=vs, device="cuda:0", first_call="inverse")
+        nf.set_tensor_cores(mode)
+        nll, _, z = nf._loss(x, y, return_z=True, **kw)
+        xs = nf.sample(y, 0.8, y, eps=eps, **kw).cpu().numpy()
+        err[mode] = (np.abs(nll.cpu().numpy() - nll_o.numpy()).max() / 4096, np.abs(z.cpu().numpy() - zo).max() / (1 + np.abs(zo).max()),
+                     np.abs(xs - xo).max() / (1 + np.abs(xo).max()))
+    print("stress model, (|dNLL| nats/dim, rel |dz|, rel |dx|): hybrid %.2e %.2e %.2e   all-fp32 %.2e %.2e %.2e" % (err["hybrid"] + err[False]))
+    assert err["hybrid"][0] < 2e-5 and err["hybrid"][1] < 5e-5 and err["hybrid"][2] < 5e-5
+
+
+def test_auto_mode_routes_sampling_to_the_hybrid_kernel(shipped):
+    hps, ck = shipped
+    x, y = synth_batch(30, seed=183)
+    eps = np.random.RandomState(184).randn(30, 32, 32, 4).astype(np.float32)
+    auto, hyb, f32 = _nf(hps, ck, "auto"), _nf(hps, ck, "hybrid"), _nf(hps, ck, False)
+    kw = dict(iso=[100.0], cam=[2.0])
+    assert torch.equal(auto.sample(y, 0.6, y, eps=eps, **kw), hyb.sample(y, 0.6, y, eps=eps, **kw))
+    assert torch.equal(auto._loss(x, y, **kw)[0], f32._loss(x, y, **kw)[0])
