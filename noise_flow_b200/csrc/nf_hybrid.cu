@@ -436,8 +436,8 @@ nf_chain_hyb_kernel(const __grid_constant__ NfModelParams mp, const NfChainArgs 
     const ZDual zs = {S.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g < TMEM_GROUPS ? g : 0) * 128), &S.z[q][lane], g >= TMEM_GROUPS};
     Worker wk;
     wk.a_row = &S.a[g][0][0][q * 32 + lane];
-    wk.a_right = lane < 31 ? wk.a_row + 1 : &S.a[GROUPS][0][0][q * 32 + lane];
-    wk.a_left = lane > 0 ? wk.a_row - 1 : &S.a[GROUPS][0][0][q * 32 + lane];
+    wk.a_right = lane < 31 ? wk.a_row + 1 : &S.a[GROUPS][0][0][2 * warp];       // every warp has its own two dump rows
+    wk.a_left = lane > 0 ? wk.a_row - 1 : &S.a[GROUPS][0][0][2 * warp + 1];
     wk.xr = S.xr[warp];
     wk.a_tile = smem_u32(&S.a[g][0][0][0]);
     wk.afull = smem_u32(&S.afull[g][0]);

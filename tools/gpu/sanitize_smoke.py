@@ -30,6 +30,15 @@ if CHAIN:
     nll_b, _ = nf._loss(x, y, iso=[100.0], cam=[2.0], is_training=True)            # batch-statistics probes, layer by layer
     nf.set_batch_stats_fused(True)
     zz, ld = nf.run_layers(0, 3, "inverse", x, yy=y, iso=[100.0], cam=[2.0])
+    if os.environ.get("NF_SANITIZE_HYBRID", "1") == "1":   # round 5: hybrid chain kernel (conv-3 on tcgen05), both directions
+        nll, _ = nf._loss(x, y, iso=[100.0], cam=[2.0])   # (the batch-statistics call above moved the BatchNorm statistics)
+        nf.set_tensor_cores("hybrid")
+        nll_h, _, z_h = nf._loss(x, y, iso=[100.0], cam=[2.0], return_z=True)
+        xs_h = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], seed=3, offset=0)
+        xr_h = nf.forward(z_h, None, yy=y, iso=[100.0], cam=[2.0])
+        print("hybrid kernel: |nll - fp32 kernel| %.2e nats/dim, round trip %.2e" % (
+            float((nll_h - nll).abs().max()) / 4096, float(np.abs(xr_h.cpu().numpy() - x).max())))
+        nf.set_tensor_cores(False)
 # batch-statistics chain of a small batch: one cooperative kernel (td_bs_chain_kernel), both directions
 nb = min(n, 9)
 nll_c, _ = nf._loss(x[:nb], y[:nb], iso=[100.0], cam=[2.0], is_training=True)
