@@ -373,6 +373,13 @@ def run_also(args, nf, hps, ck, x, y, dev, rank, world, sm_mhz, row):
         "config": {"workload": "log_prob, hybrid kernel (conv-3 on tcgen05; nf_model_set_tensor_cores 2), batch %d per GPU" % B, "per_gpu_batch": B},
         "roofline": _hbm_roofline(B, ALG_BYTES_LOG_PROB, ms, "nf_chain_hyb_kernel<true>", None, "binding roof is the FP32 FMA pipe (roofline_fp32)"),
         "roofline_fp32": _fp32_roofline(B, conv_flop, ms, sm_mhz), "gpu_launches": world * 20 * 2}
+    nf.set_tensor_cores(5)   # and on the direct-form all-fp32 kernel (round 1-4's default; the library default is the Winograd form)
+    ms = _timed(lambda i: log_prob_step(eng.handle, x, y, B), 20, 3, dev, world)
+    out["log_prob_%d_direct_kernel" % B] = {
+        "metric": "patches_per_sec_nll", "value": world * B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 20,
+        "config": {"workload": "log_prob, direct-form all-fp32 kernel (nf_model_set_tensor_cores 5), batch %d per GPU" % B, "per_gpu_batch": B},
+        "roofline": _hbm_roofline(B, ALG_BYTES_LOG_PROB, ms, "nf_chain_kernel<true>", None, "binding roof is the FP32 FMA pipe (roofline_fp32)"),
+        "roofline_fp32": _fp32_roofline(B, conv_flop, ms, sm_mhz), "gpu_launches": world * 20 * 2}
     nf.set_tensor_cores(0 if args.tc < 0 else args.tc)
     # ---- configs 2 and 4: log_prob at 4096 (config 2) and the batch sweep 1k / 16k / 64k / 256k per GPU (config 4); batches
     # smaller than the resident one walk through it slice by slice, so consecutive launches never re-read L2-resident inputs
@@ -399,7 +406,7 @@ def run_also(args, nf, hps, ck, x, y, dev, rank, world, sm_mhz, row):
             "metric": "patches_per_sec_nll", "value": world * n / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": steps,
             "config": {"workload": "log_prob Noise Flow (kernel + fp64 reduce%s), batch %d per GPU" % (" + all-reduce" if world > 1 else "", n),
                        "baseline_config": 2 if n == 4096 else 4, "per_gpu_batch": n, "l2": l2},
-            "roofline": _hbm_roofline(n, ALG_BYTES_LOG_PROB, ms, "nf_chain_kernel<true>", None,
+            "roofline": _hbm_roofline(n, ALG_BYTES_LOG_PROB, ms, "nf_chain_wino_kernel<true>" if args.tc in (-1, 0, 3, 4) else "nf_chain_kernel<true>", None,
                                       "whole step (kernel + reduce) timed; binding roof is the FP32 FMA pipe (roofline_fp32)"),
             "roofline_fp32": _fp32_roofline(n, conv_flop, ms, sm_mhz), "gpu_launches": world * steps * 2}
     # ---- the HBM-bound streaming kernel: the reference's sdn5|gain4 baseline model (job_noise_flow.sh:53); the only chain the
@@ -715,7 +722,9 @@ def main():
            "dtype": "f32", "data": "synthetic",
            "config": workload_config(args.mode, hps.arch, B, world, args.width, args.clean), "mean_nll_per_dim": mean_nll,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else (("nf_chain_hyb_kernel" if (args.tc == 2 or (args.tc == 3 and args.mode == "sample")) else "nf_chain_kernel") if args.width == 4 else "nf_wide_chain_kernel"),
+                        "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else (("nf_chain_hyb_kernel" if (args.tc == 2 or (args.tc == 3 and args.mode == "sample")) else
+                                                                                                                         ("nf_chain_wino_kernel" if (args.tc == 4 or (args.tc in (-1, 0, 3) and args.mode != "sample")) else "nf_chain_kernel"))
+                                                                                                                        if args.width == 4 else "nf_wide_chain_kernel"),
                         "kernel_ms": kms, "alg_bytes_per_patch": alg,
                         "note": ("binding roof is the FP32 FMA pipe (see roofline_fp32), not HBM" if n_couplings else
                                  "scale-layer-only chain: streaming kernel, HBM-bound")},

@@ -25,6 +25,7 @@ UNITS = [
     ("nf_stream.cu", ["-use_fast_math"]),
     ("nf_tc.cu", ["-use_fast_math"]),
     ("nf_hybrid.cu", ["-use_fast_math"]),
+    ("nf_wino.cu", ["-use_fast_math"]),
     ("nf_wide.cu", ["-use_fast_math"]),
     ("nf_wide_cond.cu", ["-use_fast_math"]),
     ("nf_wide_tc.cu", ["-use_fast_math"]),

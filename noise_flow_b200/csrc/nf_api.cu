@@ -81,9 +81,12 @@ struct nf_model {
     bool has_cond = false;       // clean-image-conditioned couplings (legacy revnet2d models): every launch takes the generic
                                  // CTA-per-patch kernel (nf_wide_cond.cu), at width 4 too
     int warps_per_cta = NF_MAX_WARPS_PER_CTA;
-    int use_tc = 0;              // width 4: 0 (default) = all-fp32 kernel; 1 = both 3x3 convs as bf16 implicit GEMMs (nf_tc.cu,
-                                 // experiment); 2 = hybrid kernel (nf_hybrid.cu: conv-3 on tcgen05) in both directions; 3 = hybrid for
-                                 // the latent -> data direction only (sampling: +7 %; data -> latent is equally fast on both)
+    int use_tc = 0;              // width 4, which chain kernel runs calls without batch-statistics probes:
+                                 //   0 (default) = all-fp32; data -> latent on the vertical-Winograd kernel (nf_wino.cu, +5 %),
+                                 //       latent -> data on the direct-form kernel (nf_kernels.cu);
+                                 //   5 = direct-form kernel everywhere; 4 = Winograd kernel everywhere;
+                                 //   2 = hybrid kernel (nf_hybrid.cu: conv-3 on tcgen05) everywhere; 3 = hybrid for latent -> data
+                                 //       (sampling +7 %), default otherwise;  1 = both 3x3 convs as bf16 implicit GEMMs (nf_tc.cu)
     int bs_small = 1;            // 1: nf_chain_batch_stats runs small batches as one cooperative kernel (nf_model_set_bs_small)
     // parameter-image / statistics buffers of the small-batch chain: a call takes one (or allocates it) and gives it back
     // after its stream synchronisation, so concurrent callers never share one and no call pays for cudaMalloc
@@ -562,6 +565,8 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
         a.last_layer = mp.n_layers;
         if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
             e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);   // HBM-bound streaming path
+        else if ((m->use_tc == 4 || ((m->use_tc == 0 || m->use_tc == 3) && inverse)) && nf::wino_program_supported(mp, a))
+            e = nf::launch_chain_wino(mp, a, inverse, num_ctas_for(m), stream);     // all-fp32, vertical Winograd F(2,3) convolutions
         else if ((m->use_tc == 2 || (m->use_tc == 3 && !inverse)) && nf::hybrid_program_supported(mp, a))
             e = nf::launch_chain_hybrid(mp, a, inverse, num_ctas_for(m), stream);   // conv-3 on tcgen05, the rest fp32
         else if (m->use_tc == 1 && nf::tc_program_supported(mp, a))
@@ -582,6 +587,8 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
         a.ldj_const = ldj;
         if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
             e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);
+        else if ((m->use_tc == 4 || ((m->use_tc == 0 || m->use_tc == 3) && inverse)) && nf::wino_program_supported(mp, a))
+            e = nf::launch_chain_wino(mp, a, inverse, num_ctas_for(m), stream);
         else if ((m->use_tc == 2 || (m->use_tc == 3 && !inverse)) && nf::hybrid_program_supported(mp, a))
             e = nf::launch_chain_hybrid(mp, a, inverse, num_ctas_for(m), stream);
         else if (m->use_tc == 1 && nf::tc_program_supported(mp, a))
@@ -916,7 +923,7 @@ int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas) {
 
 int nf_model_set_tensor_cores(nf_model* m, int enable) {
     if (!m) return fail(NF_ERR_INVALID, "null model");
-    if (m->width == 4) m->use_tc = (enable == 2 || enable == 3) ? enable : (enable ? 1 : 0);
+    if (m->width == 4) m->use_tc = (enable >= 0 && enable <= 5) ? enable : 0;
     else {
         if (!enable && !nf::wide_width_supported(m->width))
             return fail(NF_ERR_UNSUPPORTED, "width %d has no CUDA-core kernel: the tensor-core kernel cannot be switched off", m->width);

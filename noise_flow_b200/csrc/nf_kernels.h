@@ -48,4 +48,7 @@ cudaError_t launch_chain_tc(const NfModelParams& mp, const NfChainArgs& args, bo
 // hybrid chain kernel (nf_hybrid.cu): conv-3 of every coupling on tcgen05, everything else as in launch_chain
 bool hybrid_program_supported(const NfModelParams& mp, const NfChainArgs& a);
 cudaError_t launch_chain_hybrid(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, cudaStream_t stream);
+// all-fp32 chain kernel with vertical Winograd F(2,3) 3x3 convolutions (nf_wino.cu)
+bool wino_program_supported(const NfModelParams& mp, const NfChainArgs& a);
+cudaError_t launch_chain_wino(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, cudaStream_t stream);
 }  // namespace nf

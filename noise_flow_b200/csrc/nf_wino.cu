@@ -1,0 +1,420 @@
+// All-fp32 fused Noise Flow chain with the two 3x3 convolutions of every coupling net in a VERTICAL WINOGRAD F(2,3)
+// form ("Winograd" chain kernel, experiment, round 5).  Same organisation as nf_kernels.cu -- one warp owns one 32x32x4
+// patch resident in tensor memory, lane = image column, packed fma.rn.f32x2 arithmetic, weights through the uniform
+// datapath -- but a coupling pass walks the patch TWO rows per step, and a 3-tap vertical filter producing two output
+// rows costs 4 multiplies per (dx, in, out) instead of 6:
+//     [d0 d1 d2 d3] -> T0 = d0 - d2, T1 = d1 + d2, T2 = d2 - d1, T3 = d1 - d3            (input transform, owner lane)
+//     m_j = sum over (dx, in) of  U_j[dx][out][in] * T_j(column + dx - 1)                  (U = G g, folded on the host)
+//     y0 = m0 + m1 + m2,  y1 = m1 - m2 - m3                                                (output transform)
+// The owner lane transforms its own column and publishes T (4 values per channel and row pair instead of 2 rows), the
+// neighbours read it through the row rings as before.  Per row: 88 instead of 124 FFMA2, 36 instead of 51 LDCU.128, plus
+// 22 packed adds for the transforms (they amortise badly over 4 channels).
+//
+// Reference semantics: identical to nf_kernels.cu / nf_coupling.cuh (layers.py:117-130, 333-375, 452-498, 555-583,
+// 651-674; noise_flow_model.py:394-480); results differ from the direct form by fp32 rounding only.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nf_params.h"
+#include "nf_kernels.h"
+#include "nf_rng.cuh"
+#include "nf_chain_dev.cuh"
+
+#if !NF_Z_IN_TMEM
+#error "nf_wino.cu keeps the resident patches in tensor memory"
+#endif
+
+namespace nf {
+namespace wino {
+
+// NfCouplingP with the 3x3 filters in the transformed domain: index j = 0..3 instead of dy = 0..2
+struct alignas(16) CouplingW {
+    float a[4][4];
+    float ainv[4][4];
+    float w1[4][3][4][2];   // [j][dx][o][i]
+    float w2[4][4];
+    float w3[4][3][4][4];   // [j][dx][o][i]
+    float b1[4];
+    float b2[4];
+    float b3[3][3][4];
+    float scale;
+    int32_t has_mix;
+    float pad_[2];
+};
+struct ModelParamsW {
+    int32_t n_layers;
+    int32_t n_rows;
+    int32_t pad_[2];
+    int32_t op[NF_MAX_LAYERS];
+    int32_t slot[NF_MAX_LAYERS];
+    CouplingW cp[NF_MAX_COUPLINGS];
+    NfMixP mix[NF_MAX_MIX];
+    NfScaleP sc[NF_MAX_SCALE];
+};
+static_assert(sizeof(ModelParamsW) <= 32 * 1024 - 256, "kernel parameter space");
+
+struct __align__(16) WarpSmemW {
+    float4 hw[2][4][34];   // conv-3 input tiles: [slot][j][column + 1], T_j of the four h2 channels; [0] and [33] = zero halo
+    float4 xw[2][2][34];   // conv-1 input tiles: [slot][half][column + 1] = (T0 c0, T0 c1, T1 c0, T1 c1) | (T2.., T3..)
+};
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
+
+__device__ __forceinline__ void ld_rows(const ZStore& zs, int r, float4& a, float4& b) {   // rows r, r + 1 (r even)
+    uint32_t v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(zs.taddr + (uint32_t)(r * 4)));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]));
+    a = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+    b = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+}
+__device__ __forceinline__ void st_rows(const ZStore& zs, int r, const float4& a, const float4& b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(zs.taddr + (uint32_t)(r * 4)), "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
+                    "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)) : "memory");
+}
+
+// affine update of one pixel (stage C tail)
+template <bool INV>
+__device__ __forceinline__ void affine(const float (&h3)[4], const float scale, float4& z, float& ldj, const bool has_mix, const float2 (&am)[4][2]) {
+    const float ls0 = scale * fast_tanh(h3[2]);        // shift = h3[0:2], log_scale = scale * tanh(h3[2:4])   (layers.py:362 / :342)
+    const float ls1 = scale * fast_tanh(h3[3]);
+    if (INV) {
+        z.z = fmaf(z.z, fast_exp(ls0), h3[0]);                               // layers.py:363-367
+        z.w = fmaf(z.w, fast_exp(ls1), h3[1]);
+        ldj += ls0 + ls1;                                                    // layers.py:372
+    } else {
+        z.z = (z.z - h3[0]) * fast_exp(-ls0);                                // layers.py:343-347
+        z.w = (z.w - h3[1]) * fast_exp(-ls1);
+        ldj -= ls0 + ls1;                                                    // layers.py:352
+        if (has_mix) z = mix4r(z, am);                                       // Conv2d1x1._forward, layers.py:113-114
+    }
+}
+
+// Pair step u = 0..18.  Every stage works on tiles published in EARLIER steps, so a step needs one __syncwarp:
+//   stage A (rows 2u, 2u+1)  : z <- z.A (inverse only); with the retained x0 rows 2u-2, 2u-1 publish the conv-1 input tile
+//                              whose outputs are h1 rows (2u-1, 2u)
+//   stage B (tile of step u-1): conv-1 rows (2u-3, 2u-2) -> BN+ReLU, 1x1 conv, BN+ReLU -> h2 rows; with the retained h2 rows
+//                              2u-5, 2u-4 publish the conv-3 input tile whose outputs are rows (2u-4, 2u-3)
+//   stage C (tile of step u-1): conv-3 rows (2u-6, 2u-5) + edge-indicator bias -> tanh/exp affine update of z + log-det
+template <bool INV, bool GUARDED, class CP>
+__device__ __forceinline__ void wino_step(const CP& P, WarpSmemW& s, const ZStore& zs, const int lane, const int u, const bool has_mix,
+                                          float2 (&xp)[2], float4 (&hp)[2], float& ldj, const float2 (&am)[4][2], const float (&b3m)[4]) {
+    const float2 zero2 = make_float2(0.f, 0.f);
+    const bool do_a = !GUARDED || u <= 15;
+    const bool pub_x = !GUARDED || u <= 16;
+    const bool do_b = !GUARDED || (u >= 1 && u <= 17);
+    const bool pub_h = !GUARDED || (u >= 2 && u <= 17);
+    const bool do_c = !GUARDED || (u >= 3 && u <= 18);
+    zs.commit();
+    float4 za0 = make_float4(0.f, 0.f, 0.f, 0.f), za1 = za0, zc0 = za0, zc1 = za0;
+    if (do_a) ld_rows(zs, 2 * u, za0, za1);
+    if (do_c) ld_rows(zs, 2 * u - 6, zc0, zc1);
+    // ---------------- stage A
+    {
+        float2 d2 = zero2, d3 = zero2;
+        if (do_a) {
+            if (INV && has_mix) {
+                za0 = mix4r(za0, am);                           // Conv2d1x1._inverse, layers.py:117-119
+                za1 = mix4r(za1, am);
+                st_rows(zs, 2 * u, za0, za1);
+            }
+            d2 = lo2(za0);
+            d3 = lo2(za1);
+        }
+        if (pub_x) {
+            const float2 t0 = sub2(xp[0], d2), t1 = add2(xp[1], d2), t2 = sub2(d2, xp[1]), t3 = sub2(xp[1], d3);
+            s.xw[u & 1][0][lane + 1] = make_float4(t0.x, t0.y, t1.x, t1.y);
+            s.xw[u & 1][1][lane + 1] = make_float4(t2.x, t2.y, t3.x, t3.y);
+        }
+        xp[0] = d2;
+        xp[1] = d3;
+    }
+    // ---------------- stage B
+    if (do_b) {
+        float2 m[4][4];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const float4 t01 = s.xw[(u - 1) & 1][0][lane + dx], t23 = s.xw[(u - 1) & 1][1][lane + dx];
+            const float2 t[4] = {lo2(t01), hi2(t01), lo2(t23), hi2(t23)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int o = 0; o < 4; ++o) m[j][o] = ffma2(t[j], ld2(&P.w1[j][dx][o][0]), dx == 0 ? zero2 : m[j][o]);
+        }
+        float ha[4], hb[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const float2 y0 = add2(m[0][o], add2(m[1][o], m[2][o])), y1 = sub2(sub2(m[1][o], m[2][o]), m[3][o]);
+            ha[o] = fmaxf(y0.x + y0.y + P.b1[o], 0.f);                                     // BN folded, ReLU
+            hb[o] = fmaxf(y1.x + y1.y + P.b1[o], 0.f);
+        }
+        const float2 a01 = make_float2(ha[0], ha[1]), a23 = make_float2(ha[2], ha[3]);
+        const float2 b01 = make_float2(hb[0], hb[1]), b23 = make_float2(hb[2], hb[3]);
+        float ea[4], eb[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const float2 w01 = ld2(&P.w2[o][0]), w23 = ld2(&P.w2[o][2]);
+            const float2 ua = ffma2(a23, w23, ffma2(a01, w01, zero2)), ub = ffma2(b23, w23, ffma2(b01, w01, zero2));
+            ea[o] = fmaxf(ua.x + ua.y + P.b2[o], 0.f);
+            eb[o] = fmaxf(ub.x + ub.y + P.b2[o], 0.f);
+        }
+        float4 e2 = make_float4(ea[0], ea[1], ea[2], ea[3]), e3 = make_float4(eb[0], eb[1], eb[2], eb[3]);
+        if (GUARDED && u == 1) e2 = make_float4(0.f, 0.f, 0.f, 0.f);    // h2 row -1: SAME padding of conv-3
+        if (GUARDED && u == 17) e3 = make_float4(0.f, 0.f, 0.f, 0.f);   // h2 row 32
+        if (pub_h) {
+            const float2 t0l = sub2(lo2(hp[0]), lo2(e2)), t0h = sub2(hi2(hp[0]), hi2(e2));
+            const float2 t1l = add2(lo2(hp[1]), lo2(e2)), t1h = add2(hi2(hp[1]), hi2(e2));
+            const float2 t2l = sub2(lo2(e2), lo2(hp[1])), t2h = sub2(hi2(e2), hi2(hp[1]));
+            const float2 t3l = sub2(lo2(hp[1]), lo2(e3)), t3h = sub2(hi2(hp[1]), hi2(e3));
+            s.hw[u & 1][0][lane + 1] = make_float4(t0l.x, t0l.y, t0h.x, t0h.y);
+            s.hw[u & 1][1][lane + 1] = make_float4(t1l.x, t1l.y, t1h.x, t1h.y);
+            s.hw[u & 1][2][lane + 1] = make_float4(t2l.x, t2l.y, t2h.x, t2h.y);
+            s.hw[u & 1][3][lane + 1] = make_float4(t3l.x, t3l.y, t3h.x, t3h.y);
+        }
+        hp[0] = e2;
+        hp[1] = e3;
+    }
+    // ---------------- stage C
+    if (do_c) {
+        float2 m[4][4];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = s.hw[(u - 1) & 1][j][lane + dx];
+                const float2 tl = lo2(t), th = hi2(t);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    m[j][o] = ffma2(tl, ld2(&P.w3[j][dx][o][0]), dx == 0 ? zero2 : m[j][o]);
+                    m[j][o] = ffma2(th, ld2(&P.w3[j][dx][o][2]), m[j][o]);
+                }
+            }
+        }
+        float h3a[4], h3b[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const float2 y0 = add2(m[0][o], add2(m[1][o], m[2][o])), y1 = sub2(sub2(m[1][o], m[2][o]), m[3][o]);
+            float ba = b3m[o], bb = b3m[o];
+            if (GUARDED) {   // row class of the edge-indicator bias (rows 0 and 31)
+                const int cc = lane == 0 ? 0 : (lane == 31 ? 2 : 1);
+                if (u == 3) ba = P.b3[0][cc][o];
+                if (u == 18) bb = P.b3[2][cc][o];
+            }
+            h3a[o] = y0.x + y0.y + ba;
+            h3b[o] = y1.x + y1.y + bb;
+        }
+        affine<INV>(h3a, P.scale, zc0, ldj, has_mix, am);
+        affine<INV>(h3b, P.scale, zc1, ldj, has_mix, am);
+        st_rows(zs, 2 * u - 6, zc0, zc1);
+    }
+    __syncwarp();
+}
+
+template <bool INV, class CP>
+__device__ __forceinline__ void wino_pass(const CP& P, WarpSmemW& s, const ZStore& zs, const int lane, float& ldj) {
+    const bool has_mix = P.has_mix != 0;
+    float2 am[4][2];
+    load_mix_regs<INV>(P, am, s.xw[0][0][0].x);
+    float b3m[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) b3m[o] = lane == 0 ? P.b3[1][0][o] : (lane == 31 ? P.b3[1][2][o] : P.b3[1][1][o]);
+    float2 xp[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float4 hp[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+#pragma unroll 1
+    for (int u = 0; u < 19; ++u) {
+        if (u >= 4 && u <= 15) wino_step<INV, false>(P, s, zs, lane, u, has_mix, xp, hp, ldj, am, b3m);
+        else                   wino_step<INV, true>(P, s, zs, lane, u, has_mix, xp, hp, ldj, am, b3m);
+    }
+}
+
+#define NFW_FAST_SLOTS 8
+template <bool INV>
+__device__ __forceinline__ void wino_dispatch(const ModelParamsW& mp, WarpSmemW& s, const ZStore& zs, int lane, float& ldj, int slot) {
+    switch (slot) {
+#define NFW_CASE(K) case K: wino_pass<INV>(mp.cp[K], s, zs, lane, ldj); break;
+        NFW_CASE(0) NFW_CASE(1) NFW_CASE(2) NFW_CASE(3) NFW_CASE(4) NFW_CASE(5) NFW_CASE(6) NFW_CASE(7)
+#undef NFW_CASE
+        default: wino_pass<INV>(mp.cp[slot], s, zs, lane, ldj); break;
+    }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(NF_MAX_CTA_THREADS, 1)
+nf_chain_wino_kernel(const __grid_constant__ ModelParamsW mp, const NfChainArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
+    WarpSmemW& s = reinterpret_cast<WarpSmemW*>(smem_raw)[warp];
+
+    __shared__ uint32_t tmem_base_smem;
+    if (warp == 0) {   // the whole tensor memory of this SM: 512 columns x 128 lanes = 16 resident patches
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_smem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const ZStore zs = {tmem_base_smem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128)};
+    for (int e = lane; e < (int)(sizeof(WarpSmemW) / 16); e += 32) reinterpret_cast<float4*>(&s)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+
+    const long long stride = (long long)gridDim.x * warps_per_cta;
+    for (long long base = (long long)blockIdx.x * warps_per_cta; base < a.n; base += stride) {
+        const bool active = base + warp < a.n;
+        const long long p = active ? base + warp : a.n - 1;
+        int row = a.rows ? a.rows[p] : a.default_row;
+        row = min(max(row, 0), NF_MAX_ROWS - 1);
+        if (a.in) {
+            const float4* src = reinterpret_cast<const float4*>(a.in) + p * NF_PIXELS;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                float4 v = __ldcs(src + r * 32 + lane);
+                if (!INV) { v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp; }   // noise_flow_model.py:501
+                zs.store(r, v);
+            }
+        } else {
+#pragma unroll 2
+            for (int r = 0; r < 32; ++r) {
+                float4 v = philox_normal4(a.seed, a.offset, a.patch_base + (unsigned long long)p, (unsigned int)(r * 32 + lane));
+                v.x *= a.temp; v.y *= a.temp; v.z *= a.temp; v.w *= a.temp;
+                zs.store(r, v);
+            }
+        }
+        zs.commit();
+        __syncwarp();
+
+        float ldj = 0.f;
+        const int l0 = INV ? a.first_layer : a.last_layer - 1, l1 = INV ? a.last_layer : a.first_layer - 1, dl = INV ? 1 : -1;
+        for (int l = l0; l != l1; l += dl) {
+            const int op = mp.op[l], slot = mp.slot[l];
+            switch (op) {
+                case NF_KOP_COUPLING: wino_dispatch<INV>(mp, s, zs, lane, ldj, slot); break;
+                case NF_KOP_MIX: mix_pass<INV>(mp.mix[slot], zs); break;
+                case NF_KOP_SDN:
+                    sdn_pass<INV>(reinterpret_cast<const float4*>(a.y) + p * NF_PIXELS, mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], zs, lane, ldj);
+                    break;
+                case NF_KOP_GAIN:
+                    gain_pass<INV>(mp.sc[slot].t[row][0], mp.sc[slot].t[row][1], mp.sc[slot].t[row][2], zs, lane, ldj);
+                    break;
+                default: break;
+            }
+            __syncthreads();   // layer boundary: keeps the CTA's warps in the same loop body (I-cache)
+        }
+
+        zs.commit();
+        float s1 = 0.f, s2 = 0.f;
+        float4* dst = (a.out && active) ? reinterpret_cast<float4*>(a.out) + p * NF_PIXELS : nullptr;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const float4 z = zs.load(r);
+            if (dst) __stcs(dst + r * 32 + lane, z);
+            s1 += (z.x + z.y) + (z.z + z.w);
+            s2 = fmaf(z.x, z.x, fmaf(z.y, z.y, fmaf(z.z, z.z, fmaf(z.w, z.w, s2))));
+        }
+        ldj = warp_sum(ldj);
+        if (a.nll || a.sdz) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
+        if (lane == 0 && active) {
+            const float logdet = ldj + (INV ? a.ldj_const : -a.ldj_const) + (a.logdet_in ? a.logdet_in[p] : 0.f);
+            if (a.logdet) a.logdet[p] = logdet;
+            if (a.nll) {   // -(logdet + sum -0.5 (log 2pi + z^2))       noise_flow_model.py:474-475,537-539
+                const float logp = -0.5f * (NF_DIMS * 1.8378770664093453f + s2);
+                a.nll[p] = -(logdet + logp);
+            }
+            if (a.sdz) {   // population std-dev of z                     noise_flow_model.py:477-478
+                const float mean = s1 * (1.f / NF_DIMS);
+                a.sdz[p] = sqrtf(fmaxf(s2 * (1.f / NF_DIMS) - mean * mean, 0.f));
+            }
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_smem), "r"(512u) : "memory");
+}
+
+// host: G g of the vertical taps, in double
+static void to_winograd(const NfModelParams& mp, ModelParamsW& w) {
+    w.n_layers = mp.n_layers;
+    w.n_rows = mp.n_rows;
+    w.pad_[0] = w.pad_[1] = 0;
+    for (int l = 0; l < NF_MAX_LAYERS; ++l) { w.op[l] = mp.op[l]; w.slot[l] = mp.slot[l]; }
+    for (int k = 0; k < NF_MAX_MIX; ++k) w.mix[k] = mp.mix[k];
+    for (int k = 0; k < NF_MAX_SCALE; ++k) w.sc[k] = mp.sc[k];
+    for (int k = 0; k < NF_MAX_COUPLINGS; ++k) {
+        const NfCouplingP& p = mp.cp[k];
+        CouplingW& q = w.cp[k];
+        for (int i = 0; i < 16; ++i) { (&q.a[0][0])[i] = (&p.a[0][0])[i]; (&q.ainv[0][0])[i] = (&p.ainv[0][0])[i]; (&q.w2[0][0])[i] = (&p.w2[0][0])[i]; }
+        for (int i = 0; i < 4; ++i) { q.b1[i] = p.b1[i]; q.b2[i] = p.b2[i]; }
+        for (int i = 0; i < 36; ++i) (&q.b3[0][0][0])[i] = (&p.b3[0][0][0])[i];
+        q.scale = p.scale;
+        q.has_mix = p.has_mix;
+        q.pad_[0] = q.pad_[1] = 0.f;
+        for (int dx = 0; dx < 3; ++dx)
+            for (int o = 0; o < 4; ++o) {
+                for (int i = 0; i < 2; ++i) {
+                    const double g0 = p.w1[0][dx][o][i], g1 = p.w1[1][dx][o][i], g2 = p.w1[2][dx][o][i];
+                    q.w1[0][dx][o][i] = (float)g0;
+                    q.w1[1][dx][o][i] = (float)(0.5 * (g0 + g1 + g2));
+                    q.w1[2][dx][o][i] = (float)(0.5 * (g0 - g1 + g2));
+                    q.w1[3][dx][o][i] = (float)g2;
+                }
+                for (int i = 0; i < 4; ++i) {
+                    const double g0 = p.w3[0][dx][o][i], g1 = p.w3[1][dx][o][i], g2 = p.w3[2][dx][o][i];
+                    q.w3[0][dx][o][i] = (float)g0;
+                    q.w3[1][dx][o][i] = (float)(0.5 * (g0 + g1 + g2));
+                    q.w3[2][dx][o][i] = (float)(0.5 * (g0 - g1 + g2));
+                    q.w3[3][dx][o][i] = (float)g2;
+                }
+            }
+    }
+}
+
+}  // namespace wino
+
+bool wino_program_supported(const NfModelParams& mp, const NfChainArgs& a) {
+    if (a.bn_stage != 0) return false;   // batch-statistics probes run on the direct-form kernel
+    for (int l = a.first_layer; l < a.last_layer; ++l)
+        if (mp.op[l] == NF_KOP_COUPLING) return true;
+    return false;
+}
+
+cudaError_t launch_chain_wino(const NfModelParams& mp, const NfChainArgs& args, bool inverse, int num_sms, cudaStream_t stream) {
+    if (args.n <= 0) return cudaSuccess;
+    wino::ModelParamsW w;
+    wino::to_winograd(mp, w);
+    int warps = NF_MAX_WARPS_PER_CTA;
+    {   // CTA shape against wave quantisation, as launch_chain
+        const long long g = args.n < (long long)num_sms ? args.n : (long long)num_sms;
+        const long long per_sm = (args.n + g - 1) / g, rounds = (per_sm + warps - 1) / warps;
+        warps = (int)((per_sm + rounds - 1) / rounds);
+    }
+    const size_t smem = (size_t)warps * sizeof(wino::WarpSmemW);
+    static bool attr_done[NF_MAX_DEVICES][2] = {};
+    const int dev = device_slot(), k = inverse ? 0 : 1;
+    if (!attr_done[dev][k]) {
+        const int max_smem = NF_MAX_WARPS_PER_CTA * (int)sizeof(wino::WarpSmemW);
+        const cudaError_t e = inverse ? cudaFuncSetAttribute(wino::nf_chain_wino_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
+                                      : cudaFuncSetAttribute(wino::nf_chain_wino_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e != cudaSuccess) return e;
+        attr_done[dev][k] = true;
+    }
+    long long ctas = (args.n + warps - 1) / warps;
+    if (ctas > num_sms) ctas = num_sms;
+    if (inverse) wino::nf_chain_wino_kernel<true><<<(unsigned)ctas, warps * 32, smem, stream>>>(w, args);
+    else         wino::nf_chain_wino_kernel<false><<<(unsigned)ctas, warps * 32, smem, stream>>>(w, args);
+    return cudaGetLastError();
+}
+
+}  // namespace nf

@@ -251,13 +251,18 @@ class NoiseFlow(object):
         _lib.check(self._engine.lib.nf_model_set_launch(self._engine.handle, warps_per_cta, num_ctas), "nf_model_set_launch")
 
     def set_tensor_cores(self, enable=True):
-        """Width 4: ``"hybrid"`` (2) runs conv-3 of every coupling net on the tensor cores (tcgen05, fp16 hi/lo split
-        operands, csrc/nf_hybrid.cu) in both directions; ``"auto"`` (3) does so for sampling / forward only (where it is
-        faster); ``False`` (0, the default) selects the all-fp32 kernel everywhere; ``True`` (1) the older experimental kernel with both 3x3
-        convolutions as bf16 hi/lo implicit GEMMs.
+        """Width 4 -- which chain kernel runs (C ABI ``nf_model_set_tensor_cores``):
+        ``"default"`` (0): all-fp32; data -> latent on the vertical-Winograd kernel, latent -> data on the direct-form kernel;
+        ``False`` / ``"direct"`` (5): the direct-form all-fp32 kernel everywhere;  ``"winograd"`` (4): the Winograd kernel everywhere;
+        ``"hybrid"`` (2): conv-3 of every coupling net on the tensor cores (tcgen05, fp16 hi/lo split operands) in both
+        directions;  ``"auto"`` (3): hybrid for sampling / forward (where it is faster), default otherwise;
+        ``True`` (1): the older experimental kernel with both 3x3 convolutions as bf16 hi/lo implicit GEMMs.
         Widths 32 / 64 / 128: the tensor-core kernel is the default; ``False`` selects the CUDA-core kernel (width 32 only)."""
         self.build()
-        mode = {"hybrid": 2, "auto": 3}.get(enable, enable) if isinstance(enable, (str, int)) and not isinstance(enable, bool) else (1 if enable else 0)
+        if isinstance(enable, bool):
+            mode = (1 if enable else 5) if self.hps.width == 4 else int(enable)
+        else:
+            mode = {"default": 0, "hybrid": 2, "auto": 3, "winograd": 4, "direct": 5}.get(enable, enable)
         _lib.check(self._engine.lib.nf_model_set_tensor_cores(self._engine.handle, int(mode)), "nf_model_set_tensor_cores")
         return self
 

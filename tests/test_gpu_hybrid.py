@@ -131,7 +131,7 @@ def test_auto_mode_routes_sampling_to_the_hybrid_kernel(shipped):
     hps, ck = shipped
     x, y = synth_batch(30, seed=183)
     eps = np.random.RandomState(184).randn(30, 32, 32, 4).astype(np.float32)
-    auto, hyb, f32 = _nf(hps, ck, "auto"), _nf(hps, ck, "hybrid"), _nf(hps, ck, False)
+    auto, hyb, f32 = _nf(hps, ck, "auto"), _nf(hps, ck, "hybrid"), _nf(hps, ck, "default")
     kw = dict(iso=[100.0], cam=[2.0])
     assert torch.equal(auto.sample(y, 0.6, y, eps=eps, **kw), hyb.sample(y, 0.6, y, eps=eps, **kw))
     assert torch.equal(auto._loss(x, y, **kw)[0], f32._loss(x, y, **kw)[0])
