@@ -82,11 +82,10 @@ struct nf_model {
                                  // CTA-per-patch kernel (nf_wide_cond.cu), at width 4 too
     int warps_per_cta = NF_MAX_WARPS_PER_CTA;
     int use_tc = 0;              // width 4, which chain kernel runs calls without batch-statistics probes:
-                                 //   0 (default) = all-fp32; data -> latent on the vertical-Winograd kernel (nf_wino.cu, +5 %),
-                                 //       latent -> data on the direct-form kernel (nf_kernels.cu);
-                                 //   5 = direct-form kernel everywhere; 4 = Winograd kernel everywhere;
+                                 //   0 (default) = 4 = the all-fp32 vertical-Winograd kernel (nf_wino.cu: +10 % data -> latent, +3 % latent -> data);
+                                 //   5 = the all-fp32 direct-form kernel (nf_kernels.cu) everywhere;
                                  //   2 = hybrid kernel (nf_hybrid.cu: conv-3 on tcgen05) everywhere; 3 = hybrid for latent -> data
-                                 //       (sampling +7 %), default otherwise;  1 = both 3x3 convs as bf16 implicit GEMMs (nf_tc.cu)
+                                 //       (sampling +7 % over the direct form), default otherwise;  1 = both 3x3 convs as bf16 implicit GEMMs (nf_tc.cu)
     int bs_small = 1;            // 1: nf_chain_batch_stats runs small batches as one cooperative kernel (nf_model_set_bs_small)
     // parameter-image / statistics buffers of the small-batch chain: a call takes one (or allocates it) and gives it back
     // after its stream synchronisation, so concurrent callers never share one and no call pays for cudaMalloc
@@ -565,7 +564,7 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
         a.last_layer = mp.n_layers;
         if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
             e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);   // HBM-bound streaming path
-        else if ((m->use_tc == 4 || ((m->use_tc == 0 || m->use_tc == 3) && inverse)) && nf::wino_program_supported(mp, a))
+        else if ((m->use_tc == 4 || m->use_tc == 0 || (m->use_tc == 3 && inverse)) && nf::wino_program_supported(mp, a))
             e = nf::launch_chain_wino(mp, a, inverse, num_ctas_for(m), stream);     // all-fp32, vertical Winograd F(2,3) convolutions
         else if ((m->use_tc == 2 || (m->use_tc == 3 && !inverse)) && nf::hybrid_program_supported(mp, a))
             e = nf::launch_chain_hybrid(mp, a, inverse, num_ctas_for(m), stream);   // conv-3 on tcgen05, the rest fp32
@@ -587,7 +586,7 @@ int launch_range(const nf_model* m, int first, int last, bool inverse, NfChainAr
         a.ldj_const = ldj;
         if (a.in && nf::program_is_scale_only(mp, 0, mp.n_layers))
             e = nf::launch_scale_stream(mp, a, inverse, m->sm_count, stream);
-        else if ((m->use_tc == 4 || ((m->use_tc == 0 || m->use_tc == 3) && inverse)) && nf::wino_program_supported(mp, a))
+        else if ((m->use_tc == 4 || m->use_tc == 0 || (m->use_tc == 3 && inverse)) && nf::wino_program_supported(mp, a))
             e = nf::launch_chain_wino(mp, a, inverse, num_ctas_for(m), stream);
         else if ((m->use_tc == 2 || (m->use_tc == 3 && !inverse)) && nf::hybrid_program_supported(mp, a))
             e = nf::launch_chain_hybrid(mp, a, inverse, num_ctas_for(m), stream);

@@ -7,8 +7,10 @@
 //     m_j = sum over (dx, in) of  U_j[dx][out][in] * T_j(column + dx - 1)                  (U = G g, folded on the host)
 //     y0 = m0 + m1 + m2,  y1 = m1 - m2 - m3                                                (output transform)
 // The owner lane transforms its own column and publishes T (4 values per channel and row pair instead of 2 rows), the
-// neighbours read it through the row rings as before.  Per row: 88 instead of 124 FFMA2, 36 instead of 51 LDCU.128, plus
-// 22 packed adds for the transforms (they amortise badly over 4 channels).
+// neighbours read it through the row rings as before.  The packed FFMA2 pair runs over the TRANSFORM index -- (m0, m1) and
+// (m2, m3) of one output accumulate over the input channels one after the other -- so there are no (even, odd) partial sums
+// to close: y0 = m0 + (m1 + b) + m2 and y1 = (m1 + b) - m2 - m3 cost 5 adds per output and row pair.  Per row: 88 instead of
+// 124 FFMA2, 32 instead of 51 LDCU.128 (the transforms amortise badly over 4 channels).
 //
 // Reference semantics: identical to nf_kernels.cu / nf_coupling.cuh (layers.py:117-130, 333-375, 452-498, 555-583,
 // 651-674; noise_flow_model.py:394-480); results differ from the direct form by fp32 rounding only.
@@ -30,9 +32,9 @@ namespace wino {
 struct alignas(16) CouplingW {
     float a[4][4];
     float ainv[4][4];
-    float w1[4][3][4][2];   // [j][dx][o][i]
+    float w1[3][4][2][4];   // [dx][o][i][j]: the four transformed taps of one (dx, out, in) are one LDCU.128
     float w2[4][4];
-    float w3[4][3][4][4];   // [j][dx][o][i]
+    float w3[3][4][4][4];   // [dx][o][i][j]
     float b1[4];
     float b2[4];
     float b3[3][3][4];
@@ -53,8 +55,8 @@ struct ModelParamsW {
 static_assert(sizeof(ModelParamsW) <= 32 * 1024 - 256, "kernel parameter space");
 
 struct __align__(16) WarpSmemW {
-    float4 hw[2][4][34];   // conv-3 input tiles: [slot][j][column + 1], T_j of the four h2 channels; [0] and [33] = zero halo
-    float4 xw[2][2][34];   // conv-1 input tiles: [slot][half][column + 1] = (T0 c0, T0 c1, T1 c0, T1 c1) | (T2.., T3..)
+    float4 hw[2][4][34];   // conv-3 input tiles: [slot][channel][column + 1] = (T0, T1, T2, T3) of that h2 channel; [0], [33] = zero halo
+    float4 xw[2][2][34];   // conv-1 input tiles: [slot][channel][column + 1] = (T0, T1, T2, T3) of that x0 channel
 };
 
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
@@ -132,32 +134,34 @@ __device__ __forceinline__ void wino_step(const CP& P, WarpSmemW& s, const ZStor
             d2 = lo2(za0);
             d3 = lo2(za1);
         }
-        if (pub_x) {
-            const float2 t0 = sub2(xp[0], d2), t1 = add2(xp[1], d2), t2 = sub2(d2, xp[1]), t3 = sub2(xp[1], d3);
-            s.xw[u & 1][0][lane + 1] = make_float4(t0.x, t0.y, t1.x, t1.y);
-            s.xw[u & 1][1][lane + 1] = make_float4(t2.x, t2.y, t3.x, t3.y);
+        if (pub_x) {   // channel c: (T0, T1, T2, T3) = (d0 - d2, d1 + d2, d2 - d1, d1 - d3)
+            s.xw[u & 1][0][lane + 1] = make_float4(xp[0].x - d2.x, xp[1].x + d2.x, d2.x - xp[1].x, xp[1].x - d3.x);
+            s.xw[u & 1][1][lane + 1] = make_float4(xp[0].y - d2.y, xp[1].y + d2.y, d2.y - xp[1].y, xp[1].y - d3.y);
         }
         xp[0] = d2;
         xp[1] = d3;
     }
     // ---------------- stage B
     if (do_b) {
-        float2 m[4][4];
+        float2 m01[4], m23[4];
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-            const float4 t01 = s.xw[(u - 1) & 1][0][lane + dx], t23 = s.xw[(u - 1) & 1][1][lane + dx];
-            const float2 t[4] = {lo2(t01), hi2(t01), lo2(t23), hi2(t23)};
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int c = 0; c < 2; ++c) {
+                const float4 t = s.xw[(u - 1) & 1][c][lane + dx];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) m[j][o] = ffma2(t[j], ld2(&P.w1[j][dx][o][0]), dx == 0 ? zero2 : m[j][o]);
+                for (int o = 0; o < 4; ++o) {
+                    m01[o] = ffma2(lo2(t), ld2(&P.w1[dx][o][c][0]), (dx == 0 && c == 0) ? zero2 : m01[o]);
+                    m23[o] = ffma2(hi2(t), ld2(&P.w1[dx][o][c][2]), (dx == 0 && c == 0) ? zero2 : m23[o]);
+                }
+            }
         }
         float ha[4], hb[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-            const float2 y0 = add2(m[0][o], add2(m[1][o], m[2][o])), y1 = sub2(sub2(m[1][o], m[2][o]), m[3][o]);
-            ha[o] = fmaxf(y0.x + y0.y + P.b1[o], 0.f);                                     // BN folded, ReLU
-            hb[o] = fmaxf(y1.x + y1.y + P.b1[o], 0.f);
+            const float sb = m01[o].y + P.b1[o];                                           // m1 + bias: in both rows with a plus
+            ha[o] = fmaxf((m01[o].x + sb) + m23[o].x, 0.f);                                // y0 = m0 + m1 + m2; BN folded, ReLU
+            hb[o] = fmaxf((sb - m23[o].x) - m23[o].y, 0.f);                                // y1 = m1 - m2 - m3
         }
         const float2 a01 = make_float2(ha[0], ha[1]), a23 = make_float2(ha[2], ha[3]);
         const float2 b01 = make_float2(hb[0], hb[1]), b23 = make_float2(hb[2], hb[3]);
@@ -173,46 +177,40 @@ __device__ __forceinline__ void wino_step(const CP& P, WarpSmemW& s, const ZStor
         if (GUARDED && u == 1) e2 = make_float4(0.f, 0.f, 0.f, 0.f);    // h2 row -1: SAME padding of conv-3
         if (GUARDED && u == 17) e3 = make_float4(0.f, 0.f, 0.f, 0.f);   // h2 row 32
         if (pub_h) {
-            const float2 t0l = sub2(lo2(hp[0]), lo2(e2)), t0h = sub2(hi2(hp[0]), hi2(e2));
-            const float2 t1l = add2(lo2(hp[1]), lo2(e2)), t1h = add2(hi2(hp[1]), hi2(e2));
-            const float2 t2l = sub2(lo2(e2), lo2(hp[1])), t2h = sub2(hi2(e2), hi2(hp[1]));
-            const float2 t3l = sub2(lo2(hp[1]), lo2(e3)), t3h = sub2(hi2(hp[1]), hi2(e3));
-            s.hw[u & 1][0][lane + 1] = make_float4(t0l.x, t0l.y, t0h.x, t0h.y);
-            s.hw[u & 1][1][lane + 1] = make_float4(t1l.x, t1l.y, t1h.x, t1h.y);
-            s.hw[u & 1][2][lane + 1] = make_float4(t2l.x, t2l.y, t2h.x, t2h.y);
-            s.hw[u & 1][3][lane + 1] = make_float4(t3l.x, t3l.y, t3h.x, t3h.y);
+            s.hw[u & 1][0][lane + 1] = make_float4(hp[0].x - e2.x, hp[1].x + e2.x, e2.x - hp[1].x, hp[1].x - e3.x);
+            s.hw[u & 1][1][lane + 1] = make_float4(hp[0].y - e2.y, hp[1].y + e2.y, e2.y - hp[1].y, hp[1].y - e3.y);
+            s.hw[u & 1][2][lane + 1] = make_float4(hp[0].z - e2.z, hp[1].z + e2.z, e2.z - hp[1].z, hp[1].z - e3.z);
+            s.hw[u & 1][3][lane + 1] = make_float4(hp[0].w - e2.w, hp[1].w + e2.w, e2.w - hp[1].w, hp[1].w - e3.w);
         }
         hp[0] = e2;
         hp[1] = e3;
     }
     // ---------------- stage C
     if (do_c) {
-        float2 m[4][4];
+        float2 m01[4], m23[4];
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 t = s.hw[(u - 1) & 1][j][lane + dx];
-                const float2 tl = lo2(t), th = hi2(t);
+            for (int c = 0; c < 4; ++c) {
+                const float4 t = s.hw[(u - 1) & 1][c][lane + dx];
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
-                    m[j][o] = ffma2(tl, ld2(&P.w3[j][dx][o][0]), dx == 0 ? zero2 : m[j][o]);
-                    m[j][o] = ffma2(th, ld2(&P.w3[j][dx][o][2]), m[j][o]);
+                    m01[o] = ffma2(lo2(t), ld2(&P.w3[dx][o][c][0]), (dx == 0 && c == 0) ? zero2 : m01[o]);
+                    m23[o] = ffma2(hi2(t), ld2(&P.w3[dx][o][c][2]), (dx == 0 && c == 0) ? zero2 : m23[o]);
                 }
             }
         }
         float h3a[4], h3b[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-            const float2 y0 = add2(m[0][o], add2(m[1][o], m[2][o])), y1 = sub2(sub2(m[1][o], m[2][o]), m[3][o]);
             float ba = b3m[o], bb = b3m[o];
             if (GUARDED) {   // row class of the edge-indicator bias (rows 0 and 31)
                 const int cc = lane == 0 ? 0 : (lane == 31 ? 2 : 1);
                 if (u == 3) ba = P.b3[0][cc][o];
                 if (u == 18) bb = P.b3[2][cc][o];
             }
-            h3a[o] = y0.x + y0.y + ba;
-            h3b[o] = y1.x + y1.y + bb;
+            h3a[o] = (m01[o].x + (m01[o].y + ba)) + m23[o].x;      // y0 = m0 + m1 + m2
+            h3b[o] = ((m01[o].y + bb) - m23[o].x) - m23[o].y;      // y1 = m1 - m2 - m3
         }
         affine<INV>(h3a, P.scale, zc0, ldj, has_mix, am);
         affine<INV>(h3b, P.scale, zc1, ldj, has_mix, am);
@@ -365,17 +363,17 @@ static void to_winograd(const NfModelParams& mp, ModelParamsW& w) {
             for (int o = 0; o < 4; ++o) {
                 for (int i = 0; i < 2; ++i) {
                     const double g0 = p.w1[0][dx][o][i], g1 = p.w1[1][dx][o][i], g2 = p.w1[2][dx][o][i];
-                    q.w1[0][dx][o][i] = (float)g0;
-                    q.w1[1][dx][o][i] = (float)(0.5 * (g0 + g1 + g2));
-                    q.w1[2][dx][o][i] = (float)(0.5 * (g0 - g1 + g2));
-                    q.w1[3][dx][o][i] = (float)g2;
+                    q.w1[dx][o][i][0] = (float)g0;
+                    q.w1[dx][o][i][1] = (float)(0.5 * (g0 + g1 + g2));
+                    q.w1[dx][o][i][2] = (float)(0.5 * (g0 - g1 + g2));
+                    q.w1[dx][o][i][3] = (float)g2;
                 }
                 for (int i = 0; i < 4; ++i) {
                     const double g0 = p.w3[0][dx][o][i], g1 = p.w3[1][dx][o][i], g2 = p.w3[2][dx][o][i];
-                    q.w3[0][dx][o][i] = (float)g0;
-                    q.w3[1][dx][o][i] = (float)(0.5 * (g0 + g1 + g2));
-                    q.w3[2][dx][o][i] = (float)(0.5 * (g0 - g1 + g2));
-                    q.w3[3][dx][o][i] = (float)g2;
+                    q.w3[dx][o][i][0] = (float)g0;
+                    q.w3[dx][o][i][1] = (float)(0.5 * (g0 + g1 + g2));
+                    q.w3[dx][o][i][2] = (float)(0.5 * (g0 - g1 + g2));
+                    q.w3[dx][o][i][3] = (float)g2;
                 }
             }
     }
