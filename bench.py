@@ -353,7 +353,7 @@ def run_also(args, nf, hps, ck, x, y, dev, rank, world, sm_mhz, row):
         "metric": "patches_per_sec_sample", "value": world * B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 20,
         "config": {"workload": "sample (temperature 0.6, in-kernel Philox) Noise Flow, batch %d per GPU, cam S6 / ISO 100" % B,
                    "baseline_config": 3, "per_gpu_batch": B},
-        "roofline": _hbm_roofline(B, ALG_BYTES_SAMPLE, ms, "nf_chain_kernel<false>",
+        "roofline": _hbm_roofline(B, ALG_BYTES_SAMPLE, ms, "nf_chain_wino_kernel<false>" if args.tc in (-1, 0, 4) else "nf_chain_kernel<false>",
                                   _traffic("sample_%d" % B), "binding roof is the FP32 FMA pipe (roofline_fp32)"),
         "roofline_fp32": _fp32_roofline(B, conv_flop, ms, sm_mhz), "gpu_launches": world * 20}
     # the same sampler and log_prob on the hybrid kernel (conv-3 on tcgen05; opt-in: nf_model_set_tensor_cores 2)
@@ -374,6 +374,15 @@ def run_also(args, nf, hps, ck, x, y, dev, rank, world, sm_mhz, row):
         "roofline": _hbm_roofline(B, ALG_BYTES_LOG_PROB, ms, "nf_chain_hyb_kernel<true>", None, "binding roof is the FP32 FMA pipe (roofline_fp32)"),
         "roofline_fp32": _fp32_roofline(B, conv_flop, ms, sm_mhz), "gpu_launches": world * 20 * 2}
     nf.set_tensor_cores(5)   # and on the direct-form all-fp32 kernel (round 1-4's default; the library default is the Winograd form)
+    xs = torch.empty_like(x)
+    ms = _timed(lambda i: _lib.check(lib.nf_sample(eng.handle, y.data_ptr(), None, row, B, 0.6, None, 7, i, rank * B, xs.data_ptr(), stream)),
+                20, 3, dev, world)
+    out["sample_%d_direct_kernel" % B] = {
+        "metric": "patches_per_sec_sample", "value": world * B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 20,
+        "config": {"workload": "sample, direct-form all-fp32 kernel (nf_model_set_tensor_cores 5), batch %d per GPU" % B, "per_gpu_batch": B},
+        "roofline": _hbm_roofline(B, ALG_BYTES_SAMPLE, ms, "nf_chain_kernel<false>", None, "binding roof is the FP32 FMA pipe (roofline_fp32)"),
+        "roofline_fp32": _fp32_roofline(B, conv_flop, ms, sm_mhz), "gpu_launches": world * 20}
+    del xs
     ms = _timed(lambda i: log_prob_step(eng.handle, x, y, B), 20, 3, dev, world)
     out["log_prob_%d_direct_kernel" % B] = {
         "metric": "patches_per_sec_nll", "value": world * B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": 20,
@@ -723,7 +732,7 @@ def main():
            "config": workload_config(args.mode, hps.arch, B, world, args.width, args.clean), "mean_nll_per_dim": mean_nll,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "peak_source": peak_src, "kernel": "nf_scale_stream_kernel" if "unc" not in hps.arch else (("nf_chain_hyb_kernel" if (args.tc == 2 or (args.tc == 3 and args.mode == "sample")) else
-                                                                                                                         ("nf_chain_wino_kernel" if (args.tc == 4 or (args.tc in (-1, 0, 3) and args.mode != "sample")) else "nf_chain_kernel"))
+                                                                                                                         ("nf_chain_wino_kernel" if (args.tc in (-1, 0, 4) or (args.tc == 3 and args.mode != "sample")) else "nf_chain_kernel"))
                                                                                                                         if args.width == 4 else "nf_wide_chain_kernel"),
                         "kernel_ms": kms, "alg_bytes_per_patch": alg,
                         "note": ("binding roof is the FP32 FMA pipe (see roofline_fp32), not HBM" if n_couplings else

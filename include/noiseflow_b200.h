@@ -121,15 +121,14 @@ int nf_model_end_update(nf_model* m);
 /* Launch tuning: resident patches (warps) per CTA in [1, 16] and CTA count (0 = one per SM). */
 int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas);
 /* Width 4 -- which kernel runs full-chain / range calls (batch-statistics probes always use the direct-form all-fp32 kernel):
- *   0 (default): all-fp32; data -> latent (nf_log_prob / nf_inverse) on the vertical-Winograd kernel (csrc/nf_wino.cu: both 3x3
- *      convolutions of every coupling net as F(2,3) along the image rows, +5 %; differs from the direct form by fp32 rounding
- *      only), latent -> data (nf_sample / nf_forward) on the direct-form kernel (csrc/nf_kernels.cu);
- *   5: the direct-form kernel everywhere;   4: the Winograd kernel everywhere;
+ *   0 (default) = 4: the all-fp32 vertical-Winograd kernel (csrc/nf_wino.cu: both 3x3 convolutions of every coupling net as
+ *      F(2,3) along the image rows; +10 % data -> latent, +3 % latent -> data; differs from the direct form by fp32 rounding only);
+ *   5: the all-fp32 direct-form kernel (csrc/nf_kernels.cu) everywhere;
  *   2: the hybrid kernel (csrc/nf_hybrid.cu): conv-3 of every coupling net on the tensor cores (tcgen05.mma, fp16 hi/lo-split
  *      operands, fp32 accumulation in TMEM), everything else fp32 -- |dNLL| vs the fp32 kernels < 1e-6 nats/dim on the shipped
  *      model; 22 instead of 24 mantissa bits inside conv-3, which a stress model with O(1) random weights shows as 2e-5
  *      instead of 1e-5 relative error of a sampled patch -- hence opt-in;
- *   3: the hybrid kernel for the latent -> data direction only (where it is 7 % faster), the default otherwise;
+ *   3: the hybrid kernel for the latent -> data direction only (7 % faster than the direct form there), the default otherwise;
  *   1: older experiment -- both 3x3 convolutions as bf16 hi/lo implicit GEMMs (csrc/nf_tc.cu), full-chain calls with explicit
  *      inputs only; slower than 0.
  * Widths 32 ... 512 -- the tensor-core kernels (csrc/nf_wide_tc.cu, nf_wide_tcs.cu: all three convolutions as tcgen05.mma

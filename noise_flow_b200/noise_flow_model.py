@@ -252,8 +252,8 @@ class NoiseFlow(object):
 
     def set_tensor_cores(self, enable=True):
         """Width 4 -- which chain kernel runs (C ABI ``nf_model_set_tensor_cores``):
-        ``"default"`` (0): all-fp32; data -> latent on the vertical-Winograd kernel, latent -> data on the direct-form kernel;
-        ``False`` / ``"direct"`` (5): the direct-form all-fp32 kernel everywhere;  ``"winograd"`` (4): the Winograd kernel everywhere;
+        ``"default"`` (0) = ``"winograd"`` (4): the all-fp32 vertical-Winograd kernel in both directions;
+        ``False`` / ``"direct"`` (5): the direct-form all-fp32 kernel everywhere;
         ``"hybrid"`` (2): conv-3 of every coupling net on the tensor cores (tcgen05, fp16 hi/lo split operands) in both
         directions;  ``"auto"`` (3): hybrid for sampling / forward (where it is faster), default otherwise;
         ``True`` (1): the older experimental kernel with both 3x3 convolutions as bf16 hi/lo implicit GEMMs.
