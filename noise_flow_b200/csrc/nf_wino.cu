@@ -33,7 +33,7 @@ struct alignas(16) CouplingW {
     float a[4][4];
     float ainv[4][4];
     float w1[3][4][2][4];   // [dx][o][i][j]: the four transformed taps of one (dx, out, in) are one LDCU.128
-    float w2[4][4];
+    float w2[4][4][2];      // [o][i] twice: the 1x1 conv runs packed over the two rows of a step
     float w3[3][4][4][4];   // [dx][o][i][j]
     float b1[4];
     float b2[4];
@@ -163,15 +163,14 @@ __device__ __forceinline__ void wino_step(const CP& P, WarpSmemW& s, const ZStor
             ha[o] = fmaxf((m01[o].x + sb) + m23[o].x, 0.f);                                // y0 = m0 + m1 + m2; BN folded, ReLU
             hb[o] = fmaxf((sb - m23[o].x) - m23[o].y, 0.f);                                // y1 = m1 - m2 - m3
         }
-        const float2 a01 = make_float2(ha[0], ha[1]), a23 = make_float2(ha[2], ha[3]);
-        const float2 b01 = make_float2(hb[0], hb[1]), b23 = make_float2(hb[2], hb[3]);
         float ea[4], eb[4];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            const float2 w01 = ld2(&P.w2[o][0]), w23 = ld2(&P.w2[o][2]);
-            const float2 ua = ffma2(a23, w23, ffma2(a01, w01, zero2)), ub = ffma2(b23, w23, ffma2(b01, w01, zero2));
-            ea[o] = fmaxf(ua.x + ua.y + P.b2[o], 0.f);
-            eb[o] = fmaxf(ub.x + ub.y + P.b2[o], 0.f);
+        for (int o = 0; o < 4; ++o) {   // 1x1 conv, packed over the two rows: channel c of (row a, row b) times (w, w)
+            float2 acc = ffma2(make_float2(ha[0], hb[0]), ld2(&P.w2[o][0][0]), zero2);
+#pragma unroll
+            for (int c = 1; c < 4; ++c) acc = ffma2(make_float2(ha[c], hb[c]), ld2(&P.w2[o][c][0]), acc);
+            ea[o] = fmaxf(acc.x + P.b2[o], 0.f);
+            eb[o] = fmaxf(acc.y + P.b2[o], 0.f);
         }
         float4 e2 = make_float4(ea[0], ea[1], ea[2], ea[3]), e3 = make_float4(eb[0], eb[1], eb[2], eb[3]);
         if (GUARDED && u == 1) e2 = make_float4(0.f, 0.f, 0.f, 0.f);    // h2 row -1: SAME padding of conv-3
@@ -353,7 +352,7 @@ static void to_winograd(const NfModelParams& mp, ModelParamsW& w) {
     for (int k = 0; k < NF_MAX_COUPLINGS; ++k) {
         const NfCouplingP& p = mp.cp[k];
         CouplingW& q = w.cp[k];
-        for (int i = 0; i < 16; ++i) { (&q.a[0][0])[i] = (&p.a[0][0])[i]; (&q.ainv[0][0])[i] = (&p.ainv[0][0])[i]; (&q.w2[0][0])[i] = (&p.w2[0][0])[i]; }
+        for (int i = 0; i < 16; ++i) { (&q.a[0][0])[i] = (&p.a[0][0])[i]; (&q.ainv[0][0])[i] = (&p.ainv[0][0])[i]; (&q.w2[0][0][0])[2 * i] = (&q.w2[0][0][0])[2 * i + 1] = (&p.w2[0][0])[i]; }
         for (int i = 0; i < 4; ++i) { q.b1[i] = p.b1[i]; q.b2[i] = p.b2[i]; }
         for (int i = 0; i < 36; ++i) (&q.b3[0][0][0])[i] = (&p.b3[0][0][0])[i];
         q.scale = p.scale;
