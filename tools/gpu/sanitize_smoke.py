@@ -38,7 +38,15 @@ if CHAIN:
         xr_h = nf.forward(z_h, None, yy=y, iso=[100.0], cam=[2.0])
         print("hybrid kernel: |nll - fp32 kernel| %.2e nats/dim, round trip %.2e" % (
             float((nll_h - nll).abs().max()) / 4096, float(np.abs(xr_h.cpu().numpy() - x).max())))
-        nf.set_tensor_cores(False)
+        nf.set_tensor_cores("direct")
+        nll_d, _ = nf._loss(x, y, iso=[100.0], cam=[2.0])
+        nf.set_tensor_cores("winograd")                      # round 5: the default chain kernel (vertical Winograd F(2,3))
+        nll_w, _, z_w = nf._loss(x, y, iso=[100.0], cam=[2.0], return_z=True)
+        xs_w = nf.sample(y, 0.6, y, iso=[100.0], cam=[2.0], seed=3, offset=0)
+        xr_w = nf.forward(z_w, None, yy=y, iso=[100.0], cam=[2.0])
+        print("winograd kernel: |nll - direct form| %.2e nats/dim, round trip %.2e" % (
+            float((nll_w - nll_d).abs().max()) / 4096, float(np.abs(xr_w.cpu().numpy() - x).max())))
+        nf.set_tensor_cores("default")
 # batch-statistics chain of a small batch: one cooperative kernel (td_bs_chain_kernel), both directions
 nb = min(n, 9)
 nll_c, _ = nf._loss(x[:nb], y[:nb], iso=[100.0], cam=[2.0], is_training=True)
