@@ -146,6 +146,7 @@ __device__ __forceinline__ void wino_step(const CP& P, WarpSmemW& s, const ZStor
         if (do_c) ld_rows(zs, 2 * u - 2, zc0, zc1);
     }
     // ---------------- stage A
+    float4 tx[2], th[4];
     {
         float2 d2 = zero2, d3 = zero2;
         if (do_a) {
@@ -156,26 +157,35 @@ __device__ __forceinline__ void wino_step(const CP& P, WarpSmemW& s, const ZStor
             d2 = lo2(za0);
             d3 = lo2(za1);
         }
-        {   // channel c: (T0, T1, T2, T3) = (d0 - d2, d1 + d2, d2 - d1, d1 - d3)
-            s.xw[0][0][lane + 1] = make_float4(xp[0].x - d2.x, xp[1].x + d2.x, d2.x - xp[1].x, xp[1].x - d3.x);
-            s.xw[0][1][lane + 1] = make_float4(xp[0].y - d2.y, xp[1].y + d2.y, d2.y - xp[1].y, xp[1].y - d3.y);
-        }
+        // channel c: (T0, T1, T2, T3) = (d0 - d2, d1 + d2, d2 - d1, d1 - d3)
+        tx[0] = make_float4(xp[0].x - d2.x, xp[1].x + d2.x, d2.x - xp[1].x, xp[1].x - d3.x);
+        tx[1] = make_float4(xp[0].y - d2.y, xp[1].y + d2.y, d2.y - xp[1].y, xp[1].y - d3.y);
+        s.xw[0][0][lane + 1] = tx[0];
+        s.xw[0][1][lane + 1] = tx[1];
         xp[0] = d2;
         xp[1] = d3;
     }
-    __syncwarp();
-    // ---------------- stage B
+    // ---------------- stage B.  The centre tap is this lane's own tile (still in registers): its FFMA2 run BEFORE the
+    // __syncwarp that publishes the tile to the neighbours and cover the shared-memory round trip of the other two taps.
     {
         float2 m01[4], m23[4];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                m01[o] = ffma2(lo2(tx[c]), ld2(&P.w1[1][o][c][0]), c == 0 ? zero2 : m01[o]);
+                m23[o] = ffma2(hi2(tx[c]), ld2(&P.w1[1][o][c][2]), c == 0 ? zero2 : m23[o]);
+            }
+        __syncwarp();
+#pragma unroll
+        for (int dx = 0; dx < 3; dx += 2) {
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const float4 t = s.xw[0][c][lane + dx];
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
-                    m01[o] = ffma2(lo2(t), ld2(&P.w1[dx][o][c][0]), (dx == 0 && c == 0) ? zero2 : m01[o]);
-                    m23[o] = ffma2(hi2(t), ld2(&P.w1[dx][o][c][2]), (dx == 0 && c == 0) ? zero2 : m23[o]);
+                    m01[o] = ffma2(lo2(t), ld2(&P.w1[dx][o][c][0]), m01[o]);
+                    m23[o] = ffma2(hi2(t), ld2(&P.w1[dx][o][c][2]), m23[o]);
                 }
             }
         }
@@ -198,28 +208,35 @@ __device__ __forceinline__ void wino_step(const CP& P, WarpSmemW& s, const ZStor
         float4 e2 = make_float4(ea[0], ea[1], ea[2], ea[3]), e3 = make_float4(eb[0], eb[1], eb[2], eb[3]);
         if (GUARDED && u == 0) e2 = make_float4(0.f, 0.f, 0.f, 0.f);    // h2 row -1: SAME padding of conv-3
         if (GUARDED && u == 16) e3 = make_float4(0.f, 0.f, 0.f, 0.f);   // h2 row 32
-        {
-            s.hw[0][0][lane + 1] = make_float4(hp[0].x - e2.x, hp[1].x + e2.x, e2.x - hp[1].x, hp[1].x - e3.x);
-            s.hw[0][1][lane + 1] = make_float4(hp[0].y - e2.y, hp[1].y + e2.y, e2.y - hp[1].y, hp[1].y - e3.y);
-            s.hw[0][2][lane + 1] = make_float4(hp[0].z - e2.z, hp[1].z + e2.z, e2.z - hp[1].z, hp[1].z - e3.z);
-            s.hw[0][3][lane + 1] = make_float4(hp[0].w - e2.w, hp[1].w + e2.w, e2.w - hp[1].w, hp[1].w - e3.w);
-        }
+        th[0] = make_float4(hp[0].x - e2.x, hp[1].x + e2.x, e2.x - hp[1].x, hp[1].x - e3.x);
+        th[1] = make_float4(hp[0].y - e2.y, hp[1].y + e2.y, e2.y - hp[1].y, hp[1].y - e3.y);
+        th[2] = make_float4(hp[0].z - e2.z, hp[1].z + e2.z, e2.z - hp[1].z, hp[1].z - e3.z);
+        th[3] = make_float4(hp[0].w - e2.w, hp[1].w + e2.w, e2.w - hp[1].w, hp[1].w - e3.w);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s.hw[0][c][lane + 1] = th[c];
         hp[0] = e2;
         hp[1] = e3;
     }
-    __syncwarp();
-    // ---------------- stage C
-    if (do_c) {
-        float2 m01[4], m23[4];
+    // ---------------- stage C (centre tap from registers before the __syncwarp, as in stage B)
+    float2 m01[4], m23[4];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            m01[o] = ffma2(lo2(th[c]), ld2(&P.w3[1][o][c][0]), c == 0 ? zero2 : m01[o]);
+            m23[o] = ffma2(hi2(th[c]), ld2(&P.w3[1][o][c][2]), c == 0 ? zero2 : m23[o]);
+        }
+    __syncwarp();
+    if (do_c) {
+#pragma unroll
+        for (int dx = 0; dx < 3; dx += 2) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const float4 t = s.hw[0][c][lane + dx];
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
-                    m01[o] = ffma2(lo2(t), ld2(&P.w3[dx][o][c][0]), (dx == 0 && c == 0) ? zero2 : m01[o]);
-                    m23[o] = ffma2(hi2(t), ld2(&P.w3[dx][o][c][2]), (dx == 0 && c == 0) ? zero2 : m23[o]);
+                    m01[o] = ffma2(lo2(t), ld2(&P.w3[dx][o][c][0]), m01[o]);
+                    m23[o] = ffma2(hi2(t), ld2(&P.w3[dx][o][c][2]), m23[o]);
                 }
             }
         }
