@@ -86,26 +86,6 @@ __device__ __forceinline__ void st_rows(const ZStore& zs, int r, const float4& a
                     "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)) : "memory");
 }
 
-__device__ __forceinline__ void ld_rows4(const ZStore& zs, int r, float4& a, float4& b, float4& c, float4& d) {   // rows r .. r + 3 (r even)
-    uint32_t v[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(zs.taddr + (uint32_t)(r * 4)));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
-    a = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-    b = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-    c = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
-    d = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
-}
-__device__ __forceinline__ void st_rows4(const ZStore& zs, int r, const float4& a, const float4& b, const float4& c, const float4& d) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 :: "r"(zs.taddr + (uint32_t)(r * 4)), "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
-                    "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)),
-                    "r"(__float_as_uint(c.x)), "r"(__float_as_uint(c.y)), "r"(__float_as_uint(c.z)), "r"(__float_as_uint(c.w)),
-                    "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y)), "r"(__float_as_uint(d.z)), "r"(__float_as_uint(d.w)) : "memory");
-}
-
 // affine update of one pixel (stage C tail)
 template <bool INV>
 __device__ __forceinline__ void affine(const float (&h3)[4], const float scale, float4& z, float& ldj, const bool has_mix, const float2 (&am)[4][2]) {
@@ -124,8 +104,8 @@ __device__ __forceinline__ void affine(const float (&h3)[4], const float scale, 
 }
 
 // Pair step u = 0..16.  The three stages of a step hand their tile to the NEXT STAGE OF THE SAME STEP: two __syncwarp per
-// step, single-buffered tiles, 3 guarded steps per pass (u = 0, 1, 16), and the four z rows a step touches are adjacent in
-// tensor memory (one tcgen05.ld.x16 / st.x16).  (A first version passed tiles to the NEXT step -- one __syncwarp, stages free
+// step, single-buffered tiles, 3 guarded steps per pass (u = 0, 1, 16), and the rows stage A mixes stay in registers until stage C
+// of the next step finishes them (one tcgen05.ld.x8 and one st.x8 per step).  (A first version passed tiles to the NEXT step -- one __syncwarp, stages free
 // to interleave, but 19 steps of which 7 guarded: 11.56 instead of 11.92 M patches/s.)
 //   stage A (rows 2u, 2u+1)  : z <- z.A (inverse only); with the retained x0 rows 2u-2, 2u-1 publish the conv-1 input tile
 //                              whose outputs are h1 rows (2u-1, 2u)
@@ -134,17 +114,15 @@ __device__ __forceinline__ void affine(const float (&h3)[4], const float scale, 
 //   stage C: conv-3 rows (2u-2, 2u-1) + edge-indicator bias -> tanh/exp affine update of z + log-det
 template <bool INV, bool GUARDED, class CP>
 __device__ __forceinline__ void wino_step(const CP& P, WarpSmemW& s, const ZStore& zs, const int lane, const int u, const bool has_mix,
-                                          float2 (&xp)[2], float4 (&hp)[2], float& ldj, const float2 (&am)[4][2], const float (&b3m)[4]) {
+                                          float2 (&xp)[2], float4 (&hp)[2], float4 (&zp)[2], float& ldj, const float2 (&am)[4][2], const float (&b3m)[4]) {
     const float2 zero2 = make_float2(0.f, 0.f);
     const bool do_a = !GUARDED || u <= 15;
     const bool do_c = !GUARDED || u >= 1;
+    // Rows (2u, 2u+1) come from tensor memory; rows (2u-2, 2u-1), which stage C finishes, are the (mixed) rows stage A of the
+    // previous step left in registers: a row is read once and written once per coupling.
     zs.commit();
-    float4 za0 = make_float4(0.f, 0.f, 0.f, 0.f), za1 = za0, zc0 = za0, zc1 = za0;
-    if (!GUARDED) ld_rows4(zs, 2 * u - 2, zc0, zc1, za0, za1);
-    else {
-        if (do_a) ld_rows(zs, 2 * u, za0, za1);
-        if (do_c) ld_rows(zs, 2 * u - 2, zc0, zc1);
-    }
+    float4 za0 = make_float4(0.f, 0.f, 0.f, 0.f), za1 = za0, zc0 = zp[0], zc1 = zp[1];
+    if (do_a) ld_rows(zs, 2 * u, za0, za1);
     // ---------------- stage A
     float4 tx[2], th[4];
     {
@@ -255,11 +233,9 @@ __device__ __forceinline__ void wino_step(const CP& P, WarpSmemW& s, const ZStor
         affine<INV>(h3a, P.scale, zc0, ldj, has_mix, am);
         affine<INV>(h3b, P.scale, zc1, ldj, has_mix, am);
     }
-    if (!GUARDED) st_rows4(zs, 2 * u - 2, zc0, zc1, za0, za1);
-    else {
-        if (do_a && INV && has_mix) st_rows(zs, 2 * u, za0, za1);
-        if (do_c) st_rows(zs, 2 * u - 2, zc0, zc1);
-    }
+    if (do_c) st_rows(zs, 2 * u - 2, zc0, zc1);
+    zp[0] = za0;
+    zp[1] = za1;
 }
 
 template <bool INV, class CP>
@@ -272,10 +248,11 @@ __device__ __forceinline__ void wino_pass(const CP& P, WarpSmemW& s, const ZStor
     for (int o = 0; o < 4; ++o) b3m[o] = lane == 0 ? P.b3[1][0][o] : (lane == 31 ? P.b3[1][2][o] : P.b3[1][1][o]);
     float2 xp[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     float4 hp[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    float4 zp[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
 #pragma unroll 1
     for (int u = 0; u < 17; ++u) {
-        if (u >= 2 && u <= 15) wino_step<INV, false>(P, s, zs, lane, u, has_mix, xp, hp, ldj, am, b3m);
-        else                   wino_step<INV, true>(P, s, zs, lane, u, has_mix, xp, hp, ldj, am, b3m);
+        if (u >= 2 && u <= 15) wino_step<INV, false>(P, s, zs, lane, u, has_mix, xp, hp, zp, ldj, am, b3m);
+        else                   wino_step<INV, true>(P, s, zs, lane, u, has_mix, xp, hp, zp, ldj, am, b3m);
     }
     __syncwarp();
 }
