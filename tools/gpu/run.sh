@@ -7,6 +7,8 @@
 #   ncu-chain        ncu --set full of the shipped chain kernels      ncu-wide W            ... of the tensor-core wide kernel at width W
 #   launches [args]  ncu launch list of bench.py [args]               probe                 tools/tc_probe2.cu + PCIe probe
 #   sanitize         compute-sanitizer smoke (tools/gpu/sanitize_smoke.py)
+# Round 5 companions: tools/gpu/ab_chain.sh (A/B of the three width-4 chain kernels), sanitize_chain.sh (sanitizer over them),
+# final_evidence.sh (suite + default bench + ncu --set full of the shipped chain kernels + launch list in one call).
 set -u
 mkdir -p gpurun_out
 task=${1:-suite}; shift || true
