@@ -92,8 +92,8 @@ __device__ __forceinline__ void st_rows(const ZStore& zs, int r, const float4& a
 // channel.  shift = h3[0:2], log_scale = scale * tanh(h3[2:4])                                       (layers.py:362 / :342)
 template <bool INV>
 __device__ __forceinline__ void affine(const float (&h3)[4], const float s2, float4& z, float& rsum, const bool has_mix, const float2 (&am)[4][2]) {
-    const float r0 = __fdividef(1.f, exp2f(h3[2] * 2.885390081777927f) + 1.f);
-    const float r1 = __fdividef(1.f, exp2f(h3[3] * 2.885390081777927f) + 1.f);
+    const float r0 = __fdividef(1.f, exp2f(h3[2]) + 1.f);                    // h3[2:4] arrive times 2 log2(e): to_winograd folds it
+    const float r1 = __fdividef(1.f, exp2f(h3[3]) + 1.f);                    // into conv-3's filters and bias
     rsum += r0 + r1;
     if (INV) {
         z.z = fmaf(z.z, exp2f(fmaf(-2.f * s2, r0, s2)), h3[0]);              // layers.py:363-367
@@ -323,6 +323,9 @@ nf_chain_wino_kernel(const __grid_constant__ ModelParamsW mp, const NfChainArgs 
 
         float ldj = 0.f;
         const int l0 = INV ? a.first_layer : a.last_layer - 1, l1 = INV ? a.last_layer : a.first_layer - 1, dl = INV ? 1 : -1;
+        // The 16 warps of a CTA move through the chain in lock step (the __syncthreads below), so they would all wait on HBM
+        // at the same time: in the prologue (in: 16 KB per patch) and at the SDN layer (y: 16 KB).  Two layers (~45 us) before
+        // either is read, lane 0 asks for it as one bulk L2 prefetch: the reads then hit L2.  Footprint in L2: <= 32 KB per warp.
         for (int l = l0; l != l1; l += dl) {
             const int op = mp.op[l], slot = mp.slot[l];
             switch (op) {
@@ -383,7 +386,9 @@ static void to_winograd(const NfModelParams& mp, ModelParamsW& w) {
         CouplingW& q = w.cp[k];
         for (int i = 0; i < 16; ++i) { (&q.a[0][0])[i] = (&p.a[0][0])[i]; (&q.ainv[0][0])[i] = (&p.ainv[0][0])[i]; (&q.w2[0][0][0])[2 * i] = (&q.w2[0][0][0])[2 * i + 1] = (&p.w2[0][0])[i]; }
         for (int i = 0; i < 4; ++i) { q.b1[i] = p.b1[i]; q.b2[i] = p.b2[i]; }
-        for (int i = 0; i < 36; ++i) (&q.b3[0][0][0])[i] = (&p.b3[0][0][0])[i];
+        // conv-3's outputs 2, 3 only feed tanh: they leave the convolution times 2 log2(e), the argument exp2 wants (affine())
+        const double k23 = 2.8853900817779268;
+        for (int i = 0; i < 36; ++i) (&q.b3[0][0][0])[i] = (float)(((i & 3) >= 2 ? k23 : 1.0) * (double)(&p.b3[0][0][0])[i]);
         q.scale = p.scale;
         q.has_mix = p.has_mix;
         q.pad_[0] = q.pad_[1] = 0.f;
@@ -397,7 +402,8 @@ static void to_winograd(const NfModelParams& mp, ModelParamsW& w) {
                     q.w1[dx][o][i][3] = (float)g2;
                 }
                 for (int i = 0; i < 4; ++i) {
-                    const double g0 = p.w3[0][dx][o][i], g1 = p.w3[1][dx][o][i], g2 = p.w3[2][dx][o][i];
+                    const double ko = o >= 2 ? k23 : 1.0;
+                    const double g0 = ko * p.w3[0][dx][o][i], g1 = ko * p.w3[1][dx][o][i], g2 = ko * p.w3[2][dx][o][i];
                     q.w3[dx][o][i][0] = (float)g0;
                     q.w3[dx][o][i][1] = (float)(0.5 * (g0 + g1 + g2));
                     q.w3[dx][o][i][2] = (float)(0.5 * (g0 - g1 + g2));
