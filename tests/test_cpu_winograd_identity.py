@@ -34,3 +34,30 @@ def test_same_padding_rows_enter_as_zero_inputs():
         m = U * np.array([d[0] - d[2], d[1] + d[2], d[2] - d[1], d[1] - d[3]])
         out[2 * k], out[2 * k + 1] = m[0] + m[1] + m[2], m[1] - m[2] - m[3]
     assert np.allclose(out, direct, atol=1e-12)
+
+
+def test_affine_tail_from_one_reciprocal():
+    """The kernel's affine tail (csrc/nf_wino.cu `affine`): conv-3's tanh outputs arrive times 2 log2(e) (folded into the filters
+    and bias by `to_winograd`), r = 1 / (exp2(h') + 1), tanh(h) = 1 - 2 r, exp(+-scale * tanh(h)) = exp2(+-(s2 - 2 s2 r)) with
+    s2 = scale * log2(e), and the log-det of a pass is scale * (count - 2 sum r).  In fp32 this has to stay within the
+    kernel's parity bounds (|dNLL| 1e-6 nats/dim, z 2e-5 relative) of the reference form, layers.py:342-372."""
+    rng = np.random.RandomState(2)
+    scale = np.float32(0.7)
+    h = (rng.randn(64, 1024) * 3.0).astype(np.float32)               # pre-tanh outputs of one lane-column set, wide range
+    z = rng.randn(64, 1024).astype(np.float32)
+    shift = rng.randn(64, 1024).astype(np.float32)
+    k23 = np.float32(2.8853900817779268)
+    r = np.float32(1.0) / (np.exp2(h * k23, dtype=np.float32) + np.float32(1.0))
+    s2 = np.float32(scale * np.float32(1.4426950408889634))
+    x_kernel = z * np.exp2(np.float32(-2.0) * s2 * r + s2, dtype=np.float32) + shift          # inverse direction
+    ls = scale.astype(np.float64) * np.tanh(h.astype(np.float64))
+    x_ref = z.astype(np.float64) * np.exp(ls) + shift
+    assert np.abs(x_kernel - x_ref).max() <= 2e-6 * np.abs(x_ref).max()
+    z_kernel = (x_kernel - shift) * np.exp2(np.float32(2.0) * s2 * r - s2, dtype=np.float32)  # forward direction undoes it
+    assert np.abs(z_kernel - z).max() <= 1e-5 * np.abs(z).max()      # (x - shift cancels: absolute, not relative, accuracy)
+    ldj_kernel = scale * (np.float32(h.size) - np.float32(2.0) * r.sum(dtype=np.float32))
+    assert abs(float(ldj_kernel) - ls.sum()) / h.size < 1e-6          # nats per dimension
+    # the extremes saturate instead of overflowing: exp2(+inf) -> r = 0 -> tanh = 1; exp2(-inf) -> r = 1 -> tanh = -1
+    with np.errstate(over="ignore"):
+        big = np.float32(1.0) / (np.exp2(np.float32([400.0, -400.0]), dtype=np.float32) + np.float32(1.0))
+    assert big.tolist() == [0.0, 1.0]
