@@ -16,6 +16,7 @@
 // 651-674; noise_flow_model.py:394-480); results differ from the direct form by fp32 rounding only.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "nf_params.h"
 #include "nf_kernels.h"
 #include "nf_rng.cuh"
@@ -275,7 +276,7 @@ __device__ __forceinline__ void wino_dispatch(const ModelParamsW& mp, WarpSmemW&
     }
 }
 
-template <bool INV>
+template <bool INV, int TMEM_COLS>
 __global__ void __launch_bounds__(NF_MAX_CTA_THREADS, 1)
 nf_chain_wino_kernel(const __grid_constant__ ModelParamsW mp, const NfChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -284,9 +285,13 @@ nf_chain_wino_kernel(const __grid_constant__ ModelParamsW mp, const NfChainArgs 
     WarpSmemW& s = reinterpret_cast<WarpSmemW*>(smem_raw)[warp];
 
     __shared__ uint32_t tmem_base_smem;
-    if (warp == 0) {   // the whole tensor memory of this SM: 512 columns x 128 lanes = 16 resident patches
+    // 128 tensor-memory columns per group of four warps (a power of two): 16 warps take the whole tensor memory of the SM
+    // (512 columns x 128 lanes = 16 resident patches); two 8-warp CTAs per SM take half each (launch_chain_wino)
+    // (TMEM_COLS is a template parameter: as a run-time value it flips ptxas' register allocation of the coupling step)
+    if (warp == 0) {
+        const uint32_t tmem_cols = TMEM_COLS;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_smem)), "r"(512u) : "memory");
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_smem)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -370,7 +375,10 @@ nf_chain_wino_kernel(const __grid_constant__ ModelParamsW mp, const NfChainArgs 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_smem), "r"(512u) : "memory");
+    if (warp == 0) {
+        const uint32_t tmem_cols = TMEM_COLS;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_smem), "r"(tmem_cols) : "memory");
+    }
 }
 
 // host: G g of the vertical taps, in double
@@ -426,26 +434,37 @@ cudaError_t launch_chain_wino(const NfModelParams& mp, const NfChainArgs& args, 
     if (args.n <= 0) return cudaSuccess;
     wino::ModelParamsW w;
     wino::to_winograd(mp, w);
-    int warps = NF_MAX_WARPS_PER_CTA;
+    // CTA shape.  One 16-warp CTA per SM owns the whole tensor memory; two 8-warp CTAs take half each, the layer lock step then
+    // binds 8 warps and the two halves of an SM drift apart.  Measured at 65 536 patches (profiles/r06_ab_cta_warps.log):
+    // sampling with in-kernel Philox 10.76 -> 11.79 M patches/s with two CTAs (one half's FMA-bound coupling passes cover the
+    // other half's ALU-bound Philox prologue), log_prob 12.58 -> 12.44 M.  So: two CTAs when the kernel draws its own noise,
+    // one otherwise; NF_WINO_CTA_WARPS=8 / 16 forces either (A/B switch).
+    static const int forced_warps = [] { const char* e = getenv("NF_WINO_CTA_WARPS"); const int v = e ? atoi(e) : 0; return (v == 8 || v == 16) ? v : 0; }();
+    const int cta_warps = forced_warps ? forced_warps : ((!inverse && args.in == nullptr) ? 8 : NF_MAX_WARPS_PER_CTA);
+    num_sms *= NF_MAX_WARPS_PER_CTA / cta_warps;   // resident CTAs
+    int warps = cta_warps;
     {   // CTA shape against wave quantisation, as launch_chain
         const long long g = args.n < (long long)num_sms ? args.n : (long long)num_sms;
         const long long per_sm = (args.n + g - 1) / g, rounds = (per_sm + warps - 1) / warps;
         warps = (int)((per_sm + rounds - 1) / rounds);
     }
     const size_t smem = (size_t)warps * sizeof(wino::WarpSmemW);
-    static bool attr_done[NF_MAX_DEVICES][2] = {};
+    // CTAs of more than 8 warps own the whole tensor memory (512 columns); smaller ones take 256, so two fit on an SM
+    typedef void (*kern_t)(const wino::ModelParamsW, const NfChainArgs);
+    const int half = cta_warps <= 8 ? 1 : 0;
+    const kern_t kern = inverse ? (half ? wino::nf_chain_wino_kernel<true, 256> : wino::nf_chain_wino_kernel<true, 512>)
+                                : (half ? wino::nf_chain_wino_kernel<false, 256> : wino::nf_chain_wino_kernel<false, 512>);
+    static bool attr_done[NF_MAX_DEVICES][2][2] = {};
     const int dev = device_slot(), k = inverse ? 0 : 1;
-    if (!attr_done[dev][k]) {
+    if (!attr_done[dev][k][half]) {
         const int max_smem = NF_MAX_WARPS_PER_CTA * (int)sizeof(wino::WarpSmemW);
-        const cudaError_t e = inverse ? cudaFuncSetAttribute(wino::nf_chain_wino_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
-                                      : cudaFuncSetAttribute(wino::nf_chain_wino_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        const cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) return e;
-        attr_done[dev][k] = true;
+        attr_done[dev][k][half] = true;
     }
     long long ctas = (args.n + warps - 1) / warps;
     if (ctas > num_sms) ctas = num_sms;
-    if (inverse) wino::nf_chain_wino_kernel<true><<<(unsigned)ctas, warps * 32, smem, stream>>>(w, args);
-    else         wino::nf_chain_wino_kernel<false><<<(unsigned)ctas, warps * 32, smem, stream>>>(w, args);
+    kern<<<(unsigned)ctas, warps * 32, smem, stream>>>(w, args);
     return cudaGetLastError();
 }
 
