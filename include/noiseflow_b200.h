@@ -122,7 +122,10 @@ int nf_model_end_update(nf_model* m);
 int nf_model_set_launch(nf_model* m, int warps_per_cta, int num_ctas);
 /* Width 4 -- which kernel runs full-chain / range calls (batch-statistics probes always use the direct-form all-fp32 kernel):
  *   0 (default) = 4: the all-fp32 vertical-Winograd kernel (csrc/nf_wino.cu: both 3x3 convolutions of every coupling net as
- *      F(2,3) along the image rows; +10 % data -> latent, +3 % latent -> data; differs from the direct form by fp32 rounding only);
+ *      F(2,3) along the image rows; 12.6 vs 10.5 M patches/s data -> latent, 11.8 vs 9.4 M latent -> data on one B200; differs
+ *      from the direct form by fp32 rounding only).  It runs as one 16-warp CTA per SM, or as two 8-warp CTAs with half the
+ *      tensor memory each when it draws its own noise (nf_sample with eps == NULL: +10 %); the environment variable
+ *      NF_WINO_CTA_WARPS=8 / 16 forces either shape (an A/B switch, read once per process);
  *   5: the all-fp32 direct-form kernel (csrc/nf_kernels.cu) everywhere;
  *   2: the hybrid kernel (csrc/nf_hybrid.cu): conv-3 of every coupling net on the tensor cores (tcgen05.mma, fp16 hi/lo-split
  *      operands, fp32 accumulation in TMEM), everything else fp32 -- |dNLL| vs the fp32 kernels < 1e-6 nats/dim on the shipped

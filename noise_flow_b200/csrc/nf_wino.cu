@@ -10,7 +10,8 @@
 // neighbours read it through the row rings as before.  The packed FFMA2 pair runs over the TRANSFORM index -- (m0, m1) and
 // (m2, m3) of one output accumulate over the input channels one after the other -- so there are no (even, odd) partial sums
 // to close: y0 = m0 + (m1 + b) + m2 and y1 = (m1 + b) - m2 - m3 cost 5 adds per output and row pair.  Per row: 88 instead of
-// 124 FFMA2, 34 instead of 51 LDCU.128 (the transforms amortise badly over 4 channels); 12.3 instead of 10.4 M patches/s.
+// 124 FFMA2, 34 instead of 51 LDCU.128 (the transforms amortise badly over 4 channels); 12.6 instead of 10.5 M patches/s
+// data -> latent, 11.8 instead of 9.4 M latent -> data (two 8-warp CTAs per SM there, launch_chain_wino).
 //
 // Reference semantics: identical to nf_kernels.cu / nf_coupling.cuh (layers.py:117-130, 333-375, 452-498, 555-583,
 // 651-674; noise_flow_model.py:394-480); results differ from the direct form by fp32 rounding only.
