@@ -9,6 +9,7 @@
 #   sanitize         compute-sanitizer smoke (tools/gpu/sanitize_smoke.py)
 # Round 5 companions: tools/gpu/ab_chain.sh (A/B of the three width-4 chain kernels), sanitize_chain.sh (sanitizer over them),
 # final_evidence.sh (suite + default bench + ncu --set full of the shipped chain kernels + launch list in one call).
+# Round 6: ab_quick.sh (default chain kernel, both directions, 20 steps), ab_cta_warps.sh (one 16-warp CTA per SM vs two 8-warp CTAs).
 set -u
 mkdir -p gpurun_out
 task=${1:-suite}; shift || true
