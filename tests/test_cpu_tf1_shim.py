@@ -65,6 +65,20 @@ def test_conv2d_is_nhwc_cross_correlation_with_hwio_filter():
     assert np.abs(one - x @ w[0, 0]).max() < 1e-12
 
 
+def test_conv2d_against_scipy_correlate2d():
+    """A third, independent implementation: scipy.signal.correlate2d per (batch, in, out) plane -- mode 'same' with zero fill is
+    TF's SAME at stride 1 and an odd kernel, mode 'valid' is VALID (the reference's convs are 3x3 / 1x1 SAME, layers.py:452-498)."""
+    from scipy.signal import correlate2d
+    rng = np.random.RandomState(3)
+    x, w = rng.randn(2, 7, 5, 2), rng.randn(3, 3, 2, 3)
+    for padding, mode in (("SAME", "same"), ("VALID", "valid")):
+        got = _np(tf.conv2d(tf.constant(x), tf.constant(w), [1, 1, 1, 1], padding))
+        for b in range(2):
+            for k in range(3):
+                want = sum(correlate2d(x[b, :, :, q], w[:, :, q, k], mode=mode, boundary="fill", fillvalue=0.0) for q in range(2))
+                assert np.abs(got[b, :, :, k] - want).max() < 1e-12
+
+
 def test_moments_where_one_hot_pad_tile_split_gather():
     """tf.nn.moments: mean and POPULATION variance over the axes; tf.where(cond): int64 coordinates [k, rank] of the true
     elements; tf.one_hot: indices outside [0, depth) give all-zero rows; tf.pad / tf.tile / tf.split / tf.gather as
